@@ -1,0 +1,51 @@
+"""TEST INFRASTRUCTURE - not product code. Only tests/, tests/golden/make_golden.py,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg may import anything under oracle/.
+
+Sets up an interpreter so the UNMODIFIED reference modules under /root/reference import and run
+on CPU in this container: the two shims (oracle/shims: dgl, pytransform3d) go first on sys.path,
+then the reference's own directories in the order its scripts append them
+(test/metrics_from_model.py:12,17,23), cwd = <reference>/test because the reference resolves
+'../tm_panoptic.pickle' relative to cwd (parameters.py:70).
+
+The reference tree only exists in the build container; nothing on the GPU box may call this.
+"""
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get('B200POSE_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'skeleton_matching'))
+
+
+def activate(configuration='PANOPTIC', parameters_override=None):
+    """Make `import gat2, graph_generator, mlp, ...` resolve to the reference's files.
+
+    configuration: 'PANOPTIC' (as shipped) or 'ARPLAB'. The reference selects it by editing the
+    CONFIGURATION constant (parameters.py:47); here the file's text is executed in memory with that
+    one constant substituted, so the ARPLAB numbers are the reference's own (parameters.py:80-118).
+    parameters_override: optional callable(namedtuple) -> namedtuple for derived configurations
+    (e.g. ARP cut to 3 cameras) applied on top.
+    """
+    if not reference_available():
+        raise RuntimeError('reference tree not found at %s' % REFERENCE_ROOT)
+    for p in (os.path.join(REFERENCE_ROOT, ''), os.path.join(REFERENCE_ROOT, 'utils'),
+              os.path.join(REFERENCE_ROOT, 'skeleton_matching'), os.path.join(_HERE, 'shims')):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+    os.chdir(os.path.join(REFERENCE_ROOT, 'test'))
+    import types
+    src = open(os.path.join(REFERENCE_ROOT, 'parameters.py')).read()
+    marker = "CONFIGURATION = 'PANOPTIC'"
+    assert src.count(marker) == 1, 'reference parameters.py layout changed'
+    src = src.replace(marker, "CONFIGURATION = %r" % configuration)
+    mod = types.ModuleType('parameters')
+    mod.__file__ = os.path.join(REFERENCE_ROOT, 'parameters.py')
+    exec(compile(src, mod.__file__, 'exec'), mod.__dict__)
+    if parameters_override is not None:
+        mod.parameters = parameters_override(mod.parameters)
+    sys.modules['parameters'] = mod
+    return mod.parameters
