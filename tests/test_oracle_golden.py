@@ -1,0 +1,146 @@
+"""CPU: the oracle restatement (oracle/pose_oracle.py) against fixtures produced by the unmodified
+reference (tests/golden/make_golden.py). This is what pins the oracle."""
+import json
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import pose_oracle as O
+
+
+def _tabs(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    return cfg, npz, meta, O.CameraTables(cfg)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_camera_tables_bit_exact(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    for i, n in enumerate(cfg.used_sm_names):
+        assert np.array_equal(tabs.kinv32[n], npz['kinv32'][i])
+        assert np.array_equal(tabs.ti32[n], npz['ti32'][i])
+        assert np.array_equal(tabs.centre32[n], npz['centre32'][i])
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_seeded_weights_match_reference_constructors(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    W = helpers.weights_mod
+    gs = W.state_checksum(W.make_gat_state(cfg.n_features_sm, meta['gat_seed']))
+    for k, v in gs.items():
+        if k.startswith('layers.4.fc2'):
+            continue                      # calibrated after init, stored in the fixture
+        assert v == meta['gat_checksum'][k], k
+    ms = W.state_checksum(W.make_mlp_state(cfg.n_cameras * 18 * 14, 54, meta['mlp_seed']))
+    assert ms == meta['mlp_checksum']
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_graph_build_bit_exact(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    for tag in meta['cases']:
+        frame = meta['frames'][tag]
+        g = O.build_graph({c: frame[c] for c in frame if json.loads(frame[c][0])}, tabs)
+        if tag in meta['no_graph']:
+            assert g is None
+            continue
+        assert g['n_nodes'] == int(npz[tag + '/n_nodes'])
+        assert np.array_equal(g['src'], npz[tag + '/src'])
+        assert np.array_equal(g['dst'], npz[tag + '/dst'])
+        assert np.array_equal(g['indices'], npz[tag + '/indices'])
+        assert np.array_equal(g['nodes_camera'], npz[tag + '/nodes_camera'])
+        assert np.array_equal(g['rel_type'], npz[tag + '/rel_type'])
+        assert np.array_equal(np.array([g['skeleton_index'][h] for h in sorted(g['skeleton_index'])]),
+                              npz[tag + '/skeleton_index'])
+        assert g['feats'].dtype == np.float32
+        assert np.array_equal(g['feats'], npz[tag + '/feats']), 'features not bit-exact for %s' % tag
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_gat_scores(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    gat_w, _ = helpers.golden_weights(config)
+    gat_w = helpers.np_state(gat_w)
+    for tag in helpers.graph_cases(config):
+        scores, layers = O.gat_forward(gat_w, npz[tag + '/feats'], npz[tag + '/src'], npz[tag + '/dst'],
+                                       return_layers=True)
+        ref = npz[tag + '/scores']
+        idx = npz[tag + '/indices']
+        rel = np.abs(scores[idx] - ref[idx]) / np.maximum(np.abs(ref[idx]), 1e-30)
+        assert rel.max() < 1e-4, (tag, rel.max())
+        for l in range(5):
+            key = '%s/gat_l%d' % (tag, l)
+            if key in npz:
+                a, b = layers[l], npz[key]
+                assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), (tag, l)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_cluster_on_reference_scores(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    for tag in helpers.graph_cases(config):
+        frame = meta['frames'][tag]
+        g = O.build_graph({c: frame[c] for c in frame if json.loads(frame[c][0])}, tabs)
+        props = O.cluster(npz[tag + '/scores'], g['pairs'], g['nodes_camera'][:g['n_heads']], cfg.V_sm,
+                          g['n_heads'], 0.5, cfg.min_number_of_views)
+        assert np.array_equal(props, npz[tag + '/proposals']), tag
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_cluster_fuzz(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    graphs = {}
+    dup = 0
+    for i, tag in enumerate(meta['fuzz_tags']):
+        if tag not in graphs:
+            frame = meta['frames'][tag]
+            graphs[tag] = O.build_graph({c: frame[c] for c in frame if json.loads(frame[c][0])}, tabs)
+        g = graphs[tag]
+        props = O.cluster(npz['fuzz/%d/scores' % i], g['pairs'], g['nodes_camera'][:g['n_heads']], cfg.V_sm,
+                          g['n_heads'], 0.5, cfg.min_number_of_views)
+        assert np.array_equal(props, npz['fuzz/%d/proposals' % i]), (tag, i)
+    assert len(meta['fuzz_tags']) >= 60
+
+
+def test_intset_matches_cpython():
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        n = int(rng.integers(1, 200))
+        keys = [int(k) for k in rng.integers(0, 400, n)]
+        s, mine = set(), O.IntSet()
+        first = True
+        for k in keys:
+            if first:
+                s = {k}; first = False
+            else:
+                s.add(k)
+            mine.add(k)
+        assert list(s) == list(mine)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_encoder_triangulation_mlp(config):
+    cfg, npz, meta, tabs = _tabs(config)
+    _, mlp_w = helpers.golden_weights(config)
+    mlp_w = helpers.np_state(mlp_w)
+    checked = 0
+    for tag in helpers.graph_cases(config):
+        if tag + '/mlp_in' not in npz:
+            continue
+        frame = meta['frames'][tag]
+        g = O.build_graph({c: frame[c] for c in frame if json.loads(frame[c][0])}, tabs)
+        persons = helpers.person_dicts(g, npz[tag + '/proposals'], cfg)
+        enc = np.stack([O.encode_person(p, tabs) for p in persons])
+        ref = npz[tag + '/mlp_in']
+        assert enc.shape == ref.shape
+        assert np.abs(enc - ref).max() <= 1e-6, (tag, np.abs(enc - ref).max())
+        assert np.mean(enc == ref) > 0.99      # 1-ulp ray differences only (torch picks another matmul kernel for few joints)
+        out = O.mlp_forward(mlp_w, ref) * np.float32(10.)
+        assert np.abs(out - npz[tag + '/mlp_out'] * np.float32(10.)).max() < 5e-4      # metres: 0.5 mm
+        for p, person in enumerate(persons):
+            t, m = O.triangulate_baseline(person, tabs, cfg.median_axis)
+            assert np.array_equal(m, npz[tag + '/tri_mask'][p])
+            assert np.abs(t - npz[tag + '/tri'][p]).max() < 1e-9
+        checked += len(persons)
+    assert checked > 0
