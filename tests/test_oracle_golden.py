@@ -135,7 +135,11 @@ def test_encoder_triangulation_mlp(config):
         ref = npz[tag + '/mlp_in']
         assert enc.shape == ref.shape
         assert np.abs(enc - ref).max() <= 1e-6, (tag, np.abs(enc - ref).max())
-        assert np.mean(enc == ref) > 0.99      # 1-ulp ray differences only (torch picks another matmul kernel for few joints)
+        bad = np.argwhere(enc != ref)
+        # only 1-ulp differences in the ray slots (torch picks another tiny-matmul kernel when a
+        # skeleton has few joints); everything else is bit-equal
+        assert all(7 <= (i % 14) <= 9 for _, i in bad), tag
+        assert np.mean(enc == ref) > 0.95
         out = O.mlp_forward(mlp_w, ref) * np.float32(10.)
         assert np.abs(out - npz[tag + '/mlp_out'] * np.float32(10.)).max() < 5e-4      # metres: 0.5 mm
         for p, person in enumerate(persons):
