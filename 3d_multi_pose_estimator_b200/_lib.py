@@ -1,0 +1,66 @@
+"""ctypes binding of libb200pose.so (include/b200pose.h). The product path has no CPU fallback: if the
+library is missing, or a call fails, a Python exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200pose.so')
+
+EXPORTS = ['b200pose_last_error', 'b200pose_version', 'b200pose_device_cc', 'b200pose_build_graph',
+           'b200pose_node_features', 'b200pose_linear', 'b200pose_split_planes', 'b200pose_gat_aggregate',
+           'b200pose_cluster', 'b200pose_encode_persons', 'b200pose_triangulate', 'b200pose_gather_persons']
+
+
+class Cameras(C.Structure):
+    """b200pose_cameras (include/b200pose.h)."""
+    _fields_ = [('n_cameras', C.c_int32), ('v_sm', C.c_int32), ('v_pe', C.c_int32),
+                ('image_width', C.c_float), ('image_height', C.c_float),
+                ('sm_slot', C.c_void_p), ('pe_slot', C.c_void_p), ('kinv32', C.c_void_p),
+                ('t_cam2root32', C.c_void_p), ('k64', C.c_void_p), ('dist64', C.c_void_p), ('p64', C.c_void_p)]
+
+
+class B200PoseError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError('libb200pose.so not found at %s - build it with '
+                              '`python 3d_multi_pose_estimator_b200/build.py` (there is no CPU fallback)' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.b200pose_last_error.restype = C.c_char_p
+        i32, f32, f64, vp = C.c_int32, C.c_float, C.c_double, C.c_void_p
+        camp = C.POINTER(Cameras)
+        L.b200pose_build_graph.argtypes = [i32, vp, vp, vp, camp, vp, vp, vp, vp, vp, vp, vp]
+        L.b200pose_node_features.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp]
+        L.b200pose_linear.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, f32, vp, i32, vp, vp, i32, i32, vp]
+        L.b200pose_split_planes.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
+        L.b200pose_gat_aggregate.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32,
+                                             vp, vp, vp, i32, vp, vp]
+        L.b200pose_cluster.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, i32, i32, i32, vp, vp, vp]
+        L.b200pose_encode_persons.argtypes = [i32, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp, vp]
+        L.b200pose_triangulate.argtypes = [i32, vp, vp, vp, camp, i32, vp, vp, vp]
+        L.b200pose_gather_persons.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, camp, vp, vp, vp]
+        for name in EXPORTS:
+            if name != 'b200pose_last_error':
+                getattr(L, name).restype = C.c_int32
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = lib().b200pose_last_error()
+        raise B200PoseError('%s failed (%d): %s' % (what or 'b200pose call', rc, (msg or b'').decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,352 @@
+// Stage 2b: person proposals from edge-node scores, one warp per frame.
+//
+// Reference behaviour restated (utils/skeleton_matching_utils.py):
+//   :32-55   walk the edges in id order: heads enter the proposal graph when first seen as the
+//            destination of an edge leaving an edge-node; an edge-node whose score is > threshold
+//            (strict) becomes a Matching(nodes=list({h1,h2}))  -> order of the pair = CPython set order
+//   :60      stable sort by score, descending (ties keep edge-node order)
+//   :61-108  greedy camera-exclusive merge with per-head linked-camera lists and per-group camera
+//            lists; merging two groups relabels the absorbed one and FORGETS its cameras (:97-102)
+//   :117-130 nx.connected_components (BFS in node-insertion order), components smaller than
+//            min_number_of_views dropped, person[camera] = head for every head in the component's
+//            *set iteration order* (matters when a component holds two heads of one camera)
+//
+// Camera lists are only ever tested for membership, so they are 32-bit camera masks. The CPython
+// set layout (Objects/setobject.c: table of 8, LINEAR_PROBES 9, PERTURB_SHIFT 5, growth when
+// fill*5 >= mask*3 to the first power of two > 4*used) is emulated exactly; connected components
+// are labelled by a level-order BFS over the link list in insertion order, which is what
+// networkx 3.x _plain_bfs does.
+#include "common.cuh"
+
+namespace b200pose {
+
+__device__ __forceinline__ uint32_t ordered_bits(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// CPython set insert of small non-negative ints (hash(i) == i). Returns true if inserted.
+__device__ bool set_probe_insert(int* table, int mask, int key) {
+    unsigned perturb = (unsigned)key;
+    int i = key & mask;
+    while (true) {
+        if (table[i] < 0) { table[i] = key; return true; }
+        if (table[i] == key) return false;
+        if (i + 9 <= mask) {
+            for (int j = 1; j <= 9; ++j) {
+                if (table[i + j] < 0) { table[i + j] = key; return true; }
+                if (table[i + j] == key) return false;
+            }
+        }
+        perturb >>= 5;
+        i = (int)(((unsigned)i * 5u + 1u + perturb) & (unsigned)mask);
+    }
+}
+
+struct IntSet {
+    int* tab;      // current table
+    int* spare;    // scratch for growth
+    int mask;
+    int fill;
+    __device__ void init(int* a, int* b) {
+        tab = a; spare = b; mask = 7; fill = 0;
+        for (int i = 0; i < 8; ++i) tab[i] = -1;
+    }
+    __device__ void add(int key) {
+        if (!set_probe_insert(tab, mask, key)) return;
+        ++fill;
+        if (fill * 5 < mask * 3) return;
+        const int minused = fill * 4;
+        int newsize = 8;
+        while (newsize <= minused) newsize <<= 1;
+        for (int i = 0; i < newsize; ++i) spare[i] = -1;
+        for (int i = 0; i <= mask; ++i)
+            if (tab[i] >= 0) set_probe_insert(spare, newsize - 1, tab[i]);
+        int* t = tab; tab = spare; spare = t;
+        mask = newsize - 1;
+    }
+};
+
+__device__ __forceinline__ void pair_order(int h1, int h2, int& a, int& b) {
+    // list({h1, h2}) for a set built as set([h1]); add(h2): slot order in a table of 8
+    const int s1 = h1 & 7;
+    int i = h2 & 7;
+    unsigned perturb = (unsigned)h2;
+    while (i == s1) {
+        perturb >>= 5;
+        i = (int)(((unsigned)i * 5u + 1u + perturb) & 7u);
+    }
+    if (s1 < i) { a = h1; b = h2; } else { a = h2; b = h1; }
+}
+
+struct ClusterParams {
+    const int* head_off; const int* node_off; const int* pairs; const int* node_cam; const float* scores;
+    int v_sm; double threshold; int min_views;
+    int* person_heads; int* n_persons;
+    int max_heads, max_keys, table_cap;
+};
+
+__global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x;
+    const int h0 = p.head_off[b];
+    const int H = p.head_off[b + 1] - h0;
+    const int n0 = p.node_off[b];
+    const int M = p.node_off[b + 1] - n0 - H;
+    const int m0 = n0 - h0;
+    // ---- carve shared memory ----
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    int* link_a = reinterpret_cast<int*>(keys);                     // links alias the consumed front of keys
+    int* ip = reinterpret_cast<int*>(keys + p.max_keys);
+    int* cam = ip;              ip += p.max_heads;
+    int* group = ip;            ip += p.max_heads;
+    int* first_seen = ip;       ip += p.max_heads;
+    int* queue = ip;            ip += p.max_heads;
+    unsigned* linked = reinterpret_cast<unsigned*>(ip); ip += p.max_heads;
+    unsigned* cams_for = reinterpret_cast<unsigned*>(ip); ip += p.max_heads;
+    int* flag = ip;             ip += p.max_heads;
+    int* tab_a = ip;            ip += p.table_cap;
+    int* tab_b = ip;
+
+    if (H > p.max_heads || M > p.max_keys || H == 0) {              // outside the sized limits: no persons
+        if (lane == 0) p.n_persons[b] = 0;
+        return;
+    }
+    int Mpad = 1;
+    while (Mpad < M) Mpad <<= 1;
+
+    for (int h = lane; h < H; h += 32) {
+        cam[h] = p.node_cam[n0 + h];
+        group[h] = -1;
+        linked[h] = 1u << cam[h];
+        flag[h] = 0;
+    }
+    __syncwarp();
+
+    // ---- edge walk: first-seen order of the heads + matchings above the threshold (:32-55) ----
+    int n_seen = 0;
+    for (int k0 = 0; k0 < M; k0 += 32) {
+        const int k = k0 + lane;
+        int h1 = -1, h2 = -1;
+        unsigned long long key = 0ull;
+        if (k < M) {
+            h1 = p.pairs[2 * (m0 + k)];
+            h2 = p.pairs[2 * (m0 + k) + 1];
+            const float s = p.scores[n0 + H + k];
+            if ((double)s > p.threshold)
+                key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+        }
+        if (k < Mpad) keys[k] = key;
+        const int cnt = min(32, M - k0);
+        for (int t = 0; t < cnt; ++t) {
+            const int a = __shfl_sync(0xffffffffu, h1, t);
+            const int c = __shfl_sync(0xffffffffu, h2, t);
+            if (lane == 0) {
+                if (!flag[a]) { flag[a] = 1; first_seen[n_seen++] = a; }
+                if (!flag[c]) { flag[c] = 1; first_seen[n_seen++] = c; }
+            }
+        }
+    }
+    for (int k = M + lane; k < Mpad; k += 32) keys[k] = 0ull;
+    n_seen = __shfl_sync(0xffffffffu, n_seen, 0);
+    __syncwarp();
+
+    // ---- bitonic sort, descending: score desc, edge-node index asc (:60) ----
+    for (int size = 2; size <= Mpad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = lane; i < Mpad; i += 32) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const unsigned long long x = keys[i], y = keys[j];
+                    const bool desc = ((i & size) == 0);
+                    if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[j] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- greedy merge (:61-108); every lane runs the same scalar control flow ----
+    int n_links = 0, cur = 0;
+    for (int t = 0; t < M; ++t) {
+        const unsigned long long key = keys[t];
+        if (key == 0ull) break;
+        __syncwarp();
+        const int k = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+        const int h1 = p.pairs[2 * (m0 + k)], h2 = p.pairs[2 * (m0 + k) + 1];
+        int a, c;
+        pair_order(h1, h2, a, c);
+        const unsigned ca = 1u << cam[a], cc = 1u << cam[c];
+        if ((ca & linked[c]) || (cc & linked[a])) continue;                      // :67
+        const int ga = group[a], gc = group[c];
+        if (ga >= 0 && (cc & cams_for[ga])) continue;                            // :70-72
+        if (gc >= 0 && (ca & cams_for[gc])) continue;                            // :73-75
+        if (ga < 0 && gc < 0) {                                                  // :77-83
+            if (lane == 0) { group[a] = cur; group[c] = cur; cams_for[cur] = ca | cc; }
+            ++cur;
+        } else if (ga >= 0 && gc < 0) {                                          // :84-86
+            if (lane == 0) { group[c] = ga; cams_for[ga] |= cc; }
+        } else if (gc >= 0 && ga < 0) {                                          // :87-89
+            if (lane == 0) { group[a] = gc; cams_for[gc] |= ca; }
+        } else {                                                                 // :90-104
+            if (cams_for[gc] & cams_for[ga]) continue;
+            for (int h = lane; h < H; h += 32)
+                if (group[h] == gc) group[h] = ga;                               // absorbed cameras are forgotten
+        }
+        if (lane == 0) {                                                         // :106-108
+            link_a[2 * n_links] = a; link_a[2 * n_links + 1] = c;
+            linked[a] |= cc; linked[c] |= ca;
+        }
+        ++n_links;
+        __syncwarp();
+    }
+    __syncwarp();
+
+    // ---- connected components in first-seen order, BFS by levels (:117-130) ----
+    for (int h = lane; h < H; h += 32) flag[h] = 0;                              // reuse as "done"
+    __syncwarp();
+    int n_out = 0;
+    if (lane == 0) {
+        IntSet comp;
+        for (int f = 0; f < n_seen; ++f) {
+            const int v = first_seen[f];
+            if (flag[v]) continue;
+            comp.init(tab_a, tab_b);
+            comp.add(v);
+            flag[v] = 1;
+            int qb = 0, qe = 0, size = 1;
+            queue[qe++] = v;
+            while (qb < qe) {
+                const int x = queue[qb++];
+                for (int i = 0; i < n_links; ++i) {
+                    int w = -1;
+                    if (link_a[2 * i] == x) w = link_a[2 * i + 1];
+                    else if (link_a[2 * i + 1] == x) w = link_a[2 * i];
+                    if (w >= 0 && !flag[w]) { flag[w] = 1; comp.add(w); queue[qe++] = w; ++size; }
+                }
+            }
+            if (size < p.min_views) continue;
+            int* person = p.person_heads + (size_t)(h0 + n_out) * p.v_sm;
+            for (int s = 0; s < p.v_sm; ++s) person[s] = -1;
+            for (int i = 0; i <= comp.mask; ++i)
+                if (comp.tab[i] >= 0) person[cam[comp.tab[i]]] = comp.tab[i];
+            ++n_out;
+        }
+        p.n_persons[b] = n_out;
+    }
+}
+
+// flattens per-frame person slots into a dense person list with global skeleton ids per camera
+__global__ void gather_persons_kernel(int n_frames, const int* __restrict__ head_off, const int* __restrict__ person_heads,
+                                      const int* __restrict__ n_persons, const int* __restrict__ person_off,
+                                      const int* __restrict__ sm_slot, int v_sm, int n_cameras,
+                                      int* __restrict__ person_sk, int* __restrict__ person_frame)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_frames) return;
+    const int h0 = head_off[b];
+    const int np = n_persons[b];
+    const int o = person_off[b];
+    for (int q = 0; q < np; ++q) {
+        const int* ph = person_heads + (size_t)(h0 + q) * v_sm;
+        for (int c = 0; c < n_cameras; ++c) {
+            const int slot = sm_slot[c];
+            const int h = slot >= 0 ? ph[slot] : -1;
+            person_sk[(size_t)(o + q) * n_cameras + c] = h >= 0 ? h0 + h : -1;
+        }
+        person_frame[o + q] = b;
+    }
+}
+
+// single-CTA exclusive scan (n up to a few million): out[0..n] with out[n] = total
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restrict__ in, int n, int* __restrict__ out)
+{
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int beg = min(n, tid * per), end = min(n, beg + per);
+    int s = 0;
+    for (int i = beg; i < end; ++i) s += in[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int v = tid >= d ? part[tid - d] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int run = tid ? part[tid - 1] : 0;
+    for (int i = beg; i < end; ++i) { out[i] = run; run += in[i]; }
+    if (tid == 1023) out[n] = part[1023];
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+static int set_table_capacity(int max_heads) {
+    // largest CPython set table reached while inserting max_heads distinct keys
+    int mask = 7, fill = 0;
+    for (int i = 0; i < max_heads; ++i) {
+        ++fill;
+        if (fill * 5 >= mask * 3) {
+            int newsize = 8;
+            while (newsize <= fill * 4) newsize <<= 1;
+            mask = newsize - 1;
+        }
+    }
+    return mask + 1;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
+                                const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                                int32_t v_sm, double threshold, int32_t min_views,
+                                int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
+                                int32_t* person_heads, int32_t* n_persons, void* stream)
+{
+    B2_CHECK_ARG(head_off && node_off && pairs && node_cam && scores && person_heads && n_persons, "cluster: null pointer");
+    B2_CHECK_ARG(v_sm >= 1 && v_sm <= B200POSE_MAX_CAMERAS, "cluster: v_sm out of range");
+    if (n_frames == 0) return B200POSE_OK;
+    ClusterParams p;
+    p.head_off = head_off; p.node_off = node_off; p.pairs = pairs; p.node_cam = node_cam; p.scores = scores;
+    p.v_sm = v_sm; p.threshold = threshold; p.min_views = min_views; p.person_heads = person_heads; p.n_persons = n_persons;
+    p.max_heads = max_heads_per_frame < 1 ? 1 : max_heads_per_frame;
+    int keys = 1;
+    while (keys < max_enodes_per_frame) keys <<= 1;
+    p.max_keys = keys;
+    p.table_cap = set_table_capacity(p.max_heads);
+    const size_t smem = (size_t)p.max_keys * 8 + (size_t)p.max_heads * 7 * 4 + (size_t)p.table_cap * 2 * 4;
+    if (smem > 200 * 1024) {
+        set_error("cluster: frame too large for the shared-memory plan (%zu bytes: %d heads, %d edge-nodes)", smem,
+                  max_heads_per_frame, max_enodes_per_frame);
+        return B200POSE_E_UNSUPPORTED;
+    }
+    B2_CHECK_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_kernel<<<n_frames, 32, smem, (cudaStream_t)stream>>>(p);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_gather_persons(int32_t n_frames, const int32_t* head_off, const int32_t* person_heads,
+                                       const int32_t* n_persons, int32_t* person_off, int32_t scan,
+                                       const int32_t* sk_cam, int32_t v_sm, const b200pose_cameras* cams,
+                                       int32_t* person_sk, int32_t* person_frame, void* stream)
+{
+    (void)sk_cam;
+    B2_CHECK_ARG(head_off && person_heads && n_persons && person_off && cams, "gather_persons: null pointer");
+    if (n_frames == 0) return B200POSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (scan) {
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(n_persons, n_frames, person_off);
+        B2_CHECK_LAUNCH();
+    }
+    if (person_sk) {
+        B2_CHECK_ARG(person_frame, "gather_persons: person_frame missing");
+        gather_persons_kernel<<<ceil_div(n_frames, 128), 128, 0, st>>>(n_frames, head_off, person_heads, n_persons, person_off,
+                                                                       cams->sm_slot, v_sm, cams->n_cameras, person_sk, person_frame);
+        B2_CHECK_LAUNCH();
+    }
+    return B200POSE_OK;
+}

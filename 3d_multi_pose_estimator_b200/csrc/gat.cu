@@ -1,0 +1,214 @@
+// Stage 2a: fused attention logits + edge-softmax + neighbour aggregation of one GAT layer.
+//
+// Reference behaviour restated (skeleton_matching/gat2.py):
+//   :59-61,78-81  a[e]   = LeakyReLU_alpha(a1[src] + a2[dst])                 (apply_edges UDF)
+//   :63,83-88     s[e]   = exp(a[e] - max_dst) / sum_dst exp(...)             (dgl.ops.edge_softmax, by dst)
+//   :66           out[v] = sum_{u->v} s[e] * ft2[u]                           (update_all u_mul_e / sum)
+//   :141-142      next input = LeakyReLU_0.01(out.flatten(1));  :144-145 sigmoid on the last layer
+//
+// One CTA per frame, one warp per destination node walking its CSR row. The z rows of the frame's
+// heads (and, for layer 0, the single shared edge-node row) are staged in shared memory: every
+// edge-node destination reads two head rows and every head reads its own, so 2/3 of the row gathers
+// of a frame are served on chip; edge-node rows come through the read-only path. Lanes own 4 (or 2)
+// consecutive feature columns, so every row read is a coalesced, vectorised sweep.
+#include "common.cuh"
+
+namespace b200pose {
+
+struct AggParams {
+    int n_frames, n_heads_total;
+    const int* head_off; const int* node_off; const int* row_ptr; const int* col;
+    const float* z; int ldz; int heads, dim, layer0;
+    float alpha, act_slope;
+    float* raw_f32; __nv_bfloat16* act_hi; __nv_bfloat16* act_lo; int ld_planes;
+    int stage_rows;     // rows of smem available per CTA
+};
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC> __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+    else v[0] = *p;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) gat_aggregate_kernel(AggParams p)
+{
+    extern __shared__ __align__(16) float zs[];
+    const int b = blockIdx.x;
+    const int n0 = p.node_off[b];
+    const int Nb = p.node_off[b + 1] - n0;
+    const int h0 = p.head_off[b];
+    const int Hb = p.head_off[b + 1] - h0;
+    const int HD = p.heads * p.dim;
+    const int ldz = p.ldz;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    // ---- stage the frame's head rows (layer 0: + the shared edge-node row) ------------------------
+    int n_stage;
+    bool all_staged = false;
+    if (p.layer0) {
+        all_staged = (Hb + 1 <= p.stage_rows);
+        n_stage = all_staged ? Hb + 1 : 0;
+    } else {
+        n_stage = min(Hb, p.stage_rows);
+    }
+    {
+        const int vec_per_row = ldz / 4;                       // ldz is a multiple of 4
+        const int total = n_stage * vec_per_row;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int r = i / vec_per_row, c = i - r * vec_per_row;
+            size_t grow;
+            if (p.layer0) grow = (r < Hb) ? (size_t)(h0 + r) : (size_t)p.n_heads_total;
+            else grow = (size_t)(n0 + r);
+            reinterpret_cast<float4*>(zs)[i] = __ldg(reinterpret_cast<const float4*>(p.z + grow * ldz) + c);
+        }
+    }
+    __syncthreads();
+
+    auto row_of = [&](int u_global) -> const float* {         // z row of a source node
+        const int l = u_global - n0;
+        if (p.layer0) {
+            if (all_staged) return zs + (size_t)(l < Hb ? l : Hb) * ldz;
+            return p.z + (size_t)(l < Hb ? h0 + l : p.n_heads_total) * ldz;
+        }
+        if (l < n_stage) return zs + (size_t)l * ldz;
+        return p.z + (size_t)u_global * ldz;
+    };
+
+    const int n_vec = HD / VEC;
+    const int n_vec_pad = p.act_hi ? p.ld_planes / VEC : n_vec;
+    for (int v = warp; v < Nb; v += nwarps) {
+        const int gv = n0 + v;
+        const int beg = p.row_ptr[gv], end = p.row_ptr[gv + 1];
+        const float* rowv = row_of(gv);
+        for (int cv = lane; cv < n_vec_pad; cv += 32) {
+            float acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+            if (cv < n_vec) {
+                const int h = (cv * VEC) / p.dim;
+                const float a2v = rowv[HD + p.heads + h];
+                float m = -INFINITY;
+                for (int e = beg; e < end; ++e) {
+                    const float* ru = row_of(__ldg(p.col + e));
+                    m = fmaxf(m, leaky(ru[HD + h] + a2v, p.alpha));
+                }
+                float den = 0.f;
+                for (int e = beg; e < end; ++e) {
+                    const float* ru = row_of(__ldg(p.col + e));
+                    den += expf(leaky(ru[HD + h] + a2v, p.alpha) - m);
+                }
+                for (int e = beg; e < end; ++e) {
+                    const float* ru = row_of(__ldg(p.col + e));
+                    const float w = expf(leaky(ru[HD + h] + a2v, p.alpha) - m) / den;
+                    float f[VEC];
+                    load_vec<VEC>(ru + cv * VEC, f);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+                }
+                if (p.raw_f32) {
+                    float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = acc[i];
+                }
+            }
+            if (p.act_hi) {
+                __nv_bfloat16 hi[VEC], lo[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) split_bf16(leaky(acc[i], p.act_slope), hi[i], lo[i]);
+                __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + cv * VEC;
+                __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + cv * VEC;
+                if constexpr (VEC == 4) {
+                    *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+                    *reinterpret_cast<uint2*>(ol) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+                } else if constexpr (VEC == 2) {
+                    *reinterpret_cast<uint32_t*>(oh) = pack_bf16x2(hi[0], hi[1]);
+                    *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(lo[0], lo[1]);
+                } else {
+                    oh[0] = hi[0]; ol[0] = lo[0];
+                }
+            }
+        }
+    }
+}
+
+// last layer (heads*dim == 1): one thread per destination node, sigmoid fused (gat2.py:143-145)
+__global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
+    int n_nodes_total, const int* __restrict__ row_ptr, const int* __restrict__ col,
+    const float* __restrict__ z, int ldz, float alpha, float* __restrict__ raw_f32, float* __restrict__ scores)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes_total) return;
+    const int beg = row_ptr[v], end = row_ptr[v + 1];
+    const float a2v = z[(size_t)v * ldz + 2];
+    float m = -INFINITY;
+    for (int e = beg; e < end; ++e) m = fmaxf(m, leaky(z[(size_t)col[e] * ldz + 1] + a2v, alpha));
+    float den = 0.f;
+    for (int e = beg; e < end; ++e) den += expf(leaky(z[(size_t)col[e] * ldz + 1] + a2v, alpha) - m);
+    float acc = 0.f;
+    for (int e = beg; e < end; ++e) {
+        const float* ru = z + (size_t)col[e] * ldz;
+        acc = fmaf(expf(leaky(ru[1] + a2v, alpha) - m) / den, ru[0], acc);
+    }
+    if (raw_f32) raw_f32[v] = acc;
+    if (scores) scores[v] = 1.0f / (1.0f + expf(-acc));
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                                      const int32_t* head_off, const int32_t* node_off,
+                                      const int32_t* row_ptr, const int32_t* col,
+                                      const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
+                                      int32_t max_heads_per_frame, float alpha, float act_slope,
+                                      float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                                      float* scores, void* stream)
+{
+    B2_CHECK_ARG(head_off && node_off && row_ptr && col && z, "gat_aggregate: null input");
+    B2_CHECK_ARG(heads >= 1 && dim >= 1 && ldz >= heads * dim + 2 * heads, "gat_aggregate: ldz too small");
+    B2_CHECK_ARG((act_hi == nullptr) == (act_lo == nullptr), "gat_aggregate: planes go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_frames == 0 || n_nodes_total == 0) return B200POSE_OK;
+    const int HD = heads * dim;
+    if (HD == 1) {
+        B2_CHECK_ARG(!layer0 && !act_hi, "gat_aggregate: scalar layer cannot be layer 0 / produce planes");
+        gat_aggregate_scalar_kernel<<<ceil_div(n_nodes_total, 256), 256, 0, st>>>(n_nodes_total, row_ptr, col, z, ldz,
+                                                                                  alpha, raw_f32, scores);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    }
+    B2_CHECK_ARG(scores == nullptr, "gat_aggregate: scores need heads*dim == 1");
+    B2_CHECK_ARG(ldz % 4 == 0, "gat_aggregate: ldz must be a multiple of 4");
+    if (act_hi) B2_CHECK_ARG(ld_planes % 64 == 0 && ld_planes >= HD, "gat_aggregate: bad ld_planes");
+    AggParams p;
+    p.n_frames = n_frames; p.n_heads_total = n_heads_total; p.head_off = head_off; p.node_off = node_off;
+    p.row_ptr = row_ptr; p.col = col; p.z = z; p.ldz = ldz; p.heads = heads; p.dim = dim; p.layer0 = layer0;
+    p.alpha = alpha; p.act_slope = act_slope; p.raw_f32 = raw_f32;
+    p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
+    p.ld_planes = ld_planes;
+    // shared-memory staging: the frame's head rows (+1 shared edge-node row for layer 0), capped at
+    // 96 KB per CTA so at least two CTAs stay resident per SM
+    const size_t row_bytes = (size_t)ldz * sizeof(float);
+    int stage_rows = (int)((96 * 1024) / row_bytes);
+    const int want = max_heads_per_frame > 0 ? max_heads_per_frame + (layer0 ? 1 : 0) : 0;
+    if (stage_rows > want) stage_rows = want;
+    p.stage_rows = stage_rows;
+    const size_t smem = (size_t)stage_rows * row_bytes;
+    const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
+    auto launch = [&](auto kern) -> int {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_frames, 256, smem, st>>>(p);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    };
+    if (vec == 4) return launch(gat_aggregate_kernel<4>);
+    if (vec == 2) return launch(gat_aggregate_kernel<2>);
+    return launch(gat_aggregate_kernel<1>);
+}

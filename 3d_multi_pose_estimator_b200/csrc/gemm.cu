@@ -1,0 +1,481 @@
+// Dense projections out = act(A * W^T + bias) on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA, 3-term split-bf16 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM).
+//
+// Replaces the nn.Linear calls of the reference's GAT (skeleton_matching/gat2.py:53,55, with the
+// attention dots of :57-58 folded in as extra output columns) and pose MLP (utils/mlp.py:8-28).
+// Plain bf16 or TF32 inputs miss the 1e-4 score / 0.5 mm joint tolerances, so every
+// fp32 operand is carried as two bf16 planes and each k-block issues three UMMA groups.
+//
+// Kernel anatomy (one 128 x bn output tile per CTA, 192 threads):
+//   warp 0 / lane 0 : TMA producer  - cp.async.bulk.tensor 2D, 128B-swizzled K-major tiles, mbarrier tx
+//   warp 1          : TMEM allocator; lane 0 issues tcgen05.mma (M=128, N=bn, K=16) and commits
+//   warps 2..5      : epilogue - tcgen05.ld 32 lanes x 32 columns, bias + LeakyReLU + scale, writes fp32
+//                     and/or re-split bf16 planes for the next GEMM
+// bn (multiple of 16, <= 256) and the pipeline depth are runtime values: the TMA box, the instruction
+// descriptor and the TMEM allocation all take them, so one kernel serves every layer shape.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace b200pose {
+
+constexpr int kBM = 128;          // UMMA M (cta_group::1)
+constexpr int kBK = 64;           // one 128-byte swizzle atom of bf16 along K
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: turn a pipeline bug into an error, not a hang
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on the mbarrier when all prior MMAs are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+//   start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B (8 rows x 128 B) | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct GemmParams {
+    int M, N, num_kb, bn, stages;
+    const float* bias; float slope, out_scale;
+    float* out_f32; int ld_out;
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ld_planes;
+    // manual-fill (debug) variant only
+    const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo; int lda;
+    const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo; int ldw;
+};
+
+// 3 UMMA groups of one 64-wide k-block: hi*hi, lo*hi, hi*lo
+__device__ __forceinline__ void issue_kblock(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                             uint32_t tmem_d, uint32_t idesc, bool first)
+{
+#pragma unroll
+    for (int k4 = 0; k4 < kBK / kUmmaK; ++k4) {
+        const uint32_t off = k4 * kUmmaK * 2;                     // bytes inside the swizzle atom
+        const uint64_t dah = make_sw128_desc(a_hi + off), dal = make_sw128_desc(a_lo + off);
+        const uint64_t dbh = make_sw128_desc(b_hi + off), dbl = make_sw128_desc(b_lo + off);
+        umma_bf16(tmem_d, dah, dbh, idesc, (first && k4 == 0) ? 0u : 1u);
+        umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+        umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+    }
+}
+
+// epilogue of one tile: thread = one accumulator row; 32 columns per TMEM load
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int m0, int n0, int quarter, int lane)
+{
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        const int ncols = min(32, p.bn - c0);                     // bn is a multiple of 16
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int col = n0 + c0 + i;
+            float x = 0.f;
+            if (i < ncols && col < p.N) {
+                x = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + col) : 0.f);
+                x = leaky(x, p.slope) * p.out_scale;
+            }
+            v[i] = x;
+        }
+        if (!row_ok) continue;
+        if (p.out_f32) {
+            float* o = p.out_f32 + (size_t)row * p.ld_out + n0 + c0;
+            const bool vec_ok = ((p.ld_out & 3) == 0) && (((n0 + c0) & 3) == 0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                if (i >= ncols) break;
+                if (vec_ok && n0 + c0 + i + 3 < p.N) {
+                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (n0 + c0 + i + u < p.N) o[i + u] = v[i + u];
+                }
+            }
+        }
+        if (p.out_hi) {
+            uint32_t* oh = reinterpret_cast<uint32_t*>(p.out_hi + (size_t)row * p.ld_planes + n0 + c0);
+            uint32_t* ol = reinterpret_cast<uint32_t*>(p.out_lo + (size_t)row * p.ld_planes + n0 + c0);
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                if (i < ncols && n0 + c0 + i + 7 < p.ld_planes) {           // ld_planes % 64 == 0, n0+c0 % 16 == 0
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(v[i + 2 * u], h0, l0);
+                        split_bf16(v[i + 2 * u + 1], h1, l1);
+                        h[u] = pack_bf16x2(h0, h1);
+                        l[u] = pack_bf16x2(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(oh + i / 2) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(ol + i / 2) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
+    uint32_t c = 32;
+    while ((int)c < bn) c <<= 1;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// product kernel: TMA-fed, multi-stage
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc_kernel(
+    const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const GemmParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * kBM;
+    const uint32_t a_bytes = kBM * kBK * 2;                       // 16 KB per plane
+    const uint32_t b_bytes = (uint32_t)p.bn * kBK * 2;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t tiles = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t ncols = tmem_cols_for(p.bn);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, stage_bytes);
+                const uint32_t base = tiles + (uint32_t)s * stage_bytes;
+                tma_load_2d(base, &map_a_hi, kb * kBK, m0, full);
+                tma_load_2d(base + a_bytes, &map_a_lo, kb * kBK, m0, full);
+                tma_load_2d(base + 2 * a_bytes, &map_w_hi, kb * kBK, n0, full);
+                tma_load_2d(base + 2 * a_bytes + b_bytes, &map_w_lo, kb * kBK, n0, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.bn);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                tcgen05_fence_after();
+                const uint32_t base = tiles + (uint32_t)s * stage_bytes;
+                issue_kblock(base, base + a_bytes, base + 2 * a_bytes, base + 2 * a_bytes + b_bytes, tmem_base, idesc, kb == 0);
+                umma_commit(smem_u32(&bar_empty[s]));             // frees the smem slot when these MMAs retire
+            }
+            umma_commit(smem_u32(&bar_acc));                      // accumulator complete
+        }
+    } else {
+        mbar_wait(smem_u32(&bar_acc), 0);
+        tcgen05_fence_after();
+        epilogue_tile(p, tmem_base, m0, n0, warp & 3, lane);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug kernel: identical MMA + epilogue, but the tiles are written by ordinary stores (no TMA,
+// single stage). Used by the kernel self-test to separate tensor-map bugs from descriptor bugs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fill_tile_sw128(uint8_t* tile, const __nv_bfloat16* g, int ld, int row0, int rows_valid,
+                                                int rows_tile, int k0, int tid, int nthreads)
+{
+    // 16-byte chunks: chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4)
+    for (int i = tid; i < rows_tile * 8; i += nthreads) {
+        const int r = i >> 3, c = i & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid) v = *reinterpret_cast<const uint4*>(g + (size_t)(row0 + r) * ld + k0 + c * 8);
+        *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc_manual_kernel(const GemmParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * p.bn, m0 = blockIdx.y * kBM;
+    const uint32_t a_bytes = kBM * kBK * 2, b_bytes = (uint32_t)p.bn * kBK * 2;
+    uint8_t* tiles_g = smem_dyn + (((smem_u32(smem_dyn) + 1023u) & ~1023u) - smem_u32(smem_dyn));
+    const uint32_t tiles = smem_u32(tiles_g);
+    const uint32_t ncols = tmem_cols_for(p.bn);
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar_mma), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t idesc = make_idesc(p.bn);
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+        fill_tile_sw128(tiles_g, p.a_hi, p.lda, m0, max(0, min(kBM, p.M - m0)), kBM, kb * kBK, threadIdx.x, kGemmThreads);
+        fill_tile_sw128(tiles_g + a_bytes, p.a_lo, p.lda, m0, max(0, min(kBM, p.M - m0)), kBM, kb * kBK, threadIdx.x, kGemmThreads);
+        fill_tile_sw128(tiles_g + 2 * a_bytes, p.w_hi, p.ldw, n0, max(0, min(p.bn, p.N - n0)), p.bn, kb * kBK, threadIdx.x, kGemmThreads);
+        fill_tile_sw128(tiles_g + 2 * a_bytes + b_bytes, p.w_lo, p.ldw, n0, max(0, min(p.bn, p.N - n0)), p.bn, kb * kBK, threadIdx.x, kGemmThreads);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> async proxy (UMMA)
+        __syncthreads();
+        if (warp == 1 && lane == 0) {
+            tcgen05_fence_after();
+            issue_kblock(tiles, tiles + a_bytes, tiles + 2 * a_bytes, tiles + 2 * a_bytes + b_bytes, tmem_base, idesc, kb == 0);
+            umma_commit(smem_u32(&bar_mma));
+        }
+        mbar_wait(smem_u32(&bar_mma), (uint32_t)kb & 1u);                    // tiles may be overwritten now
+        __syncthreads();
+    }
+    tcgen05_fence_after();
+    if (warp >= 2) epilogue_tile(p, tmem_base, m0, n0, warp & 3, lane);
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SIMT kernel on the same planes (kernel self-test reference; not on the product path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_split_simt_kernel(const GemmParams p, int K)
+{
+    __shared__ float As[64][17];
+    __shared__ float Ws[64][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i >> 4, c = i & 15;
+            float a = 0.f, w = 0.f;
+            if (m0 + r < p.M && k0 + c < K) {
+                const size_t o = (size_t)(m0 + r) * p.lda + k0 + c;
+                a = __bfloat162float(p.a_hi[o]) + __bfloat162float(p.a_lo[o]);
+            }
+            if (n0 + r < p.N && k0 + c < K) {
+                const size_t o = (size_t)(n0 + r) * p.ldw + k0 + c;
+                w = __bfloat162float(p.w_hi[o]) + __bfloat162float(p.w_lo[o]);
+            }
+            As[r][c] = a; Ws[r][c] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[ty * 4 + i][k]; w[i] = Ws[tx * 4 + i][k]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty * 4 + i;
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            float x = 0.f;
+            if (col < p.N) x = leaky(acc[i][j] + (p.bias ? p.bias[col] : 0.f), p.slope) * p.out_scale;
+            if (p.out_f32 && col < p.N) p.out_f32[(size_t)row * p.ld_out + col] = x;
+            if (p.out_hi && col < p.ld_planes) {
+                __nv_bfloat16 h, l;
+                split_bf16(x, h, l);
+                p.out_hi[(size_t)row * p.ld_planes + col] = h;
+                p.out_lo[(size_t)row * p.ld_planes + col] = l;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int rows, int kpad, int ld, int box_rows) {
+    auto fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200POSE_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d kpad %d ld %d box %d)", (int)r, rows, kpad, ld, box_rows); return B200POSE_E_CUDA; }
+    return B200POSE_OK;
+}
+
+static int choose_bn(int n) {
+    const int tiles = ceil_div(n, 256);
+    int bn = ceil_div(ceil_div(n, tiles), 16) * 16;
+    if (bn < 16) bn = 16;
+    return bn;
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                               const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                               const float* bias, int32_t m, int32_t n, int32_t k, float slope, float out_scale,
+                               float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                               int32_t impl, void* stream)
+{
+    B2_CHECK_ARG(a_hi && a_lo && w_hi && w_lo, "linear: null operand");
+    B2_CHECK_ARG(m >= 0 && n >= 1 && k >= 1, "linear: bad shape m=%d n=%d k=%d", m, n, k);
+    const int kpad = ceil_div(k, kBK) * kBK;
+    B2_CHECK_ARG(lda % 64 == 0 && ldw % 64 == 0 && lda >= kpad && ldw >= kpad, "linear: lda/ldw must be multiples of 64 >= round_up(k,64)");
+    B2_CHECK_ARG(out_f32 || out_hi, "linear: no output requested");
+    B2_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "linear: planes go together");
+    if (out_f32) B2_CHECK_ARG(ld_out >= n, "linear: ld_out < n");
+    if (out_hi) B2_CHECK_ARG(ld_planes % 64 == 0 && ld_planes >= n, "linear: ld_planes must be a multiple of 64 >= n");
+    B2_CHECK_ARG(((uintptr_t)a_hi % 16 == 0) && ((uintptr_t)a_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) && ((uintptr_t)w_lo % 16 == 0),
+                 "linear: operands must be 16-byte aligned");
+    if (m == 0) return B200POSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmParams p;
+    p.M = m; p.N = n; p.num_kb = kpad / kBK; p.bias = bias; p.slope = slope; p.out_scale = out_scale;
+    p.out_f32 = out_f32; p.ld_out = ld_out;
+    p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi); p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); p.ld_planes = ld_planes;
+    p.a_hi = reinterpret_cast<const __nv_bfloat16*>(a_hi); p.a_lo = reinterpret_cast<const __nv_bfloat16*>(a_lo); p.lda = lda;
+    p.w_hi = reinterpret_cast<const __nv_bfloat16*>(w_hi); p.w_lo = reinterpret_cast<const __nv_bfloat16*>(w_lo); p.ldw = ldw;
+    p.bn = choose_bn(n);
+    p.stages = 1;
+    if (impl == 1) {
+        const int cols = (out_hi && ld_planes > n) ? ld_planes : n;     // also zero the K padding of the planes
+        dim3 grid(ceil_div(cols, 64), ceil_div(m, 64));
+        gemm_split_simt_kernel<<<grid, 256, 0, st>>>(p, k);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    }
+    const size_t stage_bytes = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)p.bn * kBK * 2;
+    dim3 grid(ceil_div(n, p.bn), ceil_div(m, kBM));
+    if (impl == 2) {
+        const size_t smem = stage_bytes + 1024;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc_manual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_split_tc_manual_kernel<<<grid, kGemmThreads, smem, st>>>(p);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    }
+    B2_CHECK_ARG(impl == 0, "linear: impl must be 0 (tcgen05), 1 (simt self-test) or 2 (tcgen05 manual-fill self-test)");
+    int stages = (int)((220 * 1024 - 1024) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > p.num_kb) stages = p.num_kb;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, a_hi, m, kpad, lda, kBM))) return rc;
+    if ((rc = make_map(&ma_lo, a_lo, m, kpad, lda, kBM))) return rc;
+    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, p.bn))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, p.bn))) return rc;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_split_tc_kernel<<<grid, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}

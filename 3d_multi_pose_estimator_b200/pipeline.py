@@ -1,0 +1,358 @@
+"""Batched inference pipeline: packed frames -> person proposals -> 3D joints, all on one B200.
+
+This is the frame-batched replacement of the per-frame glue the reference repeats in its drivers
+(test/metrics_from_model.py:178-300): graph build -> GAT -> clustering -> MLP-input encoding -> MLP.
+Host code is PyTorch (allocation, streams); every computation is a kernel of libb200pose.so called
+through the C ABI (include/b200pose.h). There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Cameras, check, ptr
+from .config import CameraConfig, N_JOINTS
+from .pack import PackedBatch
+from .weights import GAT_ALPHA, GAT_ACT_SLOPE, MLP_SLOPE, gat_layer_dims
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Planes:
+    """An fp32 matrix stored as hi/lo bf16 planes [rows, ld] (ld multiple of 64), zero padded."""
+
+    def __init__(self, rows: int, cols: int, device):
+        self.rows, self.cols = rows, cols
+        self.ld = round_up(max(cols, 1), 64)
+        self.hi = torch.zeros((max(rows, 1), self.ld), dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros((max(rows, 1), self.ld), dtype=torch.bfloat16, device=device)
+
+    @staticmethod
+    def from_f32(x: torch.Tensor, stream) -> "Planes":
+        x = x.contiguous().float()
+        p = Planes(x.shape[0], x.shape[1], x.device)
+        check(_lib.lib().b200pose_split_planes(ptr(x), x.shape[0], x.shape[1], x.shape[1], ptr(p.hi), ptr(p.lo), p.ld, stream),
+              'split_planes')
+        return p
+
+    def to_f32(self) -> torch.Tensor:
+        return (self.hi.float() + self.lo.float())[: self.rows, : self.cols]
+
+
+class DeviceCameras:
+    """Camera tables uploaded once per configuration (b200pose_cameras)."""
+
+    def __init__(self, cfg: CameraConfig, device):
+        self.cfg = cfg
+        Cn = cfg.n_cameras
+        sm_slot = np.full(Cn, -1, np.int32)
+        pe_slot = np.full(Cn, -1, np.int32)
+        for s, c in enumerate(cfg.used_sm):
+            sm_slot[c] = s
+        for s, c in enumerate(cfg.used_pe):
+            pe_slot[c] = s
+        kinv = np.stack([cfg.Kinv32(c) for c in range(Cn)]).astype(np.float32)
+        tinv = np.stack([cfg.T_cam2root32(c) for c in range(Cn)]).astype(np.float32)
+        k64 = np.stack([[cfg.K64_from32(c)[0, 0], cfg.K64_from32(c)[1, 1], cfg.K64_from32(c)[0, 2], cfg.K64_from32(c)[1, 2]]
+                        for c in range(Cn)]).astype(np.float64)
+        dist = np.stack([cfg.dist64(c) for c in range(Cn)]).astype(np.float64)
+        p64 = np.stack([cfg.P64(c) for c in range(Cn)]).astype(np.float64)
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.t = dict(sm_slot=up(sm_slot), pe_slot=up(pe_slot), kinv=up(kinv), tinv=up(tinv), k64=up(k64), dist=up(dist), p64=up(p64))
+        self.struct = Cameras(Cn, cfg.V_sm, cfg.V_pe, float(cfg.image_width), float(cfg.image_height),
+                              self.t['sm_slot'].data_ptr(), self.t['pe_slot'].data_ptr(), self.t['kinv'].data_ptr(),
+                              self.t['tinv'].data_ptr(), self.t['k64'].data_ptr(), self.t['dist'].data_ptr(),
+                              self.t['p64'].data_ptr())
+
+    @property
+    def ref(self):
+        return C.byref(self.struct)
+
+
+@dataclasses.dataclass
+class DeviceBatch:
+    """A PackedBatch resident in HBM."""
+    n_frames: int
+    n_heads: int
+    n_nodes: int
+    max_heads: int
+    max_enodes: int
+    sk_xy: torch.Tensor
+    sk_vp: torch.Tensor
+    sk_mask: torch.Tensor
+    sk_cam: torch.Tensor
+    head_off: torch.Tensor
+    node_off: torch.Tensor
+
+    @property
+    def n_enodes(self):
+        return self.n_nodes - self.n_heads
+
+    @property
+    def n_edges(self):
+        return self.n_heads + 5 * self.n_enodes
+
+
+class HostBatch:
+    """Pinned host copy of a PackedBatch, so host->device copies are asynchronous DMA."""
+
+    def __init__(self, pb: PackedBatch):
+        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory() if torch.cuda.is_available() \
+            else torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+        self.pb = pb
+        self.sk_xy = pin(pb.sk_xy, torch.float64)
+        self.sk_vp = pin(pb.sk_vp, torch.float32)
+        self.sk_mask = pin(pb.sk_mask.view(np.int32), torch.int32)
+        self.sk_cam = pin(pb.sk_cam, torch.int32)
+        self.head_off = pin(pb.head_off, torch.int32)
+        self.node_off = pin(pb.node_off, torch.int32)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.sk_xy, self.sk_vp, self.sk_mask, self.sk_cam, self.head_off, self.node_off))
+
+    def to_device(self, device) -> DeviceBatch:
+        pb = self.pb
+        cp = lambda t: t.to(device, non_blocking=True)
+        return DeviceBatch(pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes,
+                           cp(self.sk_xy), cp(self.sk_vp), cp(self.sk_mask), cp(self.sk_cam), cp(self.head_off), cp(self.node_off))
+
+
+class GraphArrays:
+    """Output of stage 1a (b200pose_build_graph)."""
+
+    def __init__(self, db: DeviceBatch, device, with_coo=True):
+        i32 = dict(dtype=torch.int32, device=device)
+        E = db.n_edges
+        self.src = torch.empty(max(E, 1), **i32) if with_coo else None
+        self.dst = torch.empty(max(E, 1), **i32) if with_coo else None
+        self.row_ptr = torch.empty(db.n_nodes + 1, **i32)
+        self.col = torch.empty(max(E, 1), **i32)
+        self.pairs = torch.empty((max(db.n_enodes, 1), 2), **i32)
+        self.node_cam = torch.empty(max(db.n_nodes, 1), **i32)
+
+
+class PosePipeline:
+    """Weights + camera tables resident on one GPU; `infer()` runs a whole batch of frames.
+
+    gat_state / mlp_state: state dicts with the reference's key names
+    (GAT `layers.{l}.{attn_l,attn_r,fc1.*,fc2.*}`, MLP `layers.{1,3,..,17}.{weight,bias}`).
+    """
+
+    def __init__(self, cfg: CameraConfig, gat_state: Dict[str, torch.Tensor], mlp_state: Optional[Dict[str, torch.Tensor]],
+                 device=None, gemm_impl: int = 0, threshold: float = 0.5):
+        if not torch.cuda.is_available():
+            raise RuntimeError('PosePipeline needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.cfg = cfg
+        self.L = _lib.lib()
+        self.gemm_impl = gemm_impl
+        self.threshold = float(threshold)
+        self.launches = 0
+        with torch.cuda.device(self.device):
+            self.cams = DeviceCameras(cfg, self.device)
+            self._prepare_gat(gat_state)
+            self.mlp = self._prepare_mlp(mlp_state) if mlp_state is not None else None
+            torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ weights
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _prepare_gat(self, st):
+        """Split every projection into planes; fold the attention vectors into fc2 as 2*heads extra output
+        rows: a1[n,h] = sum_d ft2[n,h,d]*attn_l[h,d] = h2[n,:] . (sum_d attn_l[h,d]*W2[hD+d,:]) + bias term
+        (gat2.py:55-58), so one GEMM yields [ft2 | a1 | a2]."""
+        self.gat = []
+        n_layers = len([k for k in st if k.endswith('fc1.weight')])
+        for l in range(n_layers):
+            g = lambda k: st['layers.%d.%s' % (l, k)].detach().to('cpu', torch.float64)
+            W1, W2 = g('fc1.weight'), g('fc2.weight')
+            din = W1.shape[1]
+            has_bias = ('layers.%d.fc1.bias' % l) in st
+            b1 = g('fc1.bias') if has_bias else torch.zeros(W1.shape[0], dtype=torch.float64)
+            b2 = g('fc2.bias') if has_bias else torch.zeros(W2.shape[0], dtype=torch.float64)
+            al, ar = g('attn_l')[:, :, 0], g('attn_r')[:, :, 0]          # [H, D]
+            H, D = al.shape
+            W2h = W2.reshape(H, D, din)
+            Wl = torch.einsum('hd,hdk->hk', al, W2h)
+            Wr = torch.einsum('hd,hdk->hk', ar, W2h)
+            bl = (al * b2.reshape(H, D)).sum(1)
+            br = (ar * b2.reshape(H, D)).sum(1)
+            W2e = torch.cat([W2, Wl, Wr], 0).float().to(self.device)
+            b2e = torch.cat([b2, bl, br], 0).float().to(self.device)
+            s = self._stream()
+            self.gat.append(dict(
+                din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4),
+                w1=Planes.from_f32(W1.float().to(self.device), s), b1=b1.float().to(self.device),
+                w2=Planes.from_f32(W2e, s), b2=b2e))
+
+    def _prepare_mlp(self, st):
+        layers = []
+        s = self._stream()
+        for l in range(1, 18, 2):
+            W = st['layers.%d.weight' % l].detach().float().to(self.device)
+            b = st['layers.%d.bias' % l].detach().float().to(self.device)
+            layers.append(dict(w=Planes.from_f32(W, s), b=b, n=W.shape[0], k=W.shape[1]))
+        return layers
+
+    # ------------------------------------------------------------------ kernels
+    def linear(self, a: Planes, m: int, w: Planes, bias, n: int, k: int, slope: float, scale: float = 1.0,
+               out_f32: Optional[torch.Tensor] = None, out_planes: Optional[Planes] = None):
+        self.launches += 1
+        check(self.L.b200pose_linear(ptr(a.hi), ptr(a.lo), a.ld, ptr(w.hi), ptr(w.lo), w.ld, ptr(bias), m, n, k,
+                                     slope, scale, ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                                     ptr(out_planes.hi) if out_planes else None, ptr(out_planes.lo) if out_planes else None,
+                                     out_planes.ld if out_planes else 0, self.gemm_impl, self._stream()), 'linear')
+
+    def build_graph(self, db: DeviceBatch, with_coo=True) -> GraphArrays:
+        g = GraphArrays(db, self.device, with_coo)
+        self.launches += 1
+        check(self.L.b200pose_build_graph(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(db.sk_cam), self.cams.ref,
+                                          ptr(g.src), ptr(g.dst), ptr(g.row_ptr), ptr(g.col), ptr(g.pairs), ptr(g.node_cam),
+                                          self._stream()), 'build_graph')
+        return g
+
+    def node_features_f32(self, db: DeviceBatch) -> torch.Tensor:
+        F = self.cfg.n_features_sm
+        out = torch.empty((max(db.n_nodes, 1), F), dtype=torch.float32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_node_features(db.n_frames, db.n_heads, db.n_nodes, ptr(db.head_off), ptr(db.node_off),
+                                            ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), ptr(db.sk_cam), self.cams.ref,
+                                            ptr(out), F, None, None, 0, self._stream()), 'node_features')
+        return out[: db.n_nodes]
+
+    def head_feature_planes(self, db: DeviceBatch) -> Planes:
+        p = Planes(db.n_heads + 1, self.cfg.n_features_sm, self.device)
+        self.launches += 1
+        check(self.L.b200pose_node_features(db.n_frames, db.n_heads, db.n_nodes, ptr(db.head_off), ptr(db.node_off),
+                                            ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), ptr(db.sk_cam), self.cams.ref,
+                                            None, 0, ptr(p.hi), ptr(p.lo), p.ld, self._stream()), 'node_features')
+        return p
+
+    def aggregate(self, db: DeviceBatch, g: GraphArrays, z: torch.Tensor, layer: dict, layer0: bool,
+                  raw: Optional[torch.Tensor], act: Optional[Planes], scores: Optional[torch.Tensor]):
+        self.launches += 1
+        check(self.L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
+                                            ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
+                                            1 if layer0 else 0, db.max_heads, GAT_ALPHA, GAT_ACT_SLOPE, ptr(raw),
+                                            ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
+                                            ptr(scores), self._stream()), 'gat_aggregate')
+
+    # ------------------------------------------------------------------ stages
+    def gat_forward(self, db: DeviceBatch, g: GraphArrays, x0: Optional[Planes] = None, dense_rows: bool = False,
+                    keep_layers: bool = False):
+        """GAT2.forward over the whole batch. By default layer 0 runs on the S+1 compact rows (every head
+        plus the one shared edge-node row). With dense_rows=True, x0 holds one row per node (the drop-in
+        GAT2.forward path, where the caller hands in an arbitrary feature matrix)."""
+        N, S = db.n_nodes, db.n_heads
+        raws = []
+        if x0 is None:
+            x0 = self.head_feature_planes(db)
+        x, rows = x0, (N if dense_rows else S + 1)
+        scores = torch.empty(max(N, 1), dtype=torch.float32, device=self.device)
+        for l, lay in enumerate(self.gat):
+            last = l == len(self.gat) - 1
+            h = Planes(rows, lay['din'], self.device)
+            self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], GAT_ALPHA, out_planes=h)
+            z = torch.empty((max(rows, 1), lay['ldz']), dtype=torch.float32, device=self.device)
+            self.linear(h, rows, lay['w2'], lay['b2'], lay['n2'], lay['din'], 1.0, out_f32=z)
+            raw = torch.empty((max(N, 1), lay['hd']), dtype=torch.float32, device=self.device) if keep_layers else None
+            act = None if last else Planes(N, lay['hd'], self.device)
+            self.aggregate(db, g, z, lay, layer0=(l == 0 and not dense_rows), raw=raw, act=act, scores=scores if last else None)
+            if keep_layers:
+                raws.append(raw[:N])
+            x, rows = act, N
+        return (scores[:N], raws) if keep_layers else scores[:N]
+
+    def cluster(self, db: DeviceBatch, g: GraphArrays, scores: torch.Tensor):
+        V = self.cfg.V_sm
+        person_heads = torch.empty((max(db.n_heads, 1), V), dtype=torch.int32, device=self.device)
+        n_persons = torch.empty(max(db.n_frames, 1), dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_cluster(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(g.pairs), ptr(g.node_cam), ptr(scores),
+                                      V, self.threshold, self.cfg.min_number_of_views, db.max_heads, db.max_enodes,
+                                      ptr(person_heads), ptr(n_persons), self._stream()), 'cluster')
+        return person_heads, n_persons[: db.n_frames]
+
+    def gather_persons(self, db: DeviceBatch, person_heads, n_persons):
+        """Dense person list. One 4-byte device->host read (the person count sizes the MLP launch)."""
+        person_off = torch.empty(db.n_frames + 1, dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(person_heads), ptr(n_persons), ptr(person_off), 1,
+                                             ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref, None, None, self._stream()), 'scan')
+        P = int(person_off[db.n_frames].item())
+        Cn = self.cfg.n_cameras
+        person_sk = torch.empty((max(P, 1), Cn), dtype=torch.int32, device=self.device)
+        person_frame = torch.empty(max(P, 1), dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(person_heads), ptr(n_persons), ptr(person_off), 0,
+                                             ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref, ptr(person_sk), ptr(person_frame),
+                                             self._stream()), 'gather_persons')
+        return P, person_off, person_sk[:P], person_frame[:P]
+
+    def encode_persons(self, db: DeviceBatch, P: int, person_sk, want_f32=False):
+        x = Planes(P, self.cfg.mlp_in, self.device)
+        valid = torch.empty(max(P, 1), dtype=torch.uint8, device=self.device)
+        xf = torch.zeros((max(P, 1), self.cfg.mlp_in), dtype=torch.float32, device=self.device) if want_f32 else None
+        self.launches += 1
+        check(self.L.b200pose_encode_persons(P, ptr(person_sk), ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), self.cams.ref,
+                                             ptr(xf), self.cfg.mlp_in if want_f32 else 0, ptr(x.hi), ptr(x.lo), x.ld, ptr(valid),
+                                             self._stream()), 'encode_persons')
+        return x, valid[:P], (xf[:P] if want_f32 else None)
+
+    def triangulate(self, db: DeviceBatch, P: int, person_sk):
+        xyz = torch.empty((max(P, 1), N_JOINTS, 3), dtype=torch.float64, device=self.device)
+        mask = torch.empty((max(P, 1), N_JOINTS), dtype=torch.uint8, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_triangulate(P, ptr(person_sk), ptr(db.sk_xy), ptr(db.sk_mask), self.cams.ref, self.cfg.median_axis,
+                                          ptr(xyz), ptr(mask), self._stream()), 'triangulate')
+        return xyz[:P], mask[:P]
+
+    def mlp_forward(self, x: Planes, P: int, scale: float = 10.0) -> torch.Tensor:
+        """PoseEstimatorMLP.forward (utils/mlp.py:8-31); `scale` is the x10 the callers apply
+        (metrics_from_model.py:282), fused into the last epilogue."""
+        out = torch.empty((max(P, 1), self.mlp[-1]['n']), dtype=torch.float32, device=self.device)
+        for i, lay in enumerate(self.mlp):
+            last = i == len(self.mlp) - 1
+            if last:
+                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out)
+            else:
+                y = Planes(P, lay['n'], self.device)
+                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], MLP_SLOPE, out_planes=y)
+                x = y
+        return out[:P]
+
+    # ------------------------------------------------------------------ whole path
+    def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):
+        """graph build -> GAT -> clustering -> encoder -> MLP for every frame of the batch."""
+        g = self.build_graph(db, with_coo=with_coo)
+        scores = self.gat_forward(db, g)
+        person_heads, n_persons = self.cluster(db, g, scores)
+        P, person_off, person_sk, person_frame = self.gather_persons(db, person_heads, n_persons)
+        res = dict(graph=g, scores=scores, person_heads=person_heads, n_persons=n_persons, person_off=person_off,
+                   person_sk=person_sk, person_frame=person_frame, n_persons_total=P)
+        if self.mlp is not None:
+            x, valid, _ = self.encode_persons(db, P, person_sk)
+            res['valid'] = valid
+            res['joints'] = self.mlp_forward(x, P) if P > 0 else torch.zeros((0, 54), device=self.device)
+        if want_triangulation:
+            res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, person_sk)
+        return res
+
+    def infer_host(self, hb: HostBatch, **kw):
+        """The public end-to-end call: pinned host buffers in, host results out."""
+        db = hb.to_device(self.device)
+        res = self.infer(db, **kw)
+        out = dict(n_persons=res['n_persons'].cpu(), person_off=res['person_off'].cpu(),
+                   person_sk=res['person_sk'].cpu(), n_persons_total=res['n_persons_total'])
+        if 'joints' in res:
+            out['joints'] = res['joints'].cpu()
+            out['valid'] = res['valid'].cpu()
+        return out

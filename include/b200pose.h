@@ -1,0 +1,192 @@
+/*
+ * b200pose.h - C ABI of libb200pose.so: the B200 (sm_100a) kernels of the per-frame inference hot
+ * path of gnns4hri/3D_multi_pose_estimator.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller allocates all
+ *     outputs (the Python host layer does so through torch); no ownership is transferred;
+ *   - every entry point enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; it is re-entrant per stream and keeps no global mutable state;
+ *   - return value: 0 = ok, negative = error (B200POSE_E_*); b200pose_last_error() returns a
+ *     thread-local message. Nothing aborts the process: the reference's callers wrap the model call
+ *     in `try/except: continue` (test/metrics_from_model.py:200-213) and the Python layer raises.
+ *   - "planes": an fp32 matrix X stored as two bf16 matrices hi = bf16(X), lo = bf16(X - hi) with a
+ *     common leading dimension (multiple of 64 elements). All tensor-core GEMMs consume and produce
+ *     planes and compute hi*hi + lo*hi + hi*lo with fp32 accumulation (3-term split-bf16).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef B200POSE_H
+#define B200POSE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200POSE_OK             0
+#define B200POSE_E_INVALID     -1   /* bad argument (shape, alignment, null pointer) */
+#define B200POSE_E_CUDA        -2   /* a CUDA runtime / driver call failed */
+#define B200POSE_E_UNSUPPORTED -3   /* configuration outside the compiled limits */
+
+#define B200POSE_N_JOINTS        18  /* COCO-18, parameters.py:8 */
+#define B200POSE_MAX_CAMERAS     32  /* camera sets are 32-bit masks in the clustering kernel */
+
+const char* b200pose_last_error(void);
+int b200pose_version(void);
+/* compute capability of the current device as major*10+minor (100 on B200); <0 on error */
+int b200pose_device_cc(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Camera tables (replaces the module-import globals of skeleton_matching/graph_generator.py:32-52
+ * and utils/pose_estimator_dataset_from_json.py:28-47). C = number of cameras (parameters.camera_names
+ * order). The struct itself lives on the HOST (it is read when a call is made); its array members are
+ * DEVICE pointers to small tables uploaded once per configuration.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_cameras;                 /* C */
+    int32_t v_sm;                      /* len(used_cameras_skeleton_matching) */
+    int32_t v_pe;                      /* len(used_cameras) */
+    float   image_width, image_height;
+    const int32_t* sm_slot;            /* [C] camera -> index in used_cameras_skeleton_matching or -1 */
+    const int32_t* pe_slot;            /* [C] camera -> index in used_cameras or -1 */
+    const float*   kinv32;             /* [C,3,3] torch.inverse(K_fp32)          (graph_generator.py:50) */
+    const float*   t_cam2root32;       /* [C,4,4] fp32(inv(T_root->cam))         (graph_generator.py:45) */
+    const double*  k64;                /* [C,4]   fx,fy,cx,cy of fp64(K_fp32)    (dataset.py:43) */
+    const double*  dist64;             /* [C,5]   k1,k2,p1,p2,k3                 (dataset.py:45) */
+    const double*  p64;                /* [C,3,4] T_root->cam[0:3,:]             (dataset.py:47) */
+} b200pose_cameras;
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed skeleton batch (replaces the JSON strings the reference re-parses per frame,
+ * graph_generator.py:587-588). S skeletons ("heads") of B frames, in head order: frame-dict camera
+ * order, then skeleton order, skeletons without joints dropped (graph_generator.py:583-601).
+ *   sk_xy   [S,18,2] fp64  pixel x,y exactly as the JSON carried them
+ *   sk_vp   [S,18,2] fp32  valid, prob
+ *   sk_mask [S]      u32   bit j set <=> joint key j present in the skeleton dict
+ *   sk_cam  [S]      i32   camera index (parameters.camera_names order)
+ *   head_off[B+1]    i32   first head of each frame
+ *   node_off[B+1]    i32   first graph node of each frame  (N_b = H_b + M_b)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Stage 1a. CSR/COO graph of every frame: MergedMultipleHumansDataset.process_test +
+ * add_edge_node_to_graph (graph_generator.py:813-876, 627-656) without DGL.
+ * Outputs (E_b = H_b + 5*M_b edges per frame, edge_off[b] = head_off[b] + 5*(node_off[b]-head_off[b])):
+ *   src,dst  [E_tot] i32 frame-local node ids in the reference's edge-id order
+ *   row_ptr  [N_tot+1] i32, col [E_tot] i32: CSR by destination, GLOBAL node ids, in-edges of a node
+ *            in ascending reference edge id
+ *   pairs    [M_tot,2] i32 frame-local (head1, head2) of every edge-node, edge-node order
+ *   node_cam [N_tot] i32 index into used_cameras_skeleton_matching, -1 for edge-nodes ('' in the reference)
+ * Any output pointer may be null to skip it. */
+int b200pose_build_graph(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
+                         const int32_t* sk_cam, const b200pose_cameras* cams_host,
+                         int32_t* src, int32_t* dst, int32_t* row_ptr, int32_t* col,
+                         int32_t* pairs, int32_t* node_cam, void* stream);
+
+/* Stage 1b. Node features of alternative '3' (HumanGraphFromView.initializeWithAlternative3,
+ * graph_generator.py:444-508), bit-exact fp32.
+ *   feats_f32 != null : dense [N_tot, ld_f32] rows for every node (edge-nodes: one-hot column 1) - what
+ *                       the reference stores in g.ndata['h'];
+ *   head_hi/lo != null: planes [S+1, ld_planes] holding the S head rows plus ONE edge-node row (row S);
+ *                       all edge-node rows are identical, so layer 0 of the GAT only projects S+1 rows. */
+int b200pose_node_features(int32_t n_frames, int32_t n_heads_total, int32_t n_nodes_total, const int32_t* head_off,
+                           const int32_t* node_off, const double* sk_xy, const float* sk_vp,
+                           const uint32_t* sk_mask, const int32_t* sk_cam,
+                           const b200pose_cameras* cams_host,
+                           float* feats_f32, int32_t ld_f32,
+                           uint16_t* head_hi, uint16_t* head_lo, int32_t ld_planes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense projections (nn.Linear of gat2.py:53,55 and utils/mlp.py:8-28):
+ *   out = act(A[M,K] * W[N,K]^T + bias[N]),  act(x) = x >= 0 ? x : slope*x   (slope = 1 -> identity)
+ * A, W as planes (K-major, lda/ldw multiples of 64, K zero-padded up to a multiple of 64).
+ * Outputs (either or both): out_f32 [M, ld_out] and/or planes out_hi/out_lo [M, ld_planes]. Plane
+ * padding columns (>= N) are only ever written as zero; the caller zero-initialises plane buffers once
+ * so the padding can be consumed as K padding by the next GEMM.
+ * out_scale multiplies the result after the activation (x10 of metrics_from_model.py:282).
+ * impl: 0 = tcgen05 + TMA tensor-core kernel (the product path); 1 = fp32 SIMT kernel and 2 = tcgen05
+ * kernel with tiles filled by ordinary stores - both exist only for the kernel self-test.
+ * ------------------------------------------------------------------------------------------- */
+int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                    const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                    const float* bias, int32_t m, int32_t n, int32_t k, float slope, float out_scale,
+                    float* out_f32, int32_t ld_out,
+                    uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                    int32_t impl, void* stream);
+
+/* fp32 [rows, ld_in] -> planes [rows, ld_planes] (used once per weight matrix at load time, and by tests) */
+int b200pose_split_planes(const float* x, int32_t rows, int32_t cols, int32_t ld_in,
+                          uint16_t* hi, uint16_t* lo, int32_t ld_planes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2a. Fused attention logits + edge-softmax + neighbour aggregation of one GAT layer:
+ * GraphAttention2.forward lines gat2.py:59-68 (apply_edges edge_attention :78-81, edge_softmax
+ * :83-88, update_all(u_mul_e, sum) :66), one warp per destination node over the CSR.
+ *   z [rows, ldz] fp32: per source row [ ft2 (heads*dim) | a1 (heads) | a2 (heads) ] as produced by
+ *     b200pose_linear with the attention vectors folded into the projection;
+ *   layer0 != 0: z holds S+1 compact rows (heads + the shared edge-node row, see node_features);
+ *   max_heads_per_frame sizes the shared-memory staging of a frame's head rows (0 = no staging);
+ *   out[v,h,:] = sum_u softmax_u(LeakyReLU_alpha(a1[u,h] + a2[v,h])) * ft2[u,h,:]
+ * Outputs (any may be null): raw_f32 [N_tot, heads*dim] (the layer output, gat2.py:68),
+ *   planes act_hi/lo [N_tot, ld_planes] = LeakyReLU_{act_slope}(out) (GAT2.forward :141-142),
+ *   scores [N_tot] = sigmoid(out[:,0]) (final_activation, :144-145; requires heads*dim == 1). */
+int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                           const int32_t* head_off, const int32_t* node_off,
+                           const int32_t* row_ptr, const int32_t* col,
+                           const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
+                           int32_t max_heads_per_frame, float alpha, float act_slope,
+                           float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                           float* scores, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2b. Person proposals: get_person_proposal_from_network_output
+ * (utils/skeleton_matching_utils.py:12-132) - threshold, score-ordered greedy camera-exclusive merge,
+ * connected components - one warp per frame, bit-exact including the CPython-set iteration order the
+ * reference's result depends on.
+ *   scores [N_tot] fp32 (only edge-node entries are read), pairs/node_cam from b200pose_build_graph;
+ *   threshold is compared as the reference does (python float(fp32 score) > threshold, strict);
+ *   max_heads_per_frame / max_enodes_per_frame size the per-frame shared-memory plan
+ * Outputs: person_heads [S_tot, v_sm] i32: rows head_off[b] .. head_off[b]+n_persons[b]-1 hold the persons
+ *   of frame b in the reference's output order, frame-local head id per camera or -1 (None);
+ *   n_persons [B] i32. */
+int b200pose_cluster(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
+                     const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                     int32_t v_sm, double threshold, int32_t min_views,
+                     int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
+                     int32_t* person_heads, int32_t* n_persons, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3a. MLP-input encoder: PoseEstimatorDataset.__init__ dict branch + get_3D_from_triangulation
+ * (utils/pose_estimator_dataset_from_json.py:237-289, 63-101): fp64 undistortion (cv2.undistortPoints,
+ * 5 iterations), back-projected rays, pairwise fp64 DLT (cv2.triangulatePoints) averaged over pairs.
+ *   person_sk [P, C] i32: GLOBAL skeleton index (into sk_*) of the person in each camera, -1 = absent
+ * Outputs: x_f32 [P, ld_f32] (may be null) and/or planes x_hi/x_lo [P, ld_planes]; row length 252*v_pe;
+ *   valid [P] u8 = 1 iff sum|x| > 1 (the reference only keeps such rows, dataset.py:287). */
+int b200pose_encode_persons(int32_t n_persons, const int32_t* person_sk,
+                            const double* sk_xy, const float* sk_vp, const uint32_t* sk_mask,
+                            const b200pose_cameras* cams_host,
+                            float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
+                            uint8_t* valid, void* stream);
+
+/* Stage 3b. Triangulation baseline: triangulate() (utils/pose_estimator_utils.py:52-75) fed as
+ * test/metrics_from_triangulation.py:237-249 does (all present joints, camera order = camera index):
+ * pairwise DLT, upper median on coordinate `median_axis`, keep pairs within 0.05 of it, mean.
+ * Outputs: xyz [P,18,3] fp64, mask [P,18] u8 (joint seen by >= 2 cameras). */
+int b200pose_triangulate(int32_t n_persons, const int32_t* person_sk,
+                         const double* sk_xy, const uint32_t* sk_mask,
+                         const b200pose_cameras* cams_host, int32_t median_axis,
+                         double* xyz, uint8_t* mask, void* stream);
+
+/* Helper for stage 2b -> 3a: flattens person_heads/n_persons into a dense person list.
+ *   person_off [B+1] i32 (exclusive scan of n_persons, computed by the caller or by this call when
+ *   scan != 0), person_sk [P_tot, C] i32 global skeleton ids, person_frame [P_tot] i32. */
+int b200pose_gather_persons(int32_t n_frames, const int32_t* head_off, const int32_t* person_heads,
+                            const int32_t* n_persons, int32_t* person_off, int32_t scan,
+                            const int32_t* sk_cam, int32_t v_sm, const b200pose_cameras* cams_host,
+                            int32_t* person_sk, int32_t* person_frame, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200POSE_H */

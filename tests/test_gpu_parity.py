@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference goldens and the oracle.
+
+Tiers (BASELINE.json north_star): graph build / features / clustering / person assignment bit-exact;
+edge scores <= 1e-4 relative; 3D joints <= 0.5 mm.
+"""
+import importlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import pose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+pipeline_mod = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+pack_mod = importlib.import_module('3d_multi_pose_estimator_b200.pack')
+
+SCORE_RTOL = 1e-4
+JOINT_TOL_M = 0.5e-3
+
+_pipes = {}
+
+
+def get_pipe(config, gemm_impl=None):
+    import os
+    if gemm_impl is None:      # B200POSE_GEMM_IMPL=1 runs the suite on the SIMT self-test GEMM (kernel bring-up only)
+        gemm_impl = int(os.environ.get('B200POSE_GEMM_IMPL', '0'))
+    key = (config, gemm_impl)
+    if key not in _pipes:
+        cfg, npz, meta = helpers.load_golden(config)
+        gat, mlp = helpers.golden_weights(config)
+        _pipes[key] = pipeline_mod.PosePipeline(cfg, gat, mlp, device='cuda:0', gemm_impl=gemm_impl)
+    return _pipes[key]
+
+
+def golden_batch(config, tags=None):
+    cfg, npz, meta = helpers.load_golden(config)
+    tags = tags or helpers.graph_cases(config)
+    frames = []
+    for t in tags:
+        f = meta['frames'][t]
+        frames.append({c: f[c] for c in f if json.loads(f[c][0])})      # metrics_from_model.py:182-191
+    pb = pack_mod.pack_frames(frames, cfg)
+    return tags, pb, pipeline_mod.HostBatch(pb).to_device('cuda:0')
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_graph_and_features_bit_exact(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    g = pipe.build_graph(db, with_coo=True)
+    feats = pipe.node_features_f32(db).cpu().numpy()
+    src, dst = g.src.cpu().numpy(), g.dst.cpu().numpy()
+    row_ptr, col = g.row_ptr.cpu().numpy(), g.col.cpu().numpy()
+    node_cam, pairs = g.node_cam.cpu().numpy(), g.pairs.cpu().numpy()
+    for b, tag in enumerate(tags):
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        h0, h1 = pb.head_off[b], pb.head_off[b + 1]
+        H, M = h1 - h0, (n1 - n0) - (h1 - h0)
+        e0 = h0 + 5 * (n0 - h0)
+        E = H + 5 * M
+        assert n1 - n0 == int(npz[tag + '/n_nodes'])
+        assert np.array_equal(src[e0:e0 + E], npz[tag + '/src']), tag
+        assert np.array_equal(dst[e0:e0 + E], npz[tag + '/dst']), tag
+        assert np.array_equal(node_cam[n0:n1], npz[tag + '/nodes_camera']), tag
+        assert np.array_equal(feats[n0:n1], npz[tag + '/feats']), 'features not bit-exact: ' + tag
+        # CSR by destination == the COO grouped by dst in edge-id order
+        rs, rd = npz[tag + '/src'], npz[tag + '/dst']
+        for v in range(n1 - n0):
+            want = rs[rd == v] + n0
+            got = col[row_ptr[n0 + v]:row_ptr[n0 + v + 1]]
+            assert np.array_equal(got, want), (tag, v)
+        m0 = n0 - h0
+        k = np.arange(M)
+        assert np.array_equal(pairs[m0:m0 + M, 0], rs[H + 5 * k]), tag
+        assert np.array_equal(pairs[m0:m0 + M, 1], rs[H + 5 * k + 2]), tag
+    assert row_ptr[pb.n_nodes] == pb.n_edges
+
+
+@pytest.mark.parametrize('impl', [1, 2, 0])
+def test_linear_kernels(impl):
+    """out = act(A W^T + b): SIMT self-test kernel (1), tcgen05 with manual tile fill (2), product TMA kernel (0)
+    against a float64 reference of the same split operands."""
+    pipe = get_pipe('panoptic')
+    L = pipe.L
+    torch.manual_seed(5)
+    shapes = [(128, 64, 64), (200, 48, 150), (77, 902, 902), (300, 420, 400), (1000, 3, 150), (260, 336, 400),
+              (129, 160, 320), (500, 3072, 1260), (64, 54, 1024)]
+    for (m, n, k) in shapes:
+        A = torch.randn(m, k, device='cuda') * 0.7
+        W = torch.randn(n, k, device='cuda') / k ** 0.5
+        b = torch.randn(n, device='cuda')
+        s = pipe._stream()
+        Ap, Wp = pipeline_mod.Planes.from_f32(A, s), pipeline_mod.Planes.from_f32(W, s)
+        out = torch.full((m, n), float('nan'), device='cuda')
+        outp = pipeline_mod.Planes(m, n, 'cuda')
+        pipeline_mod.check(L.b200pose_linear(pipeline_mod.ptr(Ap.hi), pipeline_mod.ptr(Ap.lo), Ap.ld, pipeline_mod.ptr(Wp.hi),
+                                             pipeline_mod.ptr(Wp.lo), Wp.ld, pipeline_mod.ptr(b), m, n, k, 0.15, 2.0,
+                                             pipeline_mod.ptr(out), n, pipeline_mod.ptr(outp.hi), pipeline_mod.ptr(outp.lo), outp.ld,
+                                             impl, s), 'linear')
+        torch.cuda.synchronize()
+        ref = Ap.to_f32().double() @ Wp.to_f32().double().T + b.double()
+        ref = torch.where(ref >= 0, ref, ref * 0.15) * 2.0
+        err = (out.double() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        assert err <= 2e-5 * max(scale, 1.0), ('impl %d shape %s: max err %g (scale %g)' % (impl, (m, n, k), err, scale))
+        errp = (outp.to_f32().double() - ref).abs().max().item()
+        assert errp <= 3e-5 * max(scale, 1.0), ('planes impl %d shape %s: %g' % (impl, (m, n, k), errp))
+        assert float(outp.hi[:, n:].float().abs().max() if outp.ld > n else 0.0) == 0.0
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_gat_scores_vs_reference(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    g = pipe.build_graph(db, with_coo=False)
+    scores, raws = pipe.gat_forward(db, g, keep_layers=True)
+    scores = scores.cpu().numpy()
+    worst = 0.0
+    for b, tag in enumerate(tags):
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        idx = npz[tag + '/indices']
+        ref = npz[tag + '/scores'][idx]
+        got = scores[n0:n1][idx]
+        rel = np.abs(got - ref) / np.abs(ref)
+        worst = max(worst, rel.max())
+        assert rel.max() <= SCORE_RTOL, (tag, rel.max())
+        for l in range(5):
+            key = '%s/gat_l%d' % (tag, l)
+            if key in npz:
+                a = raws[l][n0:n1].cpu().numpy().reshape(npz[key].shape)
+                assert np.abs(a - npz[key]).max() <= 1e-4 * max(1.0, np.abs(npz[key]).max()), (tag, l)
+    print('worst relative score error', config, worst)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_gat_dense_rows_path(config):
+    """GAT2.forward as the drop-in calls it: an explicit N x F feature matrix."""
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    g = pipe.build_graph(db, with_coo=False)
+    feats = pipe.node_features_f32(db)
+    x0 = pipeline_mod.Planes.from_f32(feats, pipe._stream())
+    scores = pipe.gat_forward(db, g, x0=x0, dense_rows=True).cpu().numpy()
+    for b, tag in enumerate(tags):
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        ref = npz[tag + '/scores']
+        rel = np.abs(scores[n0:n1] - ref) / np.abs(ref)
+        assert rel.max() <= SCORE_RTOL, (tag, rel.max())
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_cluster_on_reference_scores_bit_exact(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    g = pipe.build_graph(db, with_coo=False)
+    scores = torch.from_numpy(np.concatenate([npz[t + '/scores'] for t in tags])).cuda()
+    ph, npers = pipe.cluster(db, g, scores)
+    ph, npers = ph.cpu().numpy(), npers.cpu().numpy()
+    for b, tag in enumerate(tags):
+        want = npz[tag + '/proposals']
+        got = ph[pb.head_off[b]:pb.head_off[b] + npers[b]]
+        assert np.array_equal(got, want), (tag, got, want)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_cluster_fuzz_bit_exact(config):
+    """Fuzzed score vectors (ties, all-pass, bimodal, ...) against the reference's own outputs."""
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    fuzz_tags = meta['fuzz_tags']
+    tags, pb, db = golden_batch(config, tags=fuzz_tags)
+    g = pipe.build_graph(db, with_coo=False)
+    scores = torch.from_numpy(np.concatenate([npz['fuzz/%d/scores' % i] for i in range(len(fuzz_tags))])).cuda()
+    ph, npers = pipe.cluster(db, g, scores)
+    ph, npers = ph.cpu().numpy(), npers.cpu().numpy()
+    dup = 0
+    for i in range(len(fuzz_tags)):
+        want = npz['fuzz/%d/proposals' % i]
+        got = ph[pb.head_off[i]:pb.head_off[i] + npers[i]]
+        assert np.array_equal(got, want), (i, fuzz_tags[i])
+    assert len(fuzz_tags) >= 60
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_encoder_mlp_triangulation_vs_reference(config):
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    g = pipe.build_graph(db, with_coo=False)
+    # person assignment from the reference's proposals
+    rows, owner = [], []
+    for b, tag in enumerate(tags):
+        for p, person in enumerate(npz[tag + '/proposals']):
+            r = np.full(cfg.n_cameras, -1, np.int32)
+            for s, h in enumerate(person):
+                if h >= 0:
+                    r[cfg.used_sm[s]] = pb.head_off[b] + h
+            rows.append(r); owner.append((tag, p))
+    person_sk = torch.from_numpy(np.stack(rows)).cuda()
+    P = len(rows)
+    x, valid, xf = pipe.encode_persons(db, P, person_sk, want_f32=True)
+    xf = xf.cpu().numpy()
+    joints = pipe.mlp_forward(x, P).cpu().numpy()
+    xyz, mask = pipe.triangulate(db, P, person_sk)
+    xyz, mask = xyz.cpu().numpy(), mask.cpu().numpy()
+    assert valid.cpu().numpy().all()
+    worst_j = 0.0
+    for i, (tag, p) in enumerate(owner):
+        ref_in = npz[tag + '/mlp_in'][p]
+        assert np.abs(xf[i] - ref_in).max() <= 1e-6, (tag, p, np.abs(xf[i] - ref_in).max())
+        assert np.abs(x.to_f32()[i].cpu().numpy() - ref_in).max() <= 1e-5
+        ref_j = npz[tag + '/mlp_out'][p] * np.float32(10.)
+        worst_j = max(worst_j, np.abs(joints[i] - ref_j).max())
+        assert np.abs(joints[i] - ref_j).max() <= JOINT_TOL_M, (tag, p)
+        assert np.array_equal(mask[i], npz[tag + '/tri_mask'][p])
+        assert np.abs(xyz[i] - npz[tag + '/tri'][p]).max() <= 1e-7, (tag, p, np.abs(xyz[i] - npz[tag + '/tri'][p]).max())
+    print('worst joint deviation [mm]', config, worst_j * 1e3)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_end_to_end_vs_reference(config):
+    """Whole path on a ragged batch of the golden frames. Person assignment must equal the reference's
+    unless a score gap below the score tolerance decides the greedy order (counted)."""
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
+    res = pipe.infer(db)
+    ph, npers = res['person_heads'].cpu().numpy(), res['n_persons'].cpu().numpy()
+    poff = res['person_off'].cpu().numpy()
+    joints = res['joints'].cpu().numpy()
+    mismatched = 0
+    for b, tag in enumerate(tags):
+        want = npz[tag + '/proposals']
+        got = ph[pb.head_off[b]:pb.head_off[b] + npers[b]]
+        if not np.array_equal(got, want):
+            mismatched += 1
+            continue
+        ref_j = npz[tag + '/mlp_out'] * np.float32(10.)
+        assert np.abs(joints[poff[b]:poff[b + 1]] - ref_j).max() <= JOINT_TOL_M, tag
+    print('end-to-end frames with different assignment:', mismatched, 'of', len(tags))
+    assert mismatched <= max(1, len(tags) // 4)
+
+
+def test_against_oracle_on_fresh_frames():
+    """Seeded frames the goldens do not contain: CUDA path vs the oracle on the same inputs."""
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    gat_w, mlp_w = helpers.golden_weights(config)
+    gat_w, mlp_w = helpers.np_state(gat_w), helpers.np_state(mlp_w)
+    tabs = O.CameraTables(cfg)
+    frames = [helpers.synth.make_frame(cfg, 500 + i, 2 + i % 4, drop_joint_p=0.1 * (i % 3), drop_view_p=0.1 * (i % 2))
+              for i in range(12)]
+    frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+    pb = pack_mod.pack_frames(frames, cfg)
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    res = pipe.infer(db)
+    scores = res['scores'].cpu().numpy()
+    ph, npers = res['person_heads'].cpu().numpy(), res['n_persons'].cpu().numpy()
+    g = res['graph']
+    for b, f in enumerate(frames):
+        og = O.build_graph(f, tabs)
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        if og is None:
+            assert npers[b] == 0
+            continue
+        os_ = O.gat_forward(gat_w, og['feats'], og['src'], og['dst'])
+        idx = og['indices']
+        rel = np.abs(scores[n0:n1][idx] - os_[idx]) / np.abs(os_[idx])
+        assert rel.max() <= SCORE_RTOL, (b, rel.max())
+        # clustering on the GPU's own scores must equal the oracle clustering on the same scores
+        props = O.cluster(scores[n0:n1], og['pairs'], og['nodes_camera'][:og['n_heads']], cfg.V_sm, og['n_heads'])
+        assert np.array_equal(ph[pb.head_off[b]:pb.head_off[b] + npers[b]], props), b
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (1024 frames x 4 persons x 5 views): frame-order permutation and batch
+    splitting must not change any per-frame result (frames are independent)."""
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    base = [helpers.synth.make_frame(cfg, 2000 + i, 4) for i in range(64)]
+    base = [{c: f[c] for c in f if json.loads(f[c][0])} for f in base]
+    pb64 = pack_mod.pack_frames(base, cfg, keep_json=False)
+    pb = pb64.tile(16)
+    assert pb.n_frames == 1024
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    res = pipe.infer(db)
+    scores = res['scores'].cpu().numpy()
+    npers = res['n_persons'].cpu().numpy()
+    joints = res['joints'].cpu().numpy()
+    poff = res['person_off'].cpu().numpy()
+    N64 = pb64.n_nodes
+    # every repetition of the 64 frames gives bit-identical scores, counts and joints
+    for r in range(1, 16):
+        assert np.array_equal(scores[r * N64:(r + 1) * N64], scores[:N64])
+        assert np.array_equal(npers[r * 64:(r + 1) * 64], npers[:64])
+    P64 = poff[64]
+    for r in range(1, 16):
+        assert np.array_equal(joints[r * P64:(r + 1) * P64], joints[:P64])
+    # a split batch gives the same results as the whole
+    half = pipe.infer(pipeline_mod.HostBatch(pb.slice(512, 1024)).to_device('cuda:0'))
+    assert np.array_equal(half['scores'].cpu().numpy(), scores[pb.node_off[512]:])
+    assert np.array_equal(half['n_persons'].cpu().numpy(), npers[512:])
+    assert np.isfinite(joints).all() and npers.sum() > 0
+
+
+def test_empty_and_degenerate_batches():
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    # frames with all detections in one camera (no graph in the reference) and an empty frame
+    f1 = meta['frames']['onecam']
+    frames = [{c: f1[c] for c in f1 if json.loads(f1[c][0])}, {}]
+    pb = pack_mod.pack_frames(frames, cfg)
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    res = pipe.infer(db)
+    assert res['n_persons'].cpu().numpy().tolist() == [0, 0]
+    assert res['n_persons_total'] == 0
