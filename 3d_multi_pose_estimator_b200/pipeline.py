@@ -339,10 +339,14 @@ class PosePipeline:
         res = dict(graph=g, scores=scores, person_heads=person_heads, n_persons=n_persons, person_off=person_off,
                    person_sk=person_sk, person_frame=person_frame, n_persons_total=P)
         if self.mlp is not None:
-            x, valid, _ = self.encode_persons(db, P, person_sk)
-            res['valid'] = valid
-            res['joints'] = self.mlp_forward(x, P) if P > 0 else torch.zeros((0, 54), device=self.device)
-        if want_triangulation:
+            if P > 0:
+                x, valid, _ = self.encode_persons(db, P, person_sk)
+                res['valid'] = valid
+                res['joints'] = self.mlp_forward(x, P)
+            else:
+                res['valid'] = torch.zeros(0, dtype=torch.uint8, device=self.device)
+                res['joints'] = torch.zeros((0, self.mlp[-1]['n']), dtype=torch.float32, device=self.device)
+        if want_triangulation and P > 0:
             res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, person_sk)
         return res
 
