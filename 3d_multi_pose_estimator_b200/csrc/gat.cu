@@ -21,13 +21,10 @@ struct AggParams {
     const float* z; int ldz; int heads, dim, layer0;
     float alpha, act_slope;
     float* raw_f32; __nv_bfloat16* act_hi; __nv_bfloat16* act_lo; int ld_planes;
-    int stage_rows;     // rows of smem available per CTA
+    int stage_rows;     // z rows of shared memory available per CTA for staging
+    int chunk;          // destination nodes per CTA (work unit = frame x chunk)
+    int max_deg;        // largest in-degree (sizes the per-warp attention scratch)
 };
-
-template <int VEC> struct VecT;
-template <> struct VecT<4> { using type = float4; };
-template <> struct VecT<2> { using type = float2; };
-template <> struct VecT<1> { using type = float; };
 
 template <int VEC> __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
     if constexpr (VEC == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
@@ -35,18 +32,26 @@ template <int VEC> __device__ __forceinline__ void load_vec(const float* p, floa
     else v[0] = *p;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256) gat_aggregate_kernel(AggParams p)
+constexpr int kAggWarps = 8;
+
+// VEC consecutive columns per lane, KMAX column vectors per lane (heads*dim <= 32*VEC*KMAX)
+template <int VEC, int KMAX>
+__global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams p)
 {
-    extern __shared__ __align__(16) float zs[];
+    extern __shared__ __align__(16) float smem_f[];
     const int b = blockIdx.x;
     const int n0 = p.node_off[b];
     const int Nb = p.node_off[b + 1] - n0;
+    const int v_begin = blockIdx.y * p.chunk;
+    if (v_begin >= Nb) return;
+    const int v_end = min(Nb, v_begin + p.chunk);
     const int h0 = p.head_off[b];
     const int Hb = p.head_off[b + 1] - h0;
-    const int HD = p.heads * p.dim;
+    const int H = p.heads, D = p.dim, HD = H * D;
     const int ldz = p.ldz;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* zs = smem_f;                                                     // staged z rows
+    float* att = smem_f + (size_t)p.stage_rows * ldz + (size_t)warp * p.max_deg * H;   // this warp's [deg][H] scratch
 
     // ---- stage the frame's head rows (layer 0: + the shared edge-node row) ------------------------
     int n_stage;
@@ -81,46 +86,76 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(AggParams p)
     };
 
     const int n_vec = HD / VEC;
-    const int n_vec_pad = p.act_hi ? p.ld_planes / VEC : n_vec;
-    for (int v = warp; v < Nb; v += nwarps) {
-        const int gv = n0 + v;
-        const int beg = p.row_ptr[gv], end = p.row_ptr[gv + 1];
-        const float* rowv = row_of(gv);
-        for (int cv = lane; cv < n_vec_pad; cv += 32) {
-            float acc[VEC];
+    int head_of[KMAX];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-            if (cv < n_vec) {
-                const int h = (cv * VEC) / p.dim;
-                const float a2v = rowv[HD + p.heads + h];
-                float m = -INFINITY;
-                for (int e = beg; e < end; ++e) {
-                    const float* ru = row_of(__ldg(p.col + e));
-                    m = fmaxf(m, leaky(ru[HD + h] + a2v, p.alpha));
-                }
-                float den = 0.f;
-                for (int e = beg; e < end; ++e) {
-                    const float* ru = row_of(__ldg(p.col + e));
-                    den += expf(leaky(ru[HD + h] + a2v, p.alpha) - m);
-                }
-                for (int e = beg; e < end; ++e) {
-                    const float* ru = row_of(__ldg(p.col + e));
-                    const float w = expf(leaky(ru[HD + h] + a2v, p.alpha) - m) / den;
+    for (int k = 0; k < KMAX; ++k) head_of[k] = min(H - 1, ((lane + 32 * k) * VEC) / D);
+
+    for (int v = v_begin + warp; v < v_end; v += kAggWarps) {
+        const int gv = n0 + v;
+        const int beg = p.row_ptr[gv];
+        const int deg = min(p.row_ptr[gv + 1] - beg, p.max_deg);
+        const float* rowv = row_of(gv);
+        // 1. attention logits e[i][h] = LeakyReLU(a1[u_i][h] + a2[v][h])            (gat2.py:78-81)
+        const int npair = deg * H;
+        for (int t = lane; t < npair; t += 32) {
+            const int i = t / H, h = t - i * H;
+            const float* ru = row_of(__ldg(p.col + beg + i));
+            att[t] = leaky(ru[HD + h] + rowv[HD + H + h], p.alpha);
+        }
+        __syncwarp();
+        // 2. softmax over the in-edges of v, per head                                  (gat2.py:83-88)
+        float mh = -INFINITY;
+        if (lane < H) for (int i = 0; i < deg; ++i) mh = fmaxf(mh, att[i * H + lane]);
+        for (int t0 = 0; t0 < npair; t0 += 32) {                // uniform trip count: every lane takes part in the shuffle
+            const int t = t0 + lane;
+            const float m = __shfl_sync(0xffffffffu, mh, t % H);
+            if (t < npair) att[t] = expf(att[t] - m);
+        }
+        __syncwarp();
+        float dh = 0.f;
+        if (lane < H) for (int i = 0; i < deg; ++i) dh += att[i * H + lane];
+        for (int t0 = 0; t0 < npair; t0 += 32) {
+            const int t = t0 + lane;
+            const float d = __shfl_sync(0xffffffffu, dh, t % H);
+            if (t < npair) att[t] = att[t] / d;
+        }
+        __syncwarp();
+        // 3. out[v] = sum_i s[i][h] * ft2[u_i]                                        (gat2.py:66)
+        float acc[KMAX][VEC];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
+        for (int i = 0; i < deg; ++i) {
+            const float* ru = row_of(__ldg(p.col + beg + i));
+            const float* w = att + i * H;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const int cv = lane + 32 * k;
+                if (cv < n_vec) {
                     float f[VEC];
                     load_vec<VEC>(ru + cv * VEC, f);
+                    const float a = w[head_of[k]];
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w, f[i], acc[i]);
+                    for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(a, f[q], acc[k][q]);
                 }
-                if (p.raw_f32) {
-                    float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
+            }
+        }
+        __syncwarp();                                           // att is reused by the next destination
+        // 4. outputs
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) o[i] = acc[i];
-                }
+        for (int k = 0; k < KMAX; ++k) {
+            const int cv = lane + 32 * k;
+            if (cv >= n_vec) continue;
+            if (p.raw_f32) {
+                float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o[q] = acc[k][q];
             }
             if (p.act_hi) {
                 __nv_bfloat16 hi[VEC], lo[VEC];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) split_bf16(leaky(acc[i], p.act_slope), hi[i], lo[i]);
+                for (int q = 0; q < VEC; ++q) split_bf16(leaky(acc[k][q], p.act_slope), hi[q], lo[q]);
                 __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + cv * VEC;
                 __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + cv * VEC;
                 if constexpr (VEC == 4) {
@@ -132,6 +167,12 @@ __global__ void __launch_bounds__(256) gat_aggregate_kernel(AggParams p)
                 } else {
                     oh[0] = hi[0]; ol[0] = lo[0];
                 }
+            }
+        }
+        if (p.act_hi) {                                         // K padding of the planes stays zero
+            for (int c = HD + lane; c < p.ld_planes; c += 32) {
+                p.act_hi[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
+                p.act_lo[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
             }
         }
     }
@@ -193,22 +234,36 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.alpha = alpha; p.act_slope = act_slope; p.raw_f32 = raw_f32;
     p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
     p.ld_planes = ld_planes;
-    // shared-memory staging: the frame's head rows (+1 shared edge-node row for layer 0), capped at
-    // 96 KB per CTA so at least two CTAs stay resident per SM
+    // Work unit = (frame, chunk of destination nodes). In-degree of a head is 1 + H_b - n_g <= H_b and of an
+    // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
+    const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
+    p.max_deg = mh < 3 ? 3 : mh;
+    // shared memory: the frame's head rows (+1 shared edge-node row for layer 0), capped at 96 KB, plus
+    // one [max_deg][heads] attention scratch per warp
     const size_t row_bytes = (size_t)ldz * sizeof(float);
     int stage_rows = (int)((96 * 1024) / row_bytes);
     const int want = max_heads_per_frame > 0 ? max_heads_per_frame + (layer0 ? 1 : 0) : 0;
     if (stage_rows > want) stage_rows = want;
     p.stage_rows = stage_rows;
-    const size_t smem = (size_t)stage_rows * row_bytes;
+    const size_t smem = (size_t)stage_rows * row_bytes + (size_t)kAggWarps * p.max_deg * heads * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("gat_aggregate: frame too large for the shared-memory plan (%zu bytes, %d heads per frame)", smem, mh);
+        return B200POSE_E_UNSUPPORTED;
+    }
+    const int max_nodes = mh + (mh * mh) / 2;
+    p.chunk = 6 * kAggWarps;                                   // 48 destinations per CTA
+    const int n_chunks = ceil_div(max_nodes, p.chunk);
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
+    const int n_vec = HD / vec;
+    dim3 grid(n_frames, n_chunks);
     auto launch = [&](auto kern) -> int {
         B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<n_frames, 256, smem, st>>>(p);
+        kern<<<grid, kAggWarps * 32, smem, st>>>(p);
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     };
-    if (vec == 4) return launch(gat_aggregate_kernel<4>);
-    if (vec == 2) return launch(gat_aggregate_kernel<2>);
-    return launch(gat_aggregate_kernel<1>);
+    if (n_vec > 32 * 8) { set_error("gat_aggregate: heads*dim = %d too large", HD); return B200POSE_E_UNSUPPORTED; }
+    if (vec == 4) return n_vec <= 64 ? launch(gat_aggregate_kernel<4, 2>) : n_vec <= 128 ? launch(gat_aggregate_kernel<4, 4>) : launch(gat_aggregate_kernel<4, 8>);
+    if (vec == 2) return n_vec <= 64 ? launch(gat_aggregate_kernel<2, 2>) : n_vec <= 128 ? launch(gat_aggregate_kernel<2, 4>) : launch(gat_aggregate_kernel<2, 8>);
+    return n_vec <= 128 ? launch(gat_aggregate_kernel<1, 4>) : launch(gat_aggregate_kernel<1, 8>);
 }

@@ -155,11 +155,34 @@ class PosePipeline:
         self.gemm_impl = gemm_impl
         self.threshold = float(threshold)
         self.launches = 0
+        self._ws = {}
         with torch.cuda.device(self.device):
             self.cams = DeviceCameras(cfg, self.device)
             self._prepare_gat(gat_state)
             self.mlp = self._prepare_mlp(mlp_state) if mlp_state is not None else None
             torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ workspace
+    def planes_ws(self, tag: str, rows: int, cols: int) -> Planes:
+        """Activation planes from a per-pipeline workspace. They are zero-initialised once; kernels write
+        every valid column and only ever write zeros into the K padding, so reuse needs no memset."""
+        key = (tag, round_up(max(cols, 1), 64))
+        ws = self._ws.get(key)
+        if ws is None or ws.hi.shape[0] < rows:
+            cap = max(rows, int(ws.hi.shape[0] * 1.25) if ws is not None else rows)
+            ws = Planes(cap, cols, self.device)
+            self._ws[key] = ws
+        view = Planes.__new__(Planes)
+        view.rows, view.cols, view.ld, view.hi, view.lo = rows, cols, ws.ld, ws.hi, ws.lo
+        return view
+
+    def f32_ws(self, tag: str, rows: int, cols: int) -> torch.Tensor:
+        key = (tag, cols)
+        t = self._ws.get(key)
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1), cols), dtype=torch.float32, device=self.device)
+            self._ws[key] = t
+        return t
 
     # ------------------------------------------------------------------ weights
     def _stream(self):
@@ -229,7 +252,7 @@ class PosePipeline:
         return out[: db.n_nodes]
 
     def head_feature_planes(self, db: DeviceBatch) -> Planes:
-        p = Planes(db.n_heads + 1, self.cfg.n_features_sm, self.device)
+        p = self.planes_ws('x0', db.n_heads + 1, self.cfg.n_features_sm)
         self.launches += 1
         check(self.L.b200pose_node_features(db.n_frames, db.n_heads, db.n_nodes, ptr(db.head_off), ptr(db.node_off),
                                             ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), ptr(db.sk_cam), self.cams.ref,
@@ -259,12 +282,12 @@ class PosePipeline:
         scores = torch.empty(max(N, 1), dtype=torch.float32, device=self.device)
         for l, lay in enumerate(self.gat):
             last = l == len(self.gat) - 1
-            h = Planes(rows, lay['din'], self.device)
+            h = self.planes_ws('gat_h', rows, lay['din'])
             self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], GAT_ALPHA, out_planes=h)
-            z = torch.empty((max(rows, 1), lay['ldz']), dtype=torch.float32, device=self.device)
+            z = self.f32_ws('gat_z', rows, lay['ldz'])
             self.linear(h, rows, lay['w2'], lay['b2'], lay['n2'], lay['din'], 1.0, out_f32=z)
             raw = torch.empty((max(N, 1), lay['hd']), dtype=torch.float32, device=self.device) if keep_layers else None
-            act = None if last else Planes(N, lay['hd'], self.device)
+            act = None if last else self.planes_ws('gat_act%d' % (l & 1), N, lay['hd'])
             self.aggregate(db, g, z, lay, layer0=(l == 0 and not dense_rows), raw=raw, act=act, scores=scores if last else None)
             if keep_layers:
                 raws.append(raw[:N])
@@ -298,7 +321,7 @@ class PosePipeline:
         return P, person_off, person_sk[:P], person_frame[:P]
 
     def encode_persons(self, db: DeviceBatch, P: int, person_sk, want_f32=False):
-        x = Planes(P, self.cfg.mlp_in, self.device)
+        x = self.planes_ws('mlp_x', P, self.cfg.mlp_in)
         valid = torch.empty(max(P, 1), dtype=torch.uint8, device=self.device)
         xf = torch.zeros((max(P, 1), self.cfg.mlp_in), dtype=torch.float32, device=self.device) if want_f32 else None
         self.launches += 1
@@ -324,7 +347,7 @@ class PosePipeline:
             if last:
                 self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out)
             else:
-                y = Planes(P, lay['n'], self.device)
+                y = self.planes_ws('mlp_y%d' % (i & 1), P, lay['n'])
                 self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], MLP_SLOPE, out_planes=y)
                 x = y
         return out[:P]
