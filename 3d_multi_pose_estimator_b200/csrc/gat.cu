@@ -214,6 +214,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
 {
     B2_CHECK_ARG(head_off && node_off && row_ptr && col && z, "gat_aggregate: null input");
     B2_CHECK_ARG(heads >= 1 && dim >= 1 && ldz >= heads * dim + 2 * heads, "gat_aggregate: ldz too small");
+    B2_CHECK_ARG(heads <= 32, "gat_aggregate: more than 32 attention heads");
     B2_CHECK_ARG((act_hi == nullptr) == (act_lo == nullptr), "gat_aggregate: planes go together");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_frames == 0 || n_nodes_total == 0) return B200POSE_OK;

@@ -264,6 +264,242 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// product kernel v2: persistent, double-buffered TMEM accumulators, TMA-store epilogue
+//
+//   grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (n fastest, so the CTAs
+//   of one wave share A tiles through L2). The three roles run decoupled across tiles:
+//     warp 0 : TMA producer - keeps `stages` k-blocks in flight, runs ahead into the next tile while
+//              the epilogue of the previous one drains
+//     warp 1 : MMA issuer   - accumulator (tile & 1) of two TMEM buffers
+//     warps 2..5 : epilogue - TMEM -> registers -> (bias, LeakyReLU, scale, re-split) -> 128B-swizzled
+//              shared staging -> cp.async.bulk.tensor store; frees the accumulator as soon as its last
+//              TMEM load retired
+//   Output tiles are made of 64-column panels (bf16 planes: one 128-byte row per panel; fp32: two 32-column
+//   boxes), W is fetched in 64-row boxes, so a tile can be 64..256 columns wide at run time.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct GemmParams2 {
+    int M, N, num_kb;
+    int tiles_m, tiles_n, panels_total;      // 64-column output panels
+    int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
+    const float* bias; float slope, out_scale;
+    int has_f32, has_planes;
+    unsigned long long* dbg;                 // optional per-CTA timestamps (kernel bring-up)
+};
+
+struct TileInfo { int m0, n0, bn; };
+__device__ __forceinline__ TileInfo tile_info(const GemmParams2& p, int tile) {
+    const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
+    const int base = p.panels_total / p.tiles_n, rem = p.panels_total % p.tiles_n;
+    TileInfo t;
+    t.m0 = mb * kBM;
+    t.n0 = 64 * (nb * base + min(nb, rem));
+    t.bn = 64 * (base + (nb < rem ? 1 : 0));
+    return t;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
+    const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+    const __grid_constant__ CUtensorMap map_o_f32, const __grid_constant__ CUtensorMap map_o_hi,
+    const __grid_constant__ CUtensorMap map_o_lo, const GemmParams2 p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t a_bytes = kBM * kBK * 2;                                  // 16 KB per plane
+    const uint32_t b_bytes = (uint32_t)p.stage_bn * kBK * 2;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t staging_base = tiles_base + (uint32_t)p.stages * stage_bytes;   // 1024-aligned
+    const uint32_t acc_cols = tmem_cols_for(p.stage_bn);
+    const uint32_t ncols = 2 * acc_cols;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        if (p.has_f32) prefetch_tmap(&map_o_f32);
+        if (p.has_planes) { prefetch_tmap(&map_o_hi); prefetch_tmap(&map_o_lo); }
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 0] = globaltimer_ns();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileInfo t = tile_info(p, tile);
+                const uint32_t tx = 2 * a_bytes + 2 * (uint32_t)t.bn * kBK * 2;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, tx);
+                    const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
+                    tma_load_2d(base, &map_a_hi, kb * kBK, t.m0, full);
+                    tma_load_2d(base + a_bytes, &map_a_lo, kb * kBK, t.m0, full);
+                    for (int j = 0; j < t.bn / 64; ++j) {
+                        tma_load_2d(base + 2 * a_bytes + j * 8192, &map_w_hi, kb * kBK, t.n0 + 64 * j, full);
+                        tma_load_2d(base + 2 * a_bytes + b_bytes + j * 8192, &map_w_lo, kb * kBK, t.n0 + 64 * j, full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+                const TileInfo t = tile_info(p, tile);
+                const uint32_t idesc = make_idesc(t.bn);
+                const int a = i & 1;
+                mbar_wait(smem_u32(&bar_acc_empty[a]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)a * acc_cols;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    tcgen05_fence_after();
+                    const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
+                    issue_kblock(base, base + a_bytes, base + 2 * a_bytes, base + 2 * a_bytes + b_bytes, tmem_d, idesc, kb == 0);
+                    umma_commit(smem_u32(&bar_empty[s]));
+                }
+                umma_commit(smem_u32(&bar_acc_full[a]));
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;                                   // TMEM lane quarter of this warp
+        const uint32_t stage_f32 = staging_base + (uint32_t)(warp - 2) * (uint32_t)((p.has_f32 ? 8192 : 0) + (p.has_planes ? 8192 : 0));
+        const uint32_t stage_hi = stage_f32 + (p.has_f32 ? 8192u : 0u);
+        const uint32_t stage_lo = stage_hi + 4096u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        int i = 0;
+        bool stores_pending = false;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+            const TileInfo t = tile_info(p, tile);
+            const int a = i & 1;
+            mbar_wait(smem_u32(&bar_acc_full[a]), (uint32_t)(i >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_t = tmem_base + (uint32_t)a * acc_cols + ((uint32_t)(q * 32) << 16);
+            const int npanels = t.bn / 64;
+            for (int j = 0; j < npanels; ++j) {
+                const int col0 = t.n0 + 64 * j;
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(tmem_t + (uint32_t)(64 * j), r0);
+                tmem_ld_32x32(tmem_t + (uint32_t)(64 * j + 32), r1);
+                if (j == npanels - 1) {                           // accumulator drained: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[a]));
+                }
+                // bias of the panel: lane l holds columns col0+l and col0+32+l
+                float b0 = 0.f, b1 = 0.f;
+                if (p.bias) {
+                    if (col0 + lane < p.N) b0 = __ldg(p.bias + col0 + lane);
+                    if (col0 + 32 + lane < p.N) b1 = __ldg(p.bias + col0 + 32 + lane);
+                }
+                float v[64];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
+                    v[c] = (col0 + c < p.N) ? leaky(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
+                    v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                }
+                if (stores_pending) {                             // staging buffers are about to be overwritten
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
+                if (p.has_f32) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t addr = stage_f32 + (uint32_t)half * 4096u + row_off + (((uint32_t)c ^ sw) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[half * 32 + 4 * c]),
+                                         "f"(v[half * 32 + 4 * c + 1]), "f"(v[half * 32 + 4 * c + 2]), "f"(v[half * 32 + 4 * c + 3]) : "memory");
+                        }
+                }
+                if (p.has_planes) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(v[8 * c + 2 * u], h0, l0);
+                            split_bf16(v[8 * c + 2 * u + 1], h1, l1);
+                            h[u] = pack_bf16x2(h0, h1);
+                            l[u] = pack_bf16x2(l0, l1);
+                        }
+                        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int row0 = t.m0 + q * 32;
+                    if (row0 < p.M) {
+                        if (p.has_f32) {
+                            if (col0 < p.N) tma_store_2d(&map_o_f32, stage_f32, col0, row0);
+                            if (col0 + 32 < p.N) tma_store_2d(&map_o_f32, stage_f32 + 4096u, col0 + 32, row0);
+                        }
+                        if (p.has_planes) {
+                            tma_store_2d(&map_o_hi, stage_hi, col0, row0);
+                            tma_store_2d(&map_o_lo, stage_lo, col0, row0);
+                        }
+                    }
+                    bulk_commit();
+                }
+                stores_pending = true;
+            }
+        }
+        if (lane == 0) bulk_wait0();
+        if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // debug kernel: identical MMA + epilogue, but the tiles are written by ordinary stores (no TMA,
 // single stage). Used by the kernel self-test to separate tensor-map bugs from descriptor bugs.
 // ------------------------------------------------------------------------------------------------
@@ -394,18 +630,36 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int rows, int kpad, int ld, int box_rows) {
+static int make_map_ex(CUtensorMap* map, CUtensorMapDataType dt, int elt, const void* base, int rows, int cols, int ld,
+                       int box_cols, int box_rows) {
     auto fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return B200POSE_E_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * elt};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d kpad %d ld %d box %d)", (int)r, rows, kpad, ld, box_rows); return B200POSE_E_CUDA; }
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d cols %d ld %d box %dx%d)", (int)r, rows, cols, ld, box_cols, box_rows);
+        return B200POSE_E_CUDA;
+    }
     return B200POSE_OK;
+}
+static int make_map(CUtensorMap* map, const void* base, int rows, int kpad, int ld, int box_rows) {
+    return make_map_ex(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, kpad, ld, kBK, box_rows);
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 static int choose_bn(int n) {
@@ -461,21 +715,58 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
-    B2_CHECK_ARG(impl == 0, "linear: impl must be 0 (tcgen05), 1 (simt self-test) or 2 (tcgen05 manual-fill self-test)");
-    int stages = (int)((220 * 1024 - 1024) / stage_bytes);
+    if (impl == 3) {                       // v1 non-persistent kernel, kept for A/B measurements during bring-up
+        int stages = (int)((220 * 1024 - 1024) / stage_bytes);
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages > p.num_kb) stages = p.num_kb;
+        if (stages < 1) stages = 1;
+        p.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + 1024;
+        CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+        int rc;
+        if ((rc = make_map(&ma_hi, a_hi, m, kpad, lda, kBM))) return rc;
+        if ((rc = make_map(&ma_lo, a_lo, m, kpad, lda, kBM))) return rc;
+        if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, p.bn))) return rc;
+        if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, p.bn))) return rc;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_split_tc_kernel<<<grid, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    }
+    B2_CHECK_ARG(impl == 0, "linear: impl must be 0 (tcgen05 persistent), 1 (simt self-test), 2 (manual-fill self-test) or 3 (v1)");
+    // ---- persistent kernel ----
+    if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
+    if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");
+    GemmParams2 q;
+    q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
+    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = nullptr;
+    q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
+    q.tiles_n = ceil_div(q.panels_total, 4);
+    q.tiles_m = ceil_div(m, kBM);
+    q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
+    const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)q.stage_bn * kBK * 2;
+    const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
+    int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages > p.num_kb) stages = p.num_kb;
-    if (stages < 1) stages = 1;
-    p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    if (stages < 1) { set_error("linear: tile does not fit in shared memory"); return B200POSE_E_UNSUPPORTED; }
+    q.stages = stages;
+    const size_t smem = (size_t)stages * stage2 + staging + 1024;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo;
     int rc;
     if ((rc = make_map(&ma_hi, a_hi, m, kpad, lda, kBM))) return rc;
     if ((rc = make_map(&ma_lo, a_lo, m, kpad, lda, kBM))) return rc;
-    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, p.bn))) return rc;
-    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, p.bn))) return rc;
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_split_tc_kernel<<<grid, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, 64))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, 64))) return rc;
+    mo_f32 = ma_hi; mo_hi = ma_hi; mo_lo = ma_hi;                              // placeholders when unused
+    if (out_f32 && (rc = make_map_ex(&mo_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, m, n, ld_out, 32, 32))) return rc;
+    if (out_hi) {
+        if ((rc = make_map_ex(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, m, ld_planes, ld_planes, 64, 32))) return rc;
+        if ((rc = make_map_ex(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, m, ld_planes, ld_planes, 64, 32))) return rc;
+    }
+    const int total_tiles = q.tiles_m * q.tiles_n;
+    const int grid2 = total_tiles < num_sms() ? total_tiles : num_sms();
+    B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_split_tc2_kernel<<<grid2, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

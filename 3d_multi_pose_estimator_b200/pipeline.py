@@ -341,7 +341,8 @@ class PosePipeline:
     def mlp_forward(self, x: Planes, P: int, scale: float = 10.0) -> torch.Tensor:
         """PoseEstimatorMLP.forward (utils/mlp.py:8-31); `scale` is the x10 the callers apply
         (metrics_from_model.py:282), fused into the last epilogue."""
-        out = torch.empty((max(P, 1), self.mlp[-1]['n']), dtype=torch.float32, device=self.device)
+        n_out = self.mlp[-1]['n']
+        out = self.f32_ws('mlp_out', P, round_up(n_out, 4))          # TMA store needs a 16-byte row pitch
         for i, lay in enumerate(self.mlp):
             last = i == len(self.mlp) - 1
             if last:
@@ -350,7 +351,7 @@ class PosePipeline:
                 y = self.planes_ws('mlp_y%d' % (i & 1), P, lay['n'])
                 self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], MLP_SLOPE, out_planes=y)
                 x = y
-        return out[:P]
+        return out[:P, :n_out]
 
     # ------------------------------------------------------------------ whole path
     def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):

@@ -81,26 +81,28 @@ def test_graph_and_features_bit_exact(config):
     assert row_ptr[pb.n_nodes] == pb.n_edges
 
 
-@pytest.mark.parametrize('impl', [1, 2, 0])
+@pytest.mark.parametrize('impl', [1, 2, 3, 0])
 def test_linear_kernels(impl):
-    """out = act(A W^T + b): SIMT self-test kernel (1), tcgen05 with manual tile fill (2), product TMA kernel (0)
-    against a float64 reference of the same split operands."""
+    """out = act(A W^T + b): SIMT self-test kernel (1), tcgen05 with manual tile fill (2), the v1 one-tile-per-CTA
+    TMA kernel (3) and the persistent product kernel (0) against a float64 reference of the same split operands."""
     pipe = get_pipe('panoptic')
     L = pipe.L
     torch.manual_seed(5)
     shapes = [(128, 64, 64), (200, 48, 150), (77, 902, 902), (300, 420, 400), (1000, 3, 150), (260, 336, 400),
-              (129, 160, 320), (500, 3072, 1260), (64, 54, 1024)]
+              (129, 160, 320), (500, 3072, 1260), (64, 54, 1024), (40000, 400, 400), (20481, 902, 902)]
     for (m, n, k) in shapes:
         A = torch.randn(m, k, device='cuda') * 0.7
         W = torch.randn(n, k, device='cuda') / k ** 0.5
         b = torch.randn(n, device='cuda')
         s = pipe._stream()
         Ap, Wp = pipeline_mod.Planes.from_f32(A, s), pipeline_mod.Planes.from_f32(W, s)
-        out = torch.full((m, n), float('nan'), device='cuda')
+        ldo = (n + 3) // 4 * 4                                   # the TMA-store epilogue needs a 16-byte row pitch
+        out_buf = torch.full((m, ldo), float('nan'), device='cuda')
+        out = out_buf[:, :n]
         outp = pipeline_mod.Planes(m, n, 'cuda')
         pipeline_mod.check(L.b200pose_linear(pipeline_mod.ptr(Ap.hi), pipeline_mod.ptr(Ap.lo), Ap.ld, pipeline_mod.ptr(Wp.hi),
                                              pipeline_mod.ptr(Wp.lo), Wp.ld, pipeline_mod.ptr(b), m, n, k, 0.15, 2.0,
-                                             pipeline_mod.ptr(out), n, pipeline_mod.ptr(outp.hi), pipeline_mod.ptr(outp.lo), outp.ld,
+                                             pipeline_mod.ptr(out_buf), ldo, pipeline_mod.ptr(outp.hi), pipeline_mod.ptr(outp.lo), outp.ld,
                                              impl, s), 'linear')
         torch.cuda.synchronize()
         ref = Ap.to_f32().double() @ Wp.to_f32().double().T + b.double()
