@@ -145,7 +145,8 @@ class PosePipeline:
     (GAT `layers.{l}.{attn_l,attn_r,fc1.*,fc2.*}`, MLP `layers.{1,3,..,17}.{weight,bias}`).
     """
 
-    def __init__(self, cfg: CameraConfig, gat_state: Dict[str, torch.Tensor], mlp_state: Optional[Dict[str, torch.Tensor]],
+    def __init__(self, cfg: CameraConfig, gat_state: Optional[Dict[str, torch.Tensor]] = None,
+                 mlp_state: Optional[Dict[str, torch.Tensor]] = None,
                  device=None, gemm_impl: int = 0, threshold: float = 0.5):
         if not torch.cuda.is_available():
             raise RuntimeError('PosePipeline needs a CUDA device (sm_100a); there is no CPU fallback')
@@ -158,8 +159,8 @@ class PosePipeline:
         self._ws = {}
         with torch.cuda.device(self.device):
             self.cams = DeviceCameras(cfg, self.device)
-            self._prepare_gat(gat_state)
-            self.mlp = self._prepare_mlp(mlp_state) if mlp_state is not None else None
+            self.gat = self.prepare_gat(gat_state) if gat_state is not None else None
+            self.mlp = self.prepare_mlp(mlp_state) if mlp_state is not None else None
             torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ workspace
@@ -188,11 +189,11 @@ class PosePipeline:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _prepare_gat(self, st):
+    def prepare_gat(self, st):
         """Split every projection into planes; fold the attention vectors into fc2 as 2*heads extra output
         rows: a1[n,h] = sum_d ft2[n,h,d]*attn_l[h,d] = h2[n,:] . (sum_d attn_l[h,d]*W2[hD+d,:]) + bias term
         (gat2.py:55-58), so one GEMM yields [ft2 | a1 | a2]."""
-        self.gat = []
+        layers = []
         n_layers = len([k for k in st if k.endswith('fc1.weight')])
         for l in range(n_layers):
             g = lambda k: st['layers.%d.%s' % (l, k)].detach().to('cpu', torch.float64)
@@ -211,12 +212,13 @@ class PosePipeline:
             W2e = torch.cat([W2, Wl, Wr], 0).float().to(self.device)
             b2e = torch.cat([b2, bl, br], 0).float().to(self.device)
             s = self._stream()
-            self.gat.append(dict(
+            layers.append(dict(
                 din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4),
                 w1=Planes.from_f32(W1.float().to(self.device), s), b1=b1.float().to(self.device),
                 w2=Planes.from_f32(W2e, s), b2=b2e))
+        return layers
 
-    def _prepare_mlp(self, st):
+    def prepare_mlp(self, st):
         layers = []
         s = self._stream()
         for l in range(1, 18, 2):
@@ -260,17 +262,19 @@ class PosePipeline:
         return p
 
     def aggregate(self, db: DeviceBatch, g: GraphArrays, z: torch.Tensor, layer: dict, layer0: bool,
-                  raw: Optional[torch.Tensor], act: Optional[Planes], scores: Optional[torch.Tensor]):
+                  raw: Optional[torch.Tensor], act: Optional[Planes], scores: Optional[torch.Tensor],
+                  alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE):
         self.launches += 1
         check(self.L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
-                                            1 if layer0 else 0, db.max_heads, GAT_ALPHA, GAT_ACT_SLOPE, ptr(raw),
+                                            1 if layer0 else 0, db.max_heads, alpha, act_slope, ptr(raw),
                                             ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
                                             ptr(scores), self._stream()), 'gat_aggregate')
 
     # ------------------------------------------------------------------ stages
     def gat_forward(self, db: DeviceBatch, g: GraphArrays, x0: Optional[Planes] = None, dense_rows: bool = False,
-                    keep_layers: bool = False):
+                    keep_layers: bool = False, layers=None, alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE,
+                    final_sigmoid: bool = True):
         """GAT2.forward over the whole batch. By default layer 0 runs on the S+1 compact rows (every head
         plus the one shared edge-node row). With dense_rows=True, x0 holds one row per node (the drop-in
         GAT2.forward path, where the caller hands in an arbitrary feature matrix)."""
@@ -280,19 +284,25 @@ class PosePipeline:
             x0 = self.head_feature_planes(db)
         x, rows = x0, (N if dense_rows else S + 1)
         scores = torch.empty(max(N, 1), dtype=torch.float32, device=self.device)
-        for l, lay in enumerate(self.gat):
-            last = l == len(self.gat) - 1
+        layers = layers if layers is not None else self.gat
+        logits = torch.empty(max(N, 1), dtype=torch.float32, device=self.device) if not final_sigmoid else None
+        for l, lay in enumerate(layers):
+            last = l == len(layers) - 1
             h = self.planes_ws('gat_h', rows, lay['din'])
-            self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], GAT_ALPHA, out_planes=h)
+            self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], alpha, out_planes=h)
             z = self.f32_ws('gat_z', rows, lay['ldz'])
             self.linear(h, rows, lay['w2'], lay['b2'], lay['n2'], lay['din'], 1.0, out_f32=z)
             raw = torch.empty((max(N, 1), lay['hd']), dtype=torch.float32, device=self.device) if keep_layers else None
             act = None if last else self.planes_ws('gat_act%d' % (l & 1), N, lay['hd'])
-            self.aggregate(db, g, z, lay, layer0=(l == 0 and not dense_rows), raw=raw, act=act, scores=scores if last else None)
+            if last and not final_sigmoid and raw is None:
+                raw = logits.view(-1, 1)
+            self.aggregate(db, g, z, lay, layer0=(l == 0 and not dense_rows), raw=raw, act=act,
+                           scores=scores if (last and final_sigmoid) else None, alpha=alpha, act_slope=act_slope)
             if keep_layers:
                 raws.append(raw[:N])
             x, rows = act, N
-        return (scores[:N], raws) if keep_layers else scores[:N]
+        out = scores[:N] if final_sigmoid else raw.reshape(-1)[:N]
+        return (out, raws) if keep_layers else out
 
     def cluster(self, db: DeviceBatch, g: GraphArrays, scores: torch.Tensor):
         V = self.cfg.V_sm
@@ -338,18 +348,19 @@ class PosePipeline:
                                           ptr(xyz), ptr(mask), self._stream()), 'triangulate')
         return xyz[:P], mask[:P]
 
-    def mlp_forward(self, x: Planes, P: int, scale: float = 10.0) -> torch.Tensor:
+    def mlp_forward(self, x: Planes, P: int, scale: float = 10.0, layers=None, slope: float = MLP_SLOPE) -> torch.Tensor:
         """PoseEstimatorMLP.forward (utils/mlp.py:8-31); `scale` is the x10 the callers apply
         (metrics_from_model.py:282), fused into the last epilogue."""
-        n_out = self.mlp[-1]['n']
+        layers = layers if layers is not None else self.mlp
+        n_out = layers[-1]['n']
         out = self.f32_ws('mlp_out', P, round_up(n_out, 4))          # TMA store needs a 16-byte row pitch
-        for i, lay in enumerate(self.mlp):
-            last = i == len(self.mlp) - 1
+        for i, lay in enumerate(layers):
+            last = i == len(layers) - 1
             if last:
                 self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out)
             else:
                 y = self.planes_ws('mlp_y%d' % (i & 1), P, lay['n'])
-                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], MLP_SLOPE, out_planes=y)
+                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], slope, out_planes=y)
                 x = y
         return out[:P, :n_out]
 

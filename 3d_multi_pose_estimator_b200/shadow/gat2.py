@@ -1,0 +1,105 @@
+"""Drop-in for the reference's skeleton_matching/gat2.py (GraphAttention2 :17-88, GAT2 :90-154).
+
+Same constructors, parameter names (state_dict keys `layers.{l}.{attn_l,attn_r,fc1.*,fc2.*[,res_fc.*]}`) and
+initialisation order; `forward` runs on the B200 kernels (split-bf16 tcgen05 projections + the fused
+edge-softmax/aggregation kernel) instead of DGL. Inference only: dropout must be 0, no residual.
+"""
+import torch
+import torch.nn as nn
+
+import _b200pose_runtime as rt
+
+
+class GraphAttention2(nn.Module):
+    def __init__(self, g, in_dim, out_dim, num_heads, feat_drop, attn_drop, alpha, residual=False, name=None, bias=False):
+        super(GraphAttention2, self).__init__()
+        self.g = g
+        self.num_heads = num_heads
+        self.name = name
+        self.fc1 = nn.Linear(in_dim, in_dim, bias=bias)
+        self.fc2 = nn.Linear(in_dim, num_heads * out_dim, bias=bias)
+        self.feat_drop_p = feat_drop
+        self.attn_drop_p = attn_drop
+        self.attn_l = nn.Parameter(torch.Tensor(size=(num_heads, out_dim, 1)))
+        self.attn_r = nn.Parameter(torch.Tensor(size=(num_heads, out_dim, 1)))
+        nn.init.xavier_normal_(self.fc1.weight.data, gain=1.414)
+        nn.init.xavier_normal_(self.fc2.weight.data, gain=1.414)
+        nn.init.xavier_normal_(self.attn_l.data, gain=1.414)
+        nn.init.xavier_normal_(self.attn_r.data, gain=1.414)
+        self.alpha = alpha
+        self.leaky_relu = nn.LeakyReLU(alpha)
+        self.residual = residual
+        if residual:
+            if in_dim != out_dim:
+                self.res_fc = nn.Linear(in_dim, num_heads * out_dim, bias=bias)
+                nn.init.xavier_normal_(self.res_fc.weight.data, gain=1.414)
+            else:
+                self.res_fc = None
+
+    def forward(self, inputs):
+        raise NotImplementedError('GraphAttention2 layers are executed by GAT2.forward on the B200 path')
+
+
+class GAT2(nn.Module):
+    def __init__(self, g, num_layers, in_dim, num_classes, num_hidden, heads, activation, final_activation, feat_drop,
+                 attn_drop, alpha, residual, bias=False):
+        super(GAT2, self).__init__()
+        self.g = g
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList()
+        self.activation = activation
+        self.final_activation = final_activation
+        self.alpha = alpha
+        self.layers.append(GraphAttention2(g, in_dim, num_hidden[0], heads[0], feat_drop, attn_drop, alpha, False, '0', bias))
+        for l in range(1, num_layers - 1):
+            self.layers.append(GraphAttention2(g, num_hidden[l - 1] * heads[l - 1], num_hidden[l], heads[l], feat_drop,
+                                               attn_drop, alpha, residual, str(l), bias))
+        self.layers.append(GraphAttention2(g, num_hidden[-1] * heads[-1], num_classes, 1, feat_drop, attn_drop, alpha,
+                                           residual, 'X', bias))
+        self._prepared = None
+        self._prepared_key = None
+
+    def set_g(self, g):
+        self.g = g
+        for l in range(self.num_layers):
+            self.layers[l].g = g
+
+    def _check_supported(self):
+        for lyr in self.layers:
+            if lyr.feat_drop_p or lyr.attn_drop_p:
+                raise NotImplementedError('B200 GAT2 is inference-only: feat_drop/attn_drop must be 0')
+            if lyr.residual:
+                raise NotImplementedError('B200 GAT2: residual connections are not implemented')
+        if not isinstance(self.activation, nn.LeakyReLU):
+            raise NotImplementedError('B200 GAT2: the inter-layer activation must be nn.LeakyReLU')
+        if self.final_activation is not None and not isinstance(self.final_activation, nn.Sigmoid):
+            raise NotImplementedError('B200 GAT2: final_activation must be nn.Sigmoid or None')
+        if self.layers[-1].fc2.out_features != 1:
+            raise NotImplementedError('B200 GAT2: num_classes must be 1')
+
+    def _weights(self, ctx):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._prepared is None or key != self._prepared_key:
+            self._prepared = ctx.prepare_gat({k: v for k, v in self.state_dict().items()})
+            self._prepared_key = key
+        return self._prepared
+
+    def forward(self, inputs, g):
+        self.set_g(g)
+        self._check_supported()
+        ctx = rt.context()
+        if not hasattr(g, '_b200'):
+            raise TypeError('GAT2.forward needs a graph built by the B200 graph_generator drop-in')
+        db, arrays = g._b200
+        layers = self._weights(ctx)
+        feats = g.ndata['h']
+        if inputs.data_ptr() == feats.data_ptr() or (inputs.shape == feats.shape and inputs.device == feats.device
+                                                     and torch.equal(inputs, feats)):
+            x0, dense = None, False                # the graph's own features: layer 0 runs on the S+1 compact rows
+        else:
+            x0 = rt.pipeline.Planes.from_f32(inputs.to(ctx.device).float(), ctx._stream())
+            dense = True
+        out = ctx.gat_forward(db, arrays, x0=x0, dense_rows=dense, layers=layers, alpha=self.alpha,
+                              act_slope=self.activation.negative_slope,
+                              final_sigmoid=self.final_activation is not None)
+        return out.clone().reshape(-1, 1, 1)
