@@ -23,6 +23,7 @@ struct AggParams {
     float* raw_f32; __nv_bfloat16* act_hi; __nv_bfloat16* act_lo; int ld_planes;
     int stage_rows;     // z rows of shared memory available per CTA for staging
     int chunk;          // destination nodes per CTA (work unit = frame x chunk)
+    int n_chunks;       // chunks per frame (grid = n_frames * n_chunks)
     int max_deg;        // largest in-degree (sizes the per-warp attention scratch)
 };
 
@@ -39,10 +40,12 @@ template <int VEC, int KMAX>
 __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams p)
 {
     extern __shared__ __align__(16) float smem_f[];
-    const int b = blockIdx.x;
+    // chunk index fastest: the CTAs working on one frame run together, so the z rows of a frame that several of
+    // them gather (every edge-node row is read by itself and by its two heads) are served from L2
+    const int b = blockIdx.x / p.n_chunks;
     const int n0 = p.node_off[b];
     const int Nb = p.node_off[b + 1] - n0;
-    const int v_begin = blockIdx.y * p.chunk;
+    const int v_begin = (blockIdx.x - b * p.n_chunks) * p.chunk;
     if (v_begin >= Nb) return;
     const int v_end = min(Nb, v_begin + p.chunk);
     const int h0 = p.head_off[b];
@@ -254,9 +257,11 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     const int max_nodes = mh + (mh * mh) / 2;
     p.chunk = 6 * kAggWarps;                                   // 48 destinations per CTA
     const int n_chunks = ceil_div(max_nodes, p.chunk);
+    p.n_chunks = n_chunks;
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
     const int n_vec = HD / vec;
-    dim3 grid(n_frames, n_chunks);
+    B2_CHECK_ARG((long long)n_frames * n_chunks < 2147483647LL, "gat_aggregate: batch too large for one launch");
+    dim3 grid((unsigned)(n_frames * n_chunks));
     auto launch = [&](auto kern) -> int {
         B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, kAggWarps * 32, smem, st>>>(p);

@@ -300,6 +300,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 struct GemmParams2 {
     int M, N, num_kb;
     int tiles_m, tiles_n, panels_total;      // 64-column output panels
+    int group_n;                             // consecutive n-tiles of one m-tile a CTA processes per visit
     int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
     const float* bias; float slope, out_scale;
     int has_f32, has_planes;
@@ -307,6 +308,28 @@ struct GemmParams2 {
 };
 
 struct TileInfo { int m0, n0, bn; };
+// Tile walk of one CTA. Work is dealt out in "visits": visit s covers group_n consecutive n-tiles of one
+// m-tile, and CTA c takes visits c, c + grid, ... With group_n == tiles_n (tall GEMMs: many m-tiles) a CTA
+// sweeps every n-tile of an m-tile back to back, so the A tile is fetched from HBM once and re-read from L2
+// microseconds later; with group_n == 1 (wide GEMMs: few m-tiles) the walk is the plain n-fastest order.
+struct TileWalk {
+    int visit, j, groups_per_m, total_visits;
+    __device__ __forceinline__ TileWalk(const GemmParams2& p) {
+        groups_per_m = (p.tiles_n + p.group_n - 1) / p.group_n;
+        total_visits = p.tiles_m * groups_per_m;
+        visit = blockIdx.x; j = 0;
+    }
+    __device__ __forceinline__ bool valid() const { return visit < total_visits; }
+    __device__ __forceinline__ int tile(const GemmParams2& p) const {
+        const int mb = visit / groups_per_m, g = visit - mb * groups_per_m;
+        return mb * p.tiles_n + g * p.group_n + j;
+    }
+    __device__ __forceinline__ void next(const GemmParams2& p) {
+        const int g = visit % groups_per_m;
+        ++j;
+        if (j >= p.group_n || g * p.group_n + j >= p.tiles_n) { j = 0; visit += gridDim.x; }
+    }
+};
 __device__ __forceinline__ TileInfo tile_info(const GemmParams2& p, int tile) {
     const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
     const int base = p.panels_total / p.tiles_n, rem = p.panels_total % p.tiles_n;
@@ -331,7 +354,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.tiles_m * p.tiles_n;
     const uint32_t a_bytes = kBM * kBK * 2;                                  // 16 KB per plane
     const uint32_t b_bytes = (uint32_t)p.stage_bn * kBK * 2;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
@@ -359,8 +381,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         // ================= TMA producer =================
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const TileInfo t = tile_info(p, tile);
+            for (TileWalk w(p); w.valid(); w.next(p)) {
+                const TileInfo t = tile_info(p, w.tile(p));
                 const uint32_t tx = 2 * a_bytes + 2 * (uint32_t)t.bn * kBK * 2;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
@@ -382,8 +404,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         // ================= MMA issuer =================
         if (lane == 0) {
             int it = 0, i = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-                const TileInfo t = tile_info(p, tile);
+            for (TileWalk w(p); w.valid(); w.next(p), ++i) {
+                const TileInfo t = tile_info(p, w.tile(p));
                 const uint32_t idesc = make_idesc(t.bn);
                 const int a = i & 1;
                 mbar_wait(smem_u32(&bar_acc_empty[a]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
@@ -411,8 +433,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         const uint32_t row_off = (uint32_t)lane * 128u;
         int i = 0;
         bool stores_pending = false;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-            const TileInfo t = tile_info(p, tile);
+        for (TileWalk w(p); w.valid(); w.next(p), ++i) {
+            const TileInfo t = tile_info(p, w.tile(p));
             const int a = i & 1;
             mbar_wait(smem_u32(&bar_acc_full[a]), (uint32_t)(i >> 1) & 1u);
             tcgen05_fence_after();
@@ -763,8 +785,10 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         if ((rc = make_map_ex(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, m, ld_planes, ld_planes, 64, 32))) return rc;
         if ((rc = make_map_ex(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, m, ld_planes, ld_planes, 64, 32))) return rc;
     }
-    const int total_tiles = q.tiles_m * q.tiles_n;
-    const int grid2 = total_tiles < num_sms() ? total_tiles : num_sms();
+    // tall GEMMs (GAT projections: thousands of m-tiles, 1-2 n-tiles): sweep the n-tiles of an m-tile inside one CTA
+    q.group_n = (q.tiles_m >= 2 * num_sms()) ? q.tiles_n : 1;
+    const int total_visits = q.tiles_m * ceil_div(q.tiles_n, q.group_n);
+    const int grid2 = total_visits < num_sms() ? total_visits : num_sms();
     B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_split_tc2_kernel<<<grid2, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q);
     B2_CHECK_LAUNCH();

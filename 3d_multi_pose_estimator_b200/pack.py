@@ -77,6 +77,22 @@ def edge_nodes_of_groups(sizes: Sequence[int]) -> int:
     return (s * s - int(sum(n * n for n in sizes))) // 2
 
 
+def pack_skeleton(sk: dict):
+    """One skeleton dict {"<joint>": [joint, x, y, valid, prob]} -> (xy [18,2] f64, vp [18,2] f32, joint mask).
+    The "ID" key is ignored (graph_generator.py:483, pose_estimator_dataset_from_json.py:73,255)."""
+    a = np.zeros((N_JOINTS, 2), dtype=np.float64)
+    b = np.zeros((N_JOINTS, 2), dtype=np.float32)
+    m = 0
+    for j, v in sk.items():
+        if j == "ID":
+            continue
+        ji = int(j)
+        a[ji, 0] = v[1]; a[ji, 1] = v[2]
+        b[ji, 0] = v[3]; b[ji, 1] = v[4]
+        m |= 1 << ji
+    return a, b, m
+
+
 def pack_frames(frames: Sequence[Dict[str, list]], cfg: CameraConfig, keep_json: bool = True) -> PackedBatch:
     """frames: reference frame dicts {camera: [json_string | list_of_skeletons, ...]}.
 
@@ -100,16 +116,7 @@ def pack_frames(frames: Sequence[Dict[str, list]], cfg: CameraConfig, keep_json:
                 skeletons = json.loads(skeletons)
             n = 0
             for idx, sk in enumerate(skeletons):
-                a = np.zeros((N_JOINTS, 2), dtype=np.float64)
-                b = np.zeros((N_JOINTS, 2), dtype=np.float32)
-                m = 0
-                for j, v in sk.items():
-                    if j == "ID":
-                        continue
-                    ji = int(j)
-                    a[ji, 0] = v[1]; a[ji, 1] = v[2]
-                    b[ji, 0] = v[3]; b[ji, 1] = v[4]
-                    m |= 1 << ji
+                a, b, m = pack_skeleton(sk)
                 if m == 0:
                     continue
                 xy.append(a); vp.append(b); mask.append(m); cam.append(c)

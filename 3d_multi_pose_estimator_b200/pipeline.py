@@ -304,13 +304,14 @@ class PosePipeline:
         out = scores[:N] if final_sigmoid else raw.reshape(-1)[:N]
         return (out, raws) if keep_layers else out
 
-    def cluster(self, db: DeviceBatch, g: GraphArrays, scores: torch.Tensor):
+    def cluster(self, db: DeviceBatch, g: GraphArrays, scores: torch.Tensor, threshold: Optional[float] = None):
         V = self.cfg.V_sm
+        thr = self.threshold if threshold is None else float(threshold)
         person_heads = torch.empty((max(db.n_heads, 1), V), dtype=torch.int32, device=self.device)
         n_persons = torch.empty(max(db.n_frames, 1), dtype=torch.int32, device=self.device)
         self.launches += 1
         check(self.L.b200pose_cluster(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(g.pairs), ptr(g.node_cam), ptr(scores),
-                                      V, self.threshold, self.cfg.min_number_of_views, db.max_heads, db.max_enodes,
+                                      V, thr, self.cfg.min_number_of_views, db.max_heads, db.max_enodes,
                                       ptr(person_heads), ptr(n_persons), self._stream()), 'cluster')
         return person_heads, n_persons[: db.n_frames]
 
@@ -347,6 +348,51 @@ class PosePipeline:
         check(self.L.b200pose_triangulate(P, ptr(person_sk), ptr(db.sk_xy), ptr(db.sk_mask), self.cams.ref, self.cfg.median_axis,
                                           ptr(xyz), ptr(mask), self._stream()), 'triangulate')
         return xyz[:P], mask[:P]
+
+    def encode_person_dicts(self, persons: List[Dict[str, dict]]):
+        """MLP input rows for persons given as {camera_name: skeleton dict} (the `raw_input` the reference's
+        drivers hand to PoseEstimatorDataset, test/metrics_from_model.py:243-266). Returns (x [P, 252*V] fp32
+        on the device, valid [P] bool list)."""
+        from .pack import pack_skeleton
+        names = self.cfg.camera_names
+        xy, vp, mask = [], [], []
+        person_sk = np.full((max(len(persons), 1), self.cfg.n_cameras), -1, np.int32)
+        for p, person in enumerate(persons):
+            for cam, sk in person.items():
+                a, b, m = pack_skeleton(sk)
+                person_sk[p, names.index(cam)] = len(xy)
+                xy.append(a); vp.append(b); mask.append(m)
+        S = len(xy)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device)
+        sk_xy = up(np.stack(xy) if S else np.zeros((1, N_JOINTS, 2)), torch.float64)
+        sk_vp = up(np.stack(vp) if S else np.zeros((1, N_JOINTS, 2), np.float32), torch.float32)
+        sk_mask = up(np.array(mask if S else [0], dtype=np.uint32).view(np.int32), torch.int32)
+        P = len(persons)
+        psk = up(person_sk, torch.int32)
+        valid = torch.empty(max(P, 1), dtype=torch.uint8, device=self.device)
+        xf = torch.zeros((max(P, 1), self.cfg.mlp_in), dtype=torch.float32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_encode_persons(P, ptr(psk), ptr(sk_xy), ptr(sk_vp), ptr(sk_mask), self.cams.ref,
+                                             ptr(xf), self.cfg.mlp_in, None, None, 0, ptr(valid), self._stream()), 'encode_persons')
+        return xf[:P], [bool(v) for v in valid[:P].cpu().tolist()]
+
+    def triangulate_tables(self, k64, dist64, p64, sk_xy, sk_mask, median_axis: int):
+        """triangulate() with caller-supplied camera tables (utils/pose_estimator_utils.py:52-75): one person whose
+        skeleton in camera i is row i of sk_xy [C,18,2] / sk_mask [C]. Returns ([18,3] float64, [18] mask) on the host."""
+        Cn = int(k64.shape[0])
+        if Cn > 32:
+            raise ValueError('at most 32 cameras')
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device)
+        t = dict(k=up(k64, torch.float64), d=up(dist64, torch.float64), p=up(p64, torch.float64),
+                 xy=up(sk_xy, torch.float64), m=up(np.asarray(sk_mask, dtype=np.uint32).view(np.int32), torch.int32),
+                 psk=torch.arange(Cn, dtype=torch.int32, device=self.device).reshape(1, Cn))
+        cams = Cameras(Cn, 0, 0, 0.0, 0.0, None, None, None, None, t['k'].data_ptr(), t['d'].data_ptr(), t['p'].data_ptr())
+        xyz = torch.empty((1, N_JOINTS, 3), dtype=torch.float64, device=self.device)
+        mask = torch.empty((1, N_JOINTS), dtype=torch.uint8, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_triangulate(1, ptr(t['psk']), ptr(t['xy']), ptr(t['m']), C.byref(cams), int(median_axis),
+                                          ptr(xyz), ptr(mask), self._stream()), 'triangulate')
+        return xyz[0].cpu().numpy(), mask[0].cpu().numpy()
 
     def mlp_forward(self, x: Planes, P: int, scale: float = 10.0, layers=None, slope: float = MLP_SLOPE) -> torch.Tensor:
         """PoseEstimatorMLP.forward (utils/mlp.py:8-31); `scale` is the x10 the callers apply

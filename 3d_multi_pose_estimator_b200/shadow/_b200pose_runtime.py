@@ -5,6 +5,10 @@ with cwd = <reference>/test (test/metrics_from_model.py:12,17,23). Put THIS dire
 (e.g. PYTHONPATH=<repo>/3d_multi_pose_estimator_b200/shadow) and the same imports resolve to the B200 path:
 gat2, graph_generator, mlp, pose_estimator_utils, skeleton_matching_utils, pose_estimator_dataset_from_json.
 `parameters` (and the pickled TransformManager it points to) stay the reference's own.
+
+Configuration lookup order: an explicit `set_config(CameraConfig)` (tests, embedding applications), else the
+reference's `parameters.parameters` namedtuple + pickle exactly as the reference modules read them at import
+time (skeleton_matching/graph_generator.py:24,32; utils/pose_estimator_dataset_from_json.py:4,28).
 """
 import importlib
 import os
@@ -13,8 +17,6 @@ import sys
 _REPO = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..'))
 if _REPO not in sys.path:
     sys.path.insert(0, _REPO)
-sys.path.append('../')                      # same lookup the reference modules do for `parameters`
-from parameters import parameters           # noqa: E402
 
 pkg = importlib.import_module('3d_multi_pose_estimator_b200')
 pipeline = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
@@ -22,13 +24,31 @@ pack = importlib.import_module('3d_multi_pose_estimator_b200.pack')
 
 _cfg = None
 _ctx = None
+_parameters = None
+
+
+def parameters():
+    """The reference's `parameters.parameters` namedtuple (looked up like the reference modules do)."""
+    global _parameters
+    if _parameters is None:
+        if 'parameters' not in sys.modules and '../' not in sys.path:
+            sys.path.append('../')
+        _parameters = importlib.import_module('parameters').parameters
+    return _parameters
+
+
+def set_config(cfg):
+    """Use an explicit CameraConfig instead of the reference's `parameters` module. Resets the device context."""
+    global _cfg, _ctx
+    _cfg = cfg
+    _ctx = None
 
 
 def config():
     """CameraConfig built from the reference's `parameters` + pickle, once."""
     global _cfg
     if _cfg is None:
-        _cfg = pkg.CameraConfig.from_parameters(parameters)
+        _cfg = pkg.CameraConfig.from_parameters(parameters())
     return _cfg
 
 

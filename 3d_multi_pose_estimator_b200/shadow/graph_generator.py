@@ -1,0 +1,248 @@
+"""Drop-in for the reference's skeleton_matching/graph_generator.py, inference side.
+
+Same public names: `MergedMultipleHumansDataset` (:516-916), `HumanGraphFromView` (:214-508), `graphData` (:21).
+`MergedMultipleHumansDataset(frame_dict | [json paths], mode='test', alt='3')` builds, on the GPU and without
+DGL, exactly the graph `process_test` builds (:813-876): heads in frame-dict camera order, one edge-node per
+cross-camera skeleton pair wired with 5 directed edges, alternative-'3' node features bit-exact in fp32. The
+graph object it hands out offers the slice of the DGL API the reference's callers use (`.to`, `.ndata['h']`,
+`.edata`, `.edges()`, `.nodes()`, `.number_of_nodes()`), and carries the CSR the B200 GAT2 / clustering
+drop-ins consume.
+
+Out of scope (raise NotImplementedError): training-set synthesis (`mode != 'test'`, :672-810), graph
+alternatives '1' and '2' (unused by the shipped configuration, parameters.py:76) and the DGL cache files.
+"""
+import json
+import sys
+from collections import namedtuple
+
+import numpy as np
+import torch
+import torch as th
+
+import _b200pose_runtime as rt
+
+graphData = namedtuple('graphData', ['src_nodes', 'dst_nodes', 'n_nodes', 'features', 'edge_types', 'edge_norms'])
+
+if th.cuda.is_available() is True:
+    device = th.device('cuda')
+else:
+    device = th.device('cpu')
+
+_COCO18 = ["nose", "left_eye", "right_eye", "left_ear", "right_ear", "left_shoulder", "right_shoulder", "left_elbow",
+           "right_elbow", "left_wrist", "right_wrist", "left_hip", "right_hip", "left_knee", "right_knee", "left_ankle",
+           "right_ankle", "neck"]
+JOINTS_TYPES = {str(i): n for i, n in enumerate(_COCO18)}
+NODE_TYPES_ONE_HOT = ['head', 'edge_node'] + _COCO18
+JOINT_METRIC_FEATURES = ['i_coordinate', 'j_coordinate', 'valid2D', 'probability']
+OTHER_FEATURES = ['n_joints']
+_PER_JOINT = {'2': ['_i', '_j', '_valid', '_prob'],
+              '3': ['_i', '_j', '_valid', '_prob', '_line_pX', '_line_pY', '_line_pZ', '_line_vX', '_line_vY', '_line_vZ']}
+_FEATURES = {}
+# every alternative of the reference keeps the same three relation types for the matching graph (:196-211)
+RELATIONS = {'2': ['h_h', 'link', 'link_link'], '3': ['h_h', 'link', 'link_link']}
+
+
+def _features(alt):
+    """Feature-name vocabulary of an alternative (graph_generator.py:116-140); only its length and the positions
+    of 'head' / 'edge_node' matter to the callers (test/metrics_from_model.py:47)."""
+    if alt not in _FEATURES:
+        cams = list(rt.config().used_sm_names)
+        if alt == '1':
+            _FEATURES[alt] = NODE_TYPES_ONE_HOT + cams + JOINT_METRIC_FEATURES + OTHER_FEATURES
+        elif alt in _PER_JOINT:
+            _FEATURES[alt] = ['head', 'edge_node'] + [c + '_' + p + s for c in cams for p in _COCO18 for s in _PER_JOINT[alt]]
+        else:
+            raise KeyError(alt)
+    return _FEATURES[alt]
+
+
+def _frame_to_device(frame, keep_json=True):
+    ctx = rt.context()
+    pb = rt.pack.pack_frames([frame], ctx.cfg, keep_json=keep_json)
+    return ctx, pb, rt.pipeline.HostBatch(pb).to_device(ctx.device)
+
+
+class B200Graph:
+    """What `dgl.graph((src, dst), num_nodes, idtype=int32)` is to the reference's callers
+    (graph_generator.py:867-870), backed by device tensors produced by b200pose_build_graph /
+    b200pose_node_features."""
+
+    def __init__(self, db, arrays, feats):
+        self._b200 = (db, arrays)
+        self._n = db.n_nodes
+        self._e = db.n_edges
+        H = db.n_heads
+        rel = torch.ones(self._e, dtype=torch.int64, device=feats.device)
+        rel[:H] = 0                                             # RELATIONS['3'].index('h_h')
+        rel[H + 4::5] = 2                                       # every 5th edge of an edge-node: 'link_link'
+        self.ndata = {'h': feats}
+        self.edata = {'rel_type': rel, 'norm': torch.ones((self._e, 1), dtype=torch.float32, device=feats.device)}
+
+    def to(self, device, **kw):
+        return self                                             # tensors already live on the CUDA device
+
+    def edges(self):
+        _, arrays = self._b200
+        return arrays.src[: self._e], arrays.dst[: self._e]
+
+    def nodes(self):
+        return torch.arange(self._n, dtype=torch.int32, device=self.ndata['h'].device)
+
+    def number_of_nodes(self):
+        return self._n
+
+    num_nodes = number_of_nodes
+
+    def number_of_edges(self):
+        return self._e
+
+    num_edges = number_of_edges
+
+    @property
+    def device(self):
+        return self.ndata['h'].device
+
+
+class HumanGraphFromView:
+    joints = JOINTS_TYPES
+
+    def __init__(self, data, camera, alt):
+        self.labels = None
+        self.num_rels = -1
+        self.camera = camera
+        cfg = rt.config()
+        self.camera_idx = cfg.used_sm_names.index(self.camera)
+        if alt != '3':
+            if alt in ('1', '2'):
+                raise NotImplementedError('graph alternative %s is not part of the B200 path (parameters.graph_alternative is 3)' % alt)
+            print(f'Unknown network alternative {alt}')
+            sys.exit(-1)
+        # one head node with a self loop (initializeWithAlternative3, :444-508)
+        self.num_joints = len([j for j in data if j != "ID"])
+        self.n_nodes = 1
+        self.src_nodes, self.dst_nodes = [0], [0]
+        self.edge_types = [RELATIONS['3'].index('h_h')]
+        self.edge_norms = [[1.]]
+        if self.num_joints:
+            ctx, pb, db = _frame_to_device({camera: [[data]]}, keep_json=False)
+            self.features = ctx.node_features_f32(db)[:1].clone()
+        else:
+            self.features = torch.zeros((1, len(_features('3'))), dtype=torch.float32)
+            self.features[0, 0] = 1.
+        self.cam_from_root = torch.from_numpy(cfg.centre32(cfg.used_sm[self.camera_idx]))
+
+    @staticmethod
+    def get_node_types_one_hot():
+        return NODE_TYPES_ONE_HOT
+
+    @staticmethod
+    def get_cam_types():
+        return rt.config().used_sm_names
+
+    @staticmethod
+    def get_all_features(alt='1'):
+        return _features(alt)
+
+    @staticmethod
+    def get_joint_metric_features():
+        return JOINT_METRIC_FEATURES
+
+    @staticmethod
+    def get_other_features():
+        return OTHER_FEATURES
+
+    @staticmethod
+    def get_rels(alt='1'):
+        if alt not in RELATIONS:
+            raise NotImplementedError('relation vocabulary of alternative %s is not part of the B200 path' % alt)
+        return RELATIONS[alt]
+
+
+class MergedMultipleHumansDataset:
+    path_save = 'cache/'
+
+    def __init__(self, paths, probabilities=[1.], limit='100000000', alt=None, mode='train', force_reload=False,
+                 verbose=True, debug=False, raw_dir='.'):
+        if alt is None:
+            print('Alt is None')
+            sys.exit(-1)
+        self.inputs = []
+        if type(paths) == list:
+            if mode != 'test':
+                raise NotImplementedError('the B200 graph generator is inference-only (mode="test")')
+            for path in paths:
+                print('PATH', path)
+                self.inputs.append(json.loads(open(path, "rb").read()))
+        elif type(paths) == dict:
+            self.inputs.append(paths)
+        else:
+            raise Exception('Unhandled type for MergedMultipleHumansDataset')
+        if mode != 'test':
+            raise NotImplementedError('the B200 graph generator is inference-only (mode="test")')
+        if alt != '3':
+            raise NotImplementedError('graph alternative %s is not part of the B200 path' % alt)
+        self.name = "MergedMultipleHumansDataset"
+        self.probabilities = probabilities
+        self.mode = mode
+        self.alt = alt
+        self.graphs = []
+        self.labels = []
+        self.data = dict()
+        self.data['edge_nodes_indices'] = []
+        self.data['nodes_camera'] = []
+        self.debug = debug
+        self.force_reload = True
+        self.device = device
+        self.limit = limit
+        self.verbose = verbose
+        self.jsons_for_head = dict()
+        self.skeleton_index = dict()
+        self.process()
+
+    def process(self):
+        self.process_test()
+
+    def process_test(self):
+        assert len(self.inputs) == 1, "For testing, please provide __ONE__ single JSON file"
+        iterate_over = self.inputs[0] if type(self.inputs[0]) == list else self.inputs
+        names = rt.config().used_sm_names
+        idx = 0
+        for json_view in iterate_over:
+            if idx % 1000 == 0 and idx > 0:
+                print(idx)
+            if idx == self.limit:
+                break
+            idx += 1
+            ctx, pb, db = _frame_to_device(json_view)
+            # like the reference, the head bookkeeping always reflects the last frame seen (:573-605)
+            self.jsons_for_head = dict(enumerate(pb.skeletons[0]))
+            self.skeleton_index = dict(enumerate(pb.skeleton_index[0]))
+            H, N = db.n_heads, db.n_nodes
+            if N == H:                                          # no cross-camera pair: no graph (:866)
+                continue
+            arrays = ctx.build_graph(db, with_coo=True)
+            feats = ctx.node_features_f32(db)
+            self.graphs.append(B200Graph(db, arrays, feats))
+            self.labels.append(th.zeros((N - H, 1), dtype=th.float64))
+            self.data['edge_nodes_indices'].append(th.arange(H, N, dtype=th.int64).unsqueeze(1))
+            self.data['nodes_camera'].append([names[rt.config().used_sm.index(int(c))] for c in pb.sk_cam] + [''] * (N - H))
+
+    def __getitem__(self, idx):
+        return self.graphs[idx], self.labels[idx], self.data['edge_nodes_indices'][idx], self.data['nodes_camera'][idx]
+
+    def __len__(self):
+        return len(self.graphs)
+
+    def get_dataset_name(self):
+        graphs_path = self.name + '_' + self.mode + '_alt_' + self.alt + '_s_' + str(self.limit) + '.bin'
+        info_path = self.name + '_info_' + self.mode + '_alt_' + self.alt + '_s_' + str(self.limit) + '.pkl'
+        return graphs_path, info_path
+
+    def has_cache(self):
+        return False
+
+    def save(self):                                             # the reference skips the cache in test mode (:885)
+        return
+
+    def download(self):
+        pass

@@ -1,0 +1,71 @@
+"""Drop-in for the reference's utils/pose_estimator_dataset_from_json.py, inference side
+(PoseEstimatorDataset dict branch :237-298, get_3D_from_triangulation :63-101, get_skeleton_indices :49-61).
+
+The per-person MLP input (252 floats per used camera: 2D keypoints, camera centre, back-projected ray of the
+undistorted point, pairwise-DLT 3D hint) is produced by b200pose_encode_persons. The list-of-files branch
+(:146-236) builds training sets and is out of scope.
+"""
+import json
+
+import numpy as np
+import torch
+
+import _b200pose_runtime as rt
+
+numbers_per_joint = 14
+
+
+def get_skeleton_indices(input_data):
+    """Per camera, the skeleton with the most joint entries (first maximum), :49-61."""
+    out = {}
+    for c, payload in input_data.items():
+        skeletons = json.loads(payload[0])
+        best, best_n = 0, -1
+        for i, s in enumerate(skeletons):
+            if len(s) > best_n:
+                best, best_n = i, len(s)
+        out[c] = best
+    return out
+
+
+class PoseEstimatorDataset(torch.utils.data.Dataset):
+    def __init__(self, input_data, cameras, joint_list, transform=None, data_augmentation=False, reload=False,
+                 save=False, device=None):
+        self.transform = transform
+        self.data_augmentation = data_augmentation
+        self.numbers_per_joint = numbers_per_joint
+        self.data = []
+        self.orig_data = []
+        if type(input_data) is list:
+            raise NotImplementedError('the B200 PoseEstimatorDataset is inference-only (dict input); '
+                                      'training-set construction from JSON files is out of scope')
+        if type(input_data) is not dict:
+            raise Exception(f'Invalid dataset input {type(input_data)} for json_files. Only list and dict are allowed.')
+        ctx = rt.context()
+        cfg = ctx.cfg
+        indices = get_skeleton_indices(input_data)
+        person = {}
+        for c in input_data:                                     # one skeleton per camera (:249-254)
+            if c in cfg.used_pe_names:
+                skeletons = json.loads(input_data[c][0])
+                if skeletons:
+                    person[c] = skeletons[indices[c]]
+        x, valid = ctx.encode_person_dicts([person])
+        if valid[0]:
+            self.data.append(x[0])
+        # torch.stack([]) raises in the reference when nothing was kept (:287-298); keep that behaviour
+        self.data = torch.stack(self.data)
+        self.orig_data = self.data
+        if device is not None:
+            self.data = self.data.to(device=device)
+            self.orig_data = self.data
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def __getitem__(self, idx):
+        ret1 = self.data[idx]
+        ret2 = self.orig_data[idx]
+        if self.transform:
+            ret1 = self.transform(ret1)
+        return ret1, ret2
