@@ -42,8 +42,8 @@ def lib():
         L.b200pose_node_features.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp]
         L.b200pose_linear.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, f32, vp, i32, vp, vp, i32, i32, vp]
         L.b200pose_split_planes.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
-        L.b200pose_gat_aggregate.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32,
-                                             vp, vp, vp, i32, vp, vp]
+        L.b200pose_gat_aggregate.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32,
+                                             vp, vp, vp, i32, vp, i32, vp]
         L.b200pose_cluster.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, i32, i32, i32, vp, vp, vp]
         L.b200pose_encode_persons.argtypes = [i32, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp, vp]
         L.b200pose_triangulate.argtypes = [i32, vp, vp, vp, camp, i32, vp, vp, vp]

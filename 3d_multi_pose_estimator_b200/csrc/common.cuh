@@ -43,6 +43,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two fp32 -> packed (hi, hi) and (lo, lo) bf16x2 words (element 0 in the low half): same rounding as split_bf16,
+// but one packed convert per pair and the hi values recovered by bit operations
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ float leaky(float x, float slope) { return x >= 0.f ? x : x * slope; }
+// LeakyReLU for 0 <= slope <= 1: max(x, slope*x) (two instructions, no predicate)
+__device__ __forceinline__ float leaky_le1(float x, float slope) { return fmaxf(x, x * slope); }
 
 }  // namespace b200pose

@@ -39,7 +39,7 @@ constexpr int kAggWarps = 8;
 template <int VEC, int KMAX>
 __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams p)
 {
-    extern __shared__ __align__(16) float smem_f[];
+    extern __shared__ __align__(128) float smem_f[];
     // chunk index fastest: the CTAs working on one frame run together, so the z rows of a frame that several of
     // them gather (every edge-node row is read by itself and by its two heads) are served from L2
     const int b = blockIdx.x / p.n_chunks;
@@ -181,6 +181,327 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Frame-resident kernel (the product path whenever a frame's plan fits in shared memory).
+//
+// One CTA (16 warps) per frame; every z row of the frame leaves HBM exactly once per layer:
+//   * the head rows are staged in shared memory for the whole frame;
+//   * the edge-node rows - one contiguous block of M_b rows - stream through a double-buffered
+//     shared-memory ring in chunks of kChunkRows rows, fetched by 1-D bulk async copies (cp.async.bulk,
+//     mbarrier complete_tx), so the copy of chunk c+1 overlaps the arithmetic on chunk c and costs no
+//     registers or issue slots;
+//   * for every chunk, warps take (a) the edge-node destinations of the chunk - warp per destination,
+//     two head rows + the node's own row, all from shared memory - and (b) the contributions of the chunk's
+//     rows to the head destinations they own (warp w owns heads w and w+16; the accumulators of a head stay
+//     in registers across chunks, its in-edge list is walked in ascending edge id).
+// Lanes own VEC consecutive columns of KMAX column groups, so every row access is a coalesced vector sweep.
+// The summation order per output element is ascending reference edge id, exactly as in the gather kernel.
+//   phase 1: stage a1|a2 of every node, head rows, in-edge lists; thread per (destination, attention head)
+//            computes the softmax weights of its in-edges (gat2.py:78-88) into shared memory
+//   phase 2: chunk loop as above
+// ------------------------------------------------------------------------------------------------
+constexpr int kFrameWarps = 16;
+constexpr int kFrameThreads = kFrameWarps * 32;
+constexpr int kFrameOwn = 2;                                // head destinations per warp
+constexpr int kChunkRows = 32;
+
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void agg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();      // a lost copy becomes an error, not a hang
+    }
+}
+__device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct FramePlan {          // shared-memory plan of one frame (element offsets into a float array)
+    int zh, ze, buf, w, a12, lists, total_floats;
+};
+
+__host__ __device__ inline FramePlan frame_plan(int max_heads, int max_enodes, int HD, int H, int ldz) {
+    FramePlan f;
+    const int hd4 = (HD + 3) & ~3;
+    int o = 0;
+    f.buf = o; o += 2 * kChunkRows * ldz;                               // bulk-copy destinations first: 16-byte aligned
+    f.zh = o; o += max_heads * hd4;
+    f.ze = o; o += hd4;                                                 // layer 0: the shared edge-node row
+    f.w = o; o += ((max_heads + 5 * max_enodes) * H + 3) & ~3;          // softmax weight of every in-edge, CSR order
+    f.a12 = o; o += ((max_heads + max_enodes) * 2 * H + 3) & ~3;        // a1|a2 of every node (phase 1)
+    f.lists = o; o += (max_heads + 5 * max_enodes + 3) & ~3;            // frame-local CSR column indices
+    f.total_floats = o;
+    return f;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC> __device__ __forceinline__ void store_out(const AggParams& p, bool slope_le1, int gv, int c0, const float (&v)[VEC]) {
+    if (p.raw_f32) {
+        float* o = p.raw_f32 + (size_t)gv * (p.heads * p.dim) + c0;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) o[q] = v[q];
+    }
+    if (p.act_hi) {
+        float a[VEC];
+        if (slope_le1) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) a[q] = leaky_le1(v[q], p.act_slope);
+        } else {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) a[q] = leaky(v[q], p.act_slope);
+        }
+        __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + c0;
+        __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + c0;
+        if constexpr (VEC == 4) {
+            uint32_t h0, l0, h1, l1;
+            split_pack2(a[0], a[1], h0, l0);
+            split_pack2(a[2], a[3], h1, l1);
+            *reinterpret_cast<uint2*>(oh) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(ol) = make_uint2(l0, l1);
+        } else if constexpr (VEC == 2) {
+            uint32_t h0, l0;
+            split_pack2(a[0], a[1], h0, l0);
+            *reinterpret_cast<uint32_t*>(oh) = h0;
+            *reinterpret_cast<uint32_t*>(ol) = l0;
+        } else {
+            __nv_bfloat16 h, l;
+            split_bf16(a[0], h, l);
+            oh[0] = h; ol[0] = l;
+        }
+    }
+}
+
+template <int VEC, int KMAX>
+__global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(AggParams p, int max_heads, int max_enodes)
+{
+    extern __shared__ __align__(128) float smem_f[];
+    __shared__ __align__(8) uint64_t bar_full[2];
+    const int b = blockIdx.x;
+    const int n0 = p.node_off[b];
+    const int Nb = p.node_off[b + 1] - n0;
+    if (Nb == 0) return;
+    const int h0 = p.head_off[b];
+    const int Hb = p.head_off[b + 1] - h0;
+    const int Mb = Nb - Hb;
+    const int Eb = Hb + 5 * Mb;
+    const int e0 = h0 + 5 * (n0 - h0);                      // first edge (CSR position) of the frame
+    const int H = p.heads, D = p.dim, HD = H * D, ldz = p.ldz;
+    const int hd4 = (HD + 3) & ~3;
+    const FramePlan f = frame_plan(max_heads, max_enodes, HD, H, ldz);
+    float* buf = smem_f + f.buf;
+    float* zh = smem_f + f.zh;
+    float* zE = smem_f + f.ze;
+    float* w = smem_f + f.w;
+    float* a12 = smem_f + f.a12;
+    int* lst = reinterpret_cast<int*>(smem_f + f.lists);    // col[e0 + i] - n0 for every in-edge position i of the frame
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool streamed = !p.layer0 && Mb > 0;
+    const int n_chunks = (Mb + kChunkRows - 1) / kChunkRows;
+    const uint32_t bar0 = agg_smem_u32(&bar_full[0]), bar1 = agg_smem_u32(&bar_full[1]);
+    const float* zen = p.z + (size_t)(n0 + Hb) * ldz;       // first edge-node row of the frame (not layer 0)
+    auto issue_chunk = [&](int c) {                         // one thread: bulk copy of chunk c into ring slot c & 1
+        const int rows = min(kChunkRows, Mb - c * kChunkRows);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)ldz * 4u;
+        const uint32_t bar = (c & 1) ? bar1 : bar0;
+        agg_mbar_expect_tx(bar, bytes);
+        agg_bulk_load(agg_smem_u32(buf + (size_t)(c & 1) * kChunkRows * ldz), zen + (size_t)c * kChunkRows * ldz, bytes, bar);
+    };
+    if (tid == 0) {
+        agg_mbar_init(bar0, 1);
+        agg_mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (streamed) {
+            issue_chunk(0);
+            if (n_chunks > 1) issue_chunk(1);
+        }
+    }
+    // z row of frame-local node l
+    auto zrow = [&](int l) -> const float* {
+        if (p.layer0) return p.z + (size_t)(l < Hb ? h0 + l : p.n_heads_total) * ldz;
+        return p.z + (size_t)(n0 + l) * ldz;
+    };
+    const int n_a12 = p.layer0 ? Hb + 1 : Nb;               // rows of a1|a2 staged (layer 0: heads + the shared row)
+    auto a12row = [&](int l) -> const float* { return a12 + (size_t)((p.layer0 && l > Hb) ? Hb : l) * 2 * H; };
+
+    // ---- phase 1a: stage a1|a2, the head rows, the shared row (layer 0) and the in-edge lists ----
+    for (int i = tid; i < n_a12 * 2 * H; i += kFrameThreads) {
+        const int r = i / (2 * H), c = i - r * 2 * H;
+        a12[i] = __ldg(zrow(r) + HD + c);
+    }
+    {
+        const int vec_per_row = hd4 / 4;                    // ldz % 4 == 0 and columns [HD, hd4) exist in the row (a1 follows)
+        const int rows = Hb + (p.layer0 ? 1 : 0);
+        for (int i = tid; i < rows * vec_per_row; i += kFrameThreads) {
+            const int r = i / vec_per_row, c = i - r * vec_per_row;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(zrow(r)) + c);
+            float* dstp = (r < Hb) ? zh + (size_t)r * hd4 : zE;
+            reinterpret_cast<float4*>(dstp)[c] = v;
+        }
+    }
+    for (int i = tid; i < Eb; i += kFrameThreads) lst[i] = __ldg(p.col + e0 + i) - n0;
+    __syncthreads();
+    // ---- phase 1b: softmax weights of every in-edge, per attention head (gat2.py:78-88) ----
+    const int enode_pos0 = Hb + 2 * Mb;                     // CSR: head rows first, then 3 in-edges per edge-node
+    for (int q = tid; q < Nb * H; q += kFrameThreads) {
+        const int v = q / H, hh = q - v * H;
+        int beg, deg;
+        if (v >= Hb) { beg = enode_pos0 + 3 * (v - Hb); deg = 3; }
+        else { beg = __ldg(p.row_ptr + n0 + v) - e0; deg = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg; }
+        const float a2v = a12row(v)[H + hh];
+        float* wv = w + (size_t)beg * H + hh;
+        float m = -INFINITY;
+        for (int i = 0; i < deg; ++i) {
+            const float e = leaky(a12row(lst[beg + i])[hh] + a2v, p.alpha);
+            wv[i * H] = e;
+            m = fmaxf(m, e);
+        }
+        float den = 0.f;
+        for (int i = 0; i < deg; ++i) {
+            const float e = expf(wv[i * H] - m);
+            wv[i * H] = e;
+            den += e;
+        }
+        for (int i = 0; i < deg; ++i) wv[i * H] = wv[i * H] / den;
+    }
+    __syncthreads();
+    // ---- phase 2: chunk loop ----
+    const int n_vec = HD / VEC;
+    using V = typename VecT<VEC>::type;
+    const bool slope_le1 = p.act_slope >= 0.f && p.act_slope <= 1.f;
+    int cj[KMAX], hj[KMAX];
+    bool okj[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+        const int cv = lane + 32 * j;
+        okj[j] = cv < n_vec;
+        cj[j] = okj[j] ? cv * VEC : 0;
+        hj[j] = cj[j] / D;
+    }
+    // owned head destinations: accumulators in registers, initialised with the self loop (first in-edge of the row)
+    float acc[kFrameOwn][KMAX][VEC];
+    int hbeg[kFrameOwn], hdeg[kFrameOwn], hcur[kFrameOwn];
+#pragma unroll
+    for (int t = 0; t < kFrameOwn; ++t) {
+        const int h = wid + t * kFrameWarps;
+        hbeg[t] = 0; hdeg[t] = 0; hcur[t] = 1;
+        if (h < Hb) {
+            hbeg[t] = __ldg(p.row_ptr + n0 + h) - e0;
+            hdeg[t] = __ldg(p.row_ptr + n0 + h + 1) - e0 - hbeg[t];
+        }
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            float zv[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) zv[q] = 0.f;
+            float a = 0.f;
+            if (h < Hb && okj[j]) {
+                *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zh + (size_t)h * hd4 + cj[j]);
+                a = w[(size_t)hbeg[t] * H + hj[j]];
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
+        }
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int k0 = c * kChunkRows, k1 = min(Mb, k0 + kChunkRows);
+        const float* rows = zE;
+        int rstride = 0;
+        if (!p.layer0) {
+            agg_mbar_wait((c & 1) ? bar1 : bar0, (uint32_t)(c >> 1) & 1u);
+            rows = buf + (size_t)(c & 1) * kChunkRows * ldz;
+            rstride = ldz;
+        }
+        // (a) edge-node destinations of the chunk: in-edges (h1 -> e), (h2 -> e), (e -> e)
+        for (int k = k0 + wid; k < k1; k += kFrameWarps) {
+            const int q0 = enode_pos0 + 3 * k;
+            const int h1 = lst[q0], h2 = lst[q0 + 1];
+            const float* wk = w + (size_t)q0 * H;
+            const float* re = rows + (size_t)(k - k0) * rstride;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+                if (!okj[j]) continue;
+                float z1[VEC], z2[VEC], ze[VEC], o[VEC];
+                *reinterpret_cast<V*>(z1) = *reinterpret_cast<const V*>(zh + (size_t)h1 * hd4 + cj[j]);
+                *reinterpret_cast<V*>(z2) = *reinterpret_cast<const V*>(zh + (size_t)h2 * hd4 + cj[j]);
+                *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + cj[j]);
+                const float w1 = wk[hj[j]], w2 = wk[H + hj[j]], w3 = wk[2 * H + hj[j]];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o[q] = fmaf(w3, ze[q], fmaf(w2, z2[q], fmaf(w1, z1[q], 0.f)));
+                store_out<VEC>(p, slope_le1, n0 + Hb + k, cj[j], o);
+            }
+        }
+        // (b) contributions of the chunk's rows to the owned heads, ascending edge id
+#pragma unroll
+        for (int t = 0; t < kFrameOwn; ++t) {
+            while (hcur[t] < hdeg[t]) {
+                const int pos = hbeg[t] + hcur[t];
+                const int k = lst[pos] - Hb;
+                if (k >= k1) break;
+                const float* re = rows + (size_t)(k - k0) * rstride;
+                const float* wp = w + (size_t)pos * H;
+#pragma unroll
+                for (int j = 0; j < KMAX; ++j) {
+                    if (!okj[j]) continue;
+                    float ze[VEC];
+                    *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + cj[j]);
+                    const float a = wp[hj[j]];
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, ze[q], acc[t][j][q]);
+                }
+                ++hcur[t];
+            }
+        }
+        if (streamed) {
+            __syncthreads();                                // every warp is done with ring slot c & 1
+            if (tid == 0 && c + 2 < n_chunks) issue_chunk(c + 2);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kFrameOwn; ++t) {
+        const int h = wid + t * kFrameWarps;
+        if (h >= Hb) continue;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (okj[j]) store_out<VEC>(p, slope_le1, n0 + h, cj[j], acc[t][j]);
+    }
+    if (p.act_hi && p.ld_planes > HD) {                     // K padding of the planes stays zero
+        const int padc = p.ld_planes - HD;
+        if ((HD & 7) == 0) {                                // 16-byte stores (ld_planes is a multiple of 64)
+            const int pv = padc / 8;
+            for (int i = tid; i < Nb * pv; i += kFrameThreads) {
+                const int r = i / pv, cc = HD + 8 * (i - r * pv);
+                *reinterpret_cast<uint4*>(p.act_hi + (size_t)(n0 + r) * p.ld_planes + cc) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(p.act_lo + (size_t)(n0 + r) * p.ld_planes + cc) = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            for (int i = tid; i < Nb * padc; i += kFrameThreads) {
+                const int r = i / padc, cc = HD + (i - r * padc);
+                p.act_hi[(size_t)(n0 + r) * p.ld_planes + cc] = __float2bfloat16_rn(0.f);
+                p.act_lo[(size_t)(n0 + r) * p.ld_planes + cc] = __float2bfloat16_rn(0.f);
+            }
+        }
+    }
+}
+
 // last layer (heads*dim == 1): one thread per destination node, sigmoid fused (gat2.py:143-145)
 __global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
     int n_nodes_total, const int* __restrict__ row_ptr, const int* __restrict__ col,
@@ -211,9 +532,9 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
                                       const int32_t* head_off, const int32_t* node_off,
                                       const int32_t* row_ptr, const int32_t* col,
                                       const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
-                                      int32_t max_heads_per_frame, float alpha, float act_slope,
+                                      int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
                                       float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
-                                      float* scores, void* stream)
+                                      float* scores, int32_t impl, void* stream)
 {
     B2_CHECK_ARG(head_off && node_off && row_ptr && col && z, "gat_aggregate: null input");
     B2_CHECK_ARG(heads >= 1 && dim >= 1 && ldz >= heads * dim + 2 * heads, "gat_aggregate: ldz too small");
@@ -238,7 +559,27 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.alpha = alpha; p.act_slope = act_slope; p.raw_f32 = raw_f32;
     p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
     p.ld_planes = ld_planes;
-    // Work unit = (frame, chunk of destination nodes). In-degree of a head is 1 + H_b - n_g <= H_b and of an
+    const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
+    // ---- frame-resident kernel: one CTA per frame, whenever the frame plan fits in shared memory ----
+    if (impl == 0 && max_heads_per_frame > 0 && max_enodes_per_frame > 0 && max_heads_per_frame <= kFrameOwn * kFrameWarps &&
+        HD / vec <= 32 * 4) {
+        const FramePlan f = frame_plan(max_heads_per_frame, max_enodes_per_frame, HD, heads, ldz);
+        const size_t smem_frame = (size_t)f.total_floats * sizeof(float);
+        if (smem_frame <= 220 * 1024) {
+            auto launch_frame = [&](auto kern) -> int {
+                B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_frame));
+                kern<<<n_frames, kFrameThreads, smem_frame, st>>>(p, max_heads_per_frame, max_enodes_per_frame);
+                B2_CHECK_LAUNCH();
+                return B200POSE_OK;
+            };
+            const int n_vec_f = HD / vec;
+            if (vec == 4) return n_vec_f <= 64 ? launch_frame(gat_aggregate_frame_kernel<4, 2>) : launch_frame(gat_aggregate_frame_kernel<4, 4>);
+            if (vec == 2) return n_vec_f <= 64 ? launch_frame(gat_aggregate_frame_kernel<2, 2>) : launch_frame(gat_aggregate_frame_kernel<2, 4>);
+            return launch_frame(gat_aggregate_frame_kernel<1, 4>);
+        }
+    }
+    B2_CHECK_ARG(impl == 0 || impl == 1, "gat_aggregate: impl must be 0 (auto) or 1 (gather kernel)");
+    // ---- gather kernel: work unit = (frame, chunk of destination nodes). ---- In-degree of a head is 1 + H_b - n_g <= H_b and of an
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
@@ -258,7 +599,6 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.chunk = 6 * kAggWarps;                                   // 48 destinations per CTA
     const int n_chunks = ceil_div(max_nodes, p.chunk);
     p.n_chunks = n_chunks;
-    const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
     const int n_vec = HD / vec;
     B2_CHECK_ARG((long long)n_frames * n_chunks < 2147483647LL, "gat_aggregate: batch too large for one launch");
     dim3 grid((unsigned)(n_frames * n_chunks));

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         const uint32_t row_off = (uint32_t)lane * 128u;
         int i = 0;
         bool stores_pending = false;
+        const bool slope_le1 = p.slope >= 0.f && p.slope <= 1.f;
         for (TileWalk w(p); w.valid(); w.next(p), ++i) {
             const TileInfo t = tile_info(p, w.tile(p));
             const int a = i & 1;
@@ -457,11 +458,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     if (col0 + 32 + lane < p.N) b1 = __ldg(p.bias + col0 + 32 + lane);
                 }
                 float v[64];
+                if (slope_le1) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
-                    v[c] = (col0 + c < p.N) ? leaky(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
-                    v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                    for (int c = 0; c < 32; ++c) {
+                        const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
+                        v[c] = (col0 + c < p.N) ? leaky_le1(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
+                        v[32 + c] = (col0 + 32 + c < p.N) ? leaky_le1(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
+                        v[c] = (col0 + c < p.N) ? leaky(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
+                        v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                    }
                 }
                 if (stores_pending) {                             // staging buffers are about to be overwritten
                     if (lane == 0) bulk_wait_read0();
@@ -482,13 +492,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     for (int c = 0; c < 8; ++c) {
                         uint32_t h[4], l[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(v[8 * c + 2 * u], h0, l0);
-                            split_bf16(v[8 * c + 2 * u + 1], h1, l1);
-                            h[u] = pack_bf16x2(h0, h1);
-                            l[u] = pack_bf16x2(l0, l1);
-                        }
+                        for (int u = 0; u < 4; ++u) split_pack2(v[8 * c + 2 * u], v[8 * c + 2 * u + 1], h[u], l[u]);
                         const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");

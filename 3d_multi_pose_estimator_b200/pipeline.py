@@ -154,6 +154,7 @@ class PosePipeline:
         self.cfg = cfg
         self.L = _lib.lib()
         self.gemm_impl = gemm_impl
+        self.agg_impl = 0          # 0 = frame-resident aggregation kernel when it fits, 1 = gather kernel
         self.threshold = float(threshold)
         self.launches = 0
         self._ws = {}
@@ -267,9 +268,9 @@ class PosePipeline:
         self.launches += 1
         check(self.L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
-                                            1 if layer0 else 0, db.max_heads, alpha, act_slope, ptr(raw),
+                                            1 if layer0 else 0, db.max_heads, db.max_enodes, alpha, act_slope, ptr(raw),
                                             ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
-                                            ptr(scores), self._stream()), 'gat_aggregate')
+                                            ptr(scores), self.agg_impl, self._stream()), 'gat_aggregate')
 
     # ------------------------------------------------------------------ stages
     def gat_forward(self, db: DeviceBatch, g: GraphArrays, x0: Optional[Planes] = None, dense_rows: bool = False,

@@ -126,7 +126,9 @@ int b200pose_split_planes(const float* x, int32_t rows, int32_t cols, int32_t ld
  *   z [rows, ldz] fp32: per source row [ ft2 (heads*dim) | a1 (heads) | a2 (heads) ] as produced by
  *     b200pose_linear with the attention vectors folded into the projection;
  *   layer0 != 0: z holds S+1 compact rows (heads + the shared edge-node row, see node_features);
- *   max_heads_per_frame sizes the shared-memory staging of a frame's head rows (0 = no staging);
+ *   max_heads_per_frame / max_enodes_per_frame size the shared-memory plan of a frame (0 = unknown);
+ *   impl: 0 = frame-resident column-parallel kernel when a frame's plan fits in shared memory, else the
+ *         warp-per-destination gather kernel; 1 = always the gather kernel (kept for large frames and A/B runs);
  *   out[v,h,:] = sum_u softmax_u(LeakyReLU_alpha(a1[u,h] + a2[v,h])) * ft2[u,h,:]
  * Outputs (any may be null): raw_f32 [N_tot, heads*dim] (the layer output, gat2.py:68),
  *   planes act_hi/lo [N_tot, ld_planes] = LeakyReLU_{act_slope}(out) (GAT2.forward :141-142),
@@ -135,9 +137,9 @@ int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_he
                            const int32_t* head_off, const int32_t* node_off,
                            const int32_t* row_ptr, const int32_t* col,
                            const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
-                           int32_t max_heads_per_frame, float alpha, float act_slope,
+                           int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
                            float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
-                           float* scores, void* stream);
+                           float* scores, int32_t impl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 2b. Person proposals: get_person_proposal_from_network_output

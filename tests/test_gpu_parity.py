@@ -115,13 +115,20 @@ def test_linear_kernels(impl):
         assert float(outp.hi[:, n:].float().abs().max() if outp.ld > n else 0.0) == 0.0
 
 
+@pytest.mark.parametrize('agg_impl', [0, 1])
 @pytest.mark.parametrize('config', helpers.CONFIGS)
-def test_gat_scores_vs_reference(config):
+def test_gat_scores_vs_reference(config, agg_impl):
+    """agg_impl 0: frame-resident aggregation kernel where the frame plan fits (panoptic, arp3), gather kernel
+    otherwise (ring10); agg_impl 1: gather kernel everywhere."""
     cfg, npz, meta = helpers.load_golden(config)
     pipe = get_pipe(config)
     tags, pb, db = golden_batch(config)
     g = pipe.build_graph(db, with_coo=False)
-    scores, raws = pipe.gat_forward(db, g, keep_layers=True)
+    pipe.agg_impl = agg_impl
+    try:
+        scores, raws = pipe.gat_forward(db, g, keep_layers=True)
+    finally:
+        pipe.agg_impl = 0
     scores = scores.cpu().numpy()
     worst = 0.0
     for b, tag in enumerate(tags):
@@ -138,6 +145,24 @@ def test_gat_scores_vs_reference(config):
                 a = raws[l][n0:n1].cpu().numpy().reshape(npz[key].shape)
                 assert np.abs(a - npz[key]).max() <= 1e-4 * max(1.0, np.abs(npz[key]).max()), (tag, l)
     print('worst relative score error', config, worst)
+
+
+def test_aggregation_kernels_agree_bitwise():
+    """The frame-resident and the gather aggregation kernels sum every output element in the same order
+    (ascending reference edge id), so their layer outputs are bit-identical."""
+    pipe = get_pipe('panoptic')
+    tags, pb, db = golden_batch('panoptic')
+    g = pipe.build_graph(db, with_coo=False)
+    outs = []
+    for impl in (0, 1):
+        pipe.agg_impl = impl
+        try:
+            scores, raws = pipe.gat_forward(db, g, keep_layers=True)
+        finally:
+            pipe.agg_impl = 0
+        outs.append([r.cpu().numpy() for r in raws] + [scores.cpu().numpy()])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize('config', helpers.CONFIGS)
