@@ -10,15 +10,15 @@
 //   OpenCV: undistortPoints = 5 fixed-point iterations of the inverse Brown model in fp64;
 //           triangulatePoints = right singular vector of the smallest singular value of the 4x4 DLT matrix.
 //
-// One warp per person, one lane per joint. Everything geometric stays in fp64 registers: the 4x4
-// null-vector problem is solved by a register-resident one-sided (Hestenes) Jacobi SVD, which works on
+// One CTA per person; threads take (camera, joint) undistortions, then (joint, camera-pair) solves, then the
+// ordered per-joint reduction (see lift_person_kernel). Everything geometric stays in fp64 registers: the
+// 4x4 null-vector problem is solved by a register-resident one-sided (Hestenes) Jacobi SVD, which works on
 // A directly (no A^T A, so the condition number is not squared - the narrow-baseline ARP stereo pair
 // needs that).
 #include "common.cuh"
 
 namespace b200pose {
 
-constexpr int kMaxCams = B200POSE_MAX_CAMERAS;
 constexpr int kJ = B200POSE_N_JOINTS;
 
 struct LiftTables {
@@ -110,208 +110,232 @@ __device__ void triangulate_pair(const double* __restrict__ P1, const double* __
     X[0] = v0 / v3; X[1] = v1 / v3; X[2] = v2 / v3;
 }
 
-// ---- MLP-input encoder -------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) encode_persons_kernel(
-    int n_persons, const int* __restrict__ person_sk, const double* __restrict__ sk_xy, const float* __restrict__ sk_vp,
-    const uint32_t* __restrict__ sk_mask, LiftTables t,
-    float* __restrict__ x_f32, int ld_f32, __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo, int ld_planes,
-    uint8_t* __restrict__ valid)
-{
-    const int person = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (person >= n_persons) return;
-    const int C = t.n_cameras;
-    // cameras of this person in used_cameras order (dataset.py raw_input is built in that order,
-    // test/metrics_from_model.py:248-252)
-    int cam_of_slot[kMaxCams];
-    for (int s = 0; s < t.v_pe; ++s) cam_of_slot[s] = -1;
-    for (int c = 0; c < C; ++c) { const int s = t.pe_slot[c]; if (s >= 0) cam_of_slot[s] = c; }
+// ---- per-person lifting kernel ---------------------------------------------------------------------
+// One CTA per person. The work of a person is re-parallelised over its natural units instead of one lane
+// per joint:
+//   phase U: thread per (camera slot, joint)  - fp64 undistortion; the encoder also forms the 10 per-view
+//            numbers of that joint here and writes them into the shared-memory row
+//   phase S: thread per (joint, camera pair)  - one register-resident 4x4 DLT solve each, results to
+//            shared memory [joint][pair][3] (joints are processed in batches sized to 48 KB)
+//   phase R: thread per joint                 - ordered reduction over the pairs (plain mean for the encoder,
+//            upper median + 5 cm filter + mean for the baseline): same order as the reference's
+//            itertools.combinations loop, so the result does not depend on the thread mapping
+//   phase W: the whole CTA writes the person's row with 16-byte stores (fp32 and/or bf16 planes)
+constexpr int kLiftThreads = 128;
+constexpr int kPairBudgetBytes = 48 * 1024;
 
-    const int j = lane;
-    float abs_sum = 0.f;
-    double ux[kMaxCams], uy[kMaxCams];
-    uint32_t have = 0;                                    // slots where joint j is present
-    const int row_len = kJ * 14 * t.v_pe;
-    if (j < kJ) {
-        for (int s = 0; s < t.v_pe; ++s) {
-            const int c = cam_of_slot[s];
-            const int sk = (c >= 0) ? person_sk[(size_t)person * C + c] : -1;
-            float o[10];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) o[i] = 0.f;
-            if (sk >= 0 && ((sk_mask[sk] >> j) & 1u)) {
-                const double x = sk_xy[(size_t)sk * 36 + 2 * j], y = sk_xy[(size_t)sk * 36 + 2 * j + 1];
-                double nx, ny;
-                undistort(x, y, t.k64 + 4 * c, t.dist64 + 5 * c, nx, ny);
-                ux[s] = nx; uy[s] = ny;
-                have |= 1u << s;
-                const double w2 = (double)t.W / 2.0, h2 = (double)t.Hh / 2.0;
-                o[0] = sk_vp[(size_t)sk * 36 + 2 * j];
-                o[1] = __double2float_rn((x - w2) / w2);
-                o[2] = __double2float_rn((y - h2) / h2);
-                o[3] = sk_vp[(size_t)sk * 36 + 2 * j + 1];
-                const float* T = t.t_cam2root32 + 16 * c;
-                const float fx_ = __double2float_rn(nx), fy_ = __double2float_rn(ny);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    o[4 + i] = __fdiv_rn(T[4 * i + 3], 10.0f);
-                    float acc = __fmul_rn(T[4 * i], fx_);
-                    acc = __fmaf_rn(T[4 * i + 1], fy_, acc);
-                    acc = __fmaf_rn(T[4 * i + 2], 1.0f, acc);
-                    acc = __fmaf_rn(T[4 * i + 3], 0.0f, acc);
-                    o[7 + i] = __fdiv_rn(acc, 10.0f);
-                }
-            }
-            const size_t base = (size_t)s * (kJ * 14) + (size_t)j * 14;
-#pragma unroll
-            for (int i = 0; i < 10; ++i) {
-                abs_sum += fabsf(o[i]);
-                if (x_f32) x_f32[(size_t)person * ld_f32 + base + i] = o[i];
-                if (x_hi) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(o[i], h, l);
-                    x_hi[(size_t)person * ld_planes + base + i] = h;
-                    x_lo[(size_t)person * ld_planes + base + i] = l;
-                }
-            }
+struct LiftSmem {           // byte offsets into dynamic shared memory
+    int ux, uy, have, cam, pa, pb, X, row, total;
+    int n_pairs, joint_batch;
+};
+__host__ __device__ inline LiftSmem lift_smem(int n_slots, int row_len) {
+    LiftSmem L;
+    L.n_pairs = n_slots * (n_slots - 1) / 2;
+    int jb = L.n_pairs > 0 ? kPairBudgetBytes / (L.n_pairs * 24) : kJ;
+    L.joint_batch = jb < 1 ? 1 : (jb > kJ ? kJ : jb);
+    int o = 0;
+    L.ux = o; o += n_slots * kJ * 8;
+    L.uy = o; o += n_slots * kJ * 8;
+    L.X = o; o += (L.n_pairs > 0 ? L.joint_batch * L.n_pairs * 24 : 8);
+    L.have = o; o += kJ * 4;
+    L.cam = o; o += n_slots * 4;
+    L.pa = o; o += (L.n_pairs + 1) * 2;
+    L.pb = o; o += (L.n_pairs + 1) * 2;
+    o = (o + 15) & ~15;
+    L.row = o; o += ((row_len + 3) & ~3) * 4;
+    L.total = o;
+    return L;
+}
+
+template <bool ENCODE>
+__global__ void __launch_bounds__(kLiftThreads) lift_person_kernel(
+    int n_persons, const int* __restrict__ person_sk, const double* __restrict__ sk_xy, const float* __restrict__ sk_vp,
+    const uint32_t* __restrict__ sk_mask, LiftTables t, int n_slots, int median_axis,
+    float* __restrict__ x_f32, int ld_f32, __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo, int ld_planes,
+    uint8_t* __restrict__ valid, double* __restrict__ xyz, uint8_t* __restrict__ mask)
+{
+    extern __shared__ __align__(16) unsigned char lift_raw[];
+    __shared__ float red[kLiftThreads / 32];
+    const int person = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int C = t.n_cameras;
+    const int row_len = ENCODE ? kJ * 14 * n_slots : 0;
+    const LiftSmem L = lift_smem(n_slots, row_len);
+    double* ux = reinterpret_cast<double*>(lift_raw + L.ux);
+    double* uy = reinterpret_cast<double*>(lift_raw + L.uy);
+    double* X = reinterpret_cast<double*>(lift_raw + L.X);
+    uint32_t* have = reinterpret_cast<uint32_t*>(lift_raw + L.have);
+    int* cam_of_slot = reinterpret_cast<int*>(lift_raw + L.cam);
+    unsigned short* pa = reinterpret_cast<unsigned short*>(lift_raw + L.pa);
+    unsigned short* pb = reinterpret_cast<unsigned short*>(lift_raw + L.pb);
+    float* row = reinterpret_cast<float*>(lift_raw + L.row);
+    const int NP = L.n_pairs;
+
+    // ---- setup: slot -> camera, pair table (lexicographic s1 < s2), zeroed row ----
+    if (tid < n_slots) {
+        int c = tid;                                     // baseline: slot = camera index (metrics_from_triangulation.py:239)
+        if (ENCODE) {                                    // encoder: slots are used_cameras order (metrics_from_model.py:248-252)
+            c = -1;
+            for (int cc = 0; cc < C; ++cc) if (t.pe_slot[cc] == tid) c = cc;
         }
-        // pairwise triangulation hint (joint id > 0: dataset.py:75)
-        float tri[4] = {0.f, 0.f, 0.f, 0.f};
-        if (j > 0 && __popc(have) >= 2) {
-            double acc[3] = {0, 0, 0};
-            int n = 0;
-            for (int s1 = 0; s1 < t.v_pe; ++s1) {
-                if (!((have >> s1) & 1u)) continue;
-                for (int s2 = s1 + 1; s2 < t.v_pe; ++s2) {
-                    if (!((have >> s2) & 1u)) continue;
-                    double X[3];
-                    triangulate_pair(t.p64 + 12 * cam_of_slot[s1], t.p64 + 12 * cam_of_slot[s2], ux[s1], uy[s1], ux[s2], uy[s2], X);
-                    acc[0] += X[0]; acc[1] += X[1]; acc[2] += X[2];
-                    ++n;
-                }
-            }
-            tri[0] = 1.0f;
+        cam_of_slot[tid] = c;
+    }
+    for (int i = tid; i < NP; i += kLiftThreads) {
+        int a = 0, rem = i;                              // pair i -> (a, b)
+        while (rem >= n_slots - 1 - a) { rem -= n_slots - 1 - a; ++a; }
+        pa[i] = (unsigned short)a; pb[i] = (unsigned short)(a + 1 + rem);
+    }
+    if (tid < kJ) have[tid] = 0;
+    if (ENCODE) for (int i = tid; i < ((row_len + 3) & ~3); i += kLiftThreads) row[i] = 0.f;
+    __syncthreads();
+
+    // ---- phase U: undistortion (+ the per-view numbers of the encoder) ----
+    for (int i = tid; i < n_slots * kJ; i += kLiftThreads) {
+        const int s = i / kJ, j = i - s * kJ;
+        const int c = cam_of_slot[s];
+        const int sk = (c >= 0) ? person_sk[(size_t)person * C + c] : -1;
+        if (sk < 0 || !((sk_mask[sk] >> j) & 1u)) continue;
+        const double x = sk_xy[(size_t)sk * 36 + 2 * j], y = sk_xy[(size_t)sk * 36 + 2 * j + 1];
+        double nx, ny;
+        undistort(x, y, t.k64 + 4 * c, t.dist64 + 5 * c, nx, ny);
+        ux[i] = nx; uy[i] = ny;
+        atomicOr(&have[j], 1u << s);
+        if (ENCODE) {
+            float* o = row + (size_t)s * (kJ * 14) + (size_t)j * 14;
+            const double w2 = (double)t.W / 2.0, h2 = (double)t.Hh / 2.0;
+            o[0] = sk_vp[(size_t)sk * 36 + 2 * j];
+            o[1] = __double2float_rn((x - w2) / w2);
+            o[2] = __double2float_rn((y - h2) / h2);
+            o[3] = sk_vp[(size_t)sk * 36 + 2 * j + 1];
+            const float* T = t.t_cam2root32 + 16 * c;
+            const float fx_ = __double2float_rn(nx), fy_ = __double2float_rn(ny);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) tri[1 + i] = __double2float_rn((acc[i] / (double)n) / 10.0);
-        }
-        for (int s = 0; s < t.v_pe; ++s) {                 // every used-camera block (dataset.py:280-285)
-            const size_t base = (size_t)s * (kJ * 14) + (size_t)j * 14 + 10;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                abs_sum += fabsf(tri[i]);
-                if (x_f32) x_f32[(size_t)person * ld_f32 + base + i] = tri[i];
-                if (x_hi) {
-                    __nv_bfloat16 h, l;
-                    split_bf16(tri[i], h, l);
-                    x_hi[(size_t)person * ld_planes + base + i] = h;
-                    x_lo[(size_t)person * ld_planes + base + i] = l;
-                }
+            for (int r = 0; r < 3; ++r) {
+                o[4 + r] = __fdiv_rn(T[4 * r + 3], 10.0f);
+                float acc = __fmul_rn(T[4 * r], fx_);
+                acc = __fmaf_rn(T[4 * r + 1], fy_, acc);
+                acc = __fmaf_rn(T[4 * r + 2], 1.0f, acc);
+                acc = __fmaf_rn(T[4 * r + 3], 0.0f, acc);
+                o[7 + r] = __fdiv_rn(acc, 10.0f);
             }
         }
     }
-    // zero the K padding of the planes
+    __syncthreads();
+
+    // ---- phases S + R, joints in batches ----
+    const int j_first = ENCODE ? 1 : 0;                  // the encoder's hint skips joint 0 (dataset.py:75: `pos[0] > 0.`)
+    for (int jb0 = j_first; jb0 < kJ; jb0 += L.joint_batch) {
+        const int jb1 = min(kJ, jb0 + L.joint_batch);
+        for (int i = tid; i < (jb1 - jb0) * NP; i += kLiftThreads) {
+            const int jl = i / NP, pi = i - jl * NP;
+            const int j = jb0 + jl;
+            const int s1 = pa[pi], s2 = pb[pi];
+            const uint32_t hv = have[j];
+            if (!((hv >> s1) & 1u) || !((hv >> s2) & 1u)) continue;
+            double Xp[3];
+            triangulate_pair(t.p64 + 12 * cam_of_slot[s1], t.p64 + 12 * cam_of_slot[s2],
+                             ux[s1 * kJ + j], uy[s1 * kJ + j], ux[s2 * kJ + j], uy[s2 * kJ + j], Xp);
+            double* o = X + (size_t)i * 3;
+            o[0] = Xp[0]; o[1] = Xp[1]; o[2] = Xp[2];
+        }
+        __syncthreads();
+        if (tid < jb1 - jb0) {
+            const int j = jb0 + tid;
+            const uint32_t hv = have[j];
+            const double* Xj = X + (size_t)tid * NP * 3;
+            if (ENCODE) {
+                if (__popc(hv) >= 2) {
+                    double acc[3] = {0, 0, 0};
+                    int n = 0;
+                    for (int pi = 0; pi < NP; ++pi) {
+                        if (!((hv >> pa[pi]) & 1u) || !((hv >> pb[pi]) & 1u)) continue;
+                        acc[0] += Xj[3 * pi]; acc[1] += Xj[3 * pi + 1]; acc[2] += Xj[3 * pi + 2];
+                        ++n;
+                    }
+                    float tri[4];
+                    tri[0] = 1.0f;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) tri[1 + r] = __double2float_rn((acc[r] / (double)n) / 10.0);
+                    for (int s = 0; s < n_slots; ++s) {  // every used-camera block (dataset.py:280-285)
+                        float* o = row + (size_t)s * (kJ * 14) + (size_t)j * 14 + 10;
+                        o[0] = tri[0]; o[1] = tri[1]; o[2] = tri[2]; o[3] = tri[3];
+                    }
+                }
+            } else {
+                double* out = xyz + ((size_t)person * kJ + j) * 3;
+                if (__popc(hv) < 2) {
+                    out[0] = out[1] = out[2] = 0.0;
+                    mask[(size_t)person * kJ + j] = 0;
+                } else {
+                    // upper median of the median-axis coordinate by counting (ties by pair order), utils.py:70-71
+                    int npairs = 0;
+                    for (int pi = 0; pi < NP; ++pi) npairs += ((hv >> pa[pi]) & 1u) && ((hv >> pb[pi]) & 1u);
+                    const int target = npairs / 2;
+                    double med = 0.0;
+                    for (int a = 0; a < NP; ++a) {
+                        if (!((hv >> pa[a]) & 1u) || !((hv >> pb[a]) & 1u)) continue;
+                        const double va = Xj[3 * a + median_axis];
+                        int less = 0, eq_before = 0;
+                        for (int k = 0; k < NP; ++k) {
+                            if (!((hv >> pa[k]) & 1u) || !((hv >> pb[k]) & 1u)) continue;
+                            const double vk = Xj[3 * k + median_axis];
+                            less += vk < va;
+                            eq_before += (vk == va) && (k < a);
+                        }
+                        if (less + eq_before == target) med = va;
+                    }
+                    double acc[3] = {0, 0, 0};
+                    int kept = 0;
+                    for (int pi = 0; pi < NP; ++pi) {
+                        if (!((hv >> pa[pi]) & 1u) || !((hv >> pb[pi]) & 1u)) continue;
+                        if (fabs(Xj[3 * pi + median_axis] - med) < 0.05) {
+                            acc[0] += Xj[3 * pi]; acc[1] += Xj[3 * pi + 1]; acc[2] += Xj[3 * pi + 2];
+                            ++kept;
+                        }
+                    }
+                    out[0] = acc[0] / kept; out[1] = acc[1] / kept; out[2] = acc[2] / kept;
+                    mask[(size_t)person * kJ + j] = 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!ENCODE) return;
+
+    // ---- phase W: the person's row, 16-byte stores ----
+    float abs_sum = 0.f;
     if (x_hi) {
-        for (int c = row_len + lane; c < ld_planes; c += 32) {
-            x_hi[(size_t)person * ld_planes + c] = __float2bfloat16_rn(0.f);
-            x_lo[(size_t)person * ld_planes + c] = __float2bfloat16_rn(0.f);
+        for (int v8 = tid; v8 < ld_planes / 8; v8 += kLiftThreads) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c0 = 8 * v8 + 2 * u;
+                const float a = c0 < row_len ? row[c0] : 0.f, b = c0 + 1 < row_len ? row[c0 + 1] : 0.f;
+                split_pack2(a, b, h[u], l[u]);
+            }
+            *reinterpret_cast<uint4*>(x_hi + (size_t)person * ld_planes + 8 * v8) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(x_lo + (size_t)person * ld_planes + 8 * v8) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+    }
+    const bool vec_ok = x_f32 && (ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_f32) & 15) == 0) && (row_len % 4 == 0);
+    for (int v4 = tid; v4 < (row_len + 3) / 4; v4 += kLiftThreads) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * v4);
+        abs_sum += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);      // row is zero padded to a multiple of 4
+        if (vec_ok) *reinterpret_cast<float4*>(x_f32 + (size_t)person * ld_f32 + 4 * v4) = v;
+        else if (x_f32) {
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            for (int u = 0; u < 4; ++u) if (4 * v4 + u < row_len) x_f32[(size_t)person * ld_f32 + 4 * v4 + u] = e[u];
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) abs_sum += __shfl_xor_sync(0xffffffffu, abs_sum, o);
-    if (valid && lane == 0) valid[person] = abs_sum > 1.0f ? 1 : 0;          // dataset.py:287
-}
-
-// ---- triangulation baseline ---------------------------------------------------------------------
-__global__ void __launch_bounds__(128) triangulate_kernel(
-    int n_persons, const int* __restrict__ person_sk, const double* __restrict__ sk_xy, const uint32_t* __restrict__ sk_mask,
-    LiftTables t, int median_axis, double* __restrict__ xyz, uint8_t* __restrict__ mask)
-{
-    const int person = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int j = threadIdx.x & 31;
-    if (person >= n_persons || j >= kJ) return;
-    const int C = t.n_cameras;
-    double ux[kMaxCams], uy[kMaxCams];
-    uint32_t have = 0;
-    for (int c = 0; c < C; ++c) {                           // camera index order (metrics_from_triangulation.py:239)
-        const int sk = person_sk[(size_t)person * C + c];
-        if (sk >= 0 && ((sk_mask[sk] >> j) & 1u)) {
-            undistort(sk_xy[(size_t)sk * 36 + 2 * j], sk_xy[(size_t)sk * 36 + 2 * j + 1], t.k64 + 4 * c, t.dist64 + 5 * c, ux[c], uy[c]);
-            have |= 1u << c;
-        }
+    if ((tid & 31) == 0) red[tid >> 5] = abs_sum;
+    __syncthreads();
+    if (valid && tid == 0) {
+        float sum = 0.f;
+        for (int i = 0; i < kLiftThreads / 32; ++i) sum += red[i];
+        valid[person] = sum > 1.0f ? 1 : 0;                                  // dataset.py:287
     }
-    double* out = xyz + ((size_t)person * kJ + j) * 3;
-    const int ncam = __popc(have);
-    if (ncam < 2) {
-        out[0] = out[1] = out[2] = 0.0;
-        mask[(size_t)person * kJ + j] = 0;
-        return;
-    }
-    // pass 1: the coordinate used by the median filter, for every pair (<= 496 pairs; kept implicit)
-    // The pair results are recomputed in pass 2 instead of being stored: registers over local memory.
-    const int npairs = ncam * (ncam - 1) / 2;
-    const int target = npairs / 2;                         // index of the upper median in sorted order
-    // selection by counting: median = value v with exactly `target` values smaller (ties by pair order)
-    double med = 0.0;
-    {
-        // gather the median-axis values in local memory (npairs <= 496)
-        double vals[64];
-        const bool small = npairs <= 64;
-        int n = 0;
-        for (int c1 = 0; c1 < C; ++c1) {
-            if (!((have >> c1) & 1u)) continue;
-            for (int c2 = c1 + 1; c2 < C; ++c2) {
-                if (!((have >> c2) & 1u)) continue;
-                double X[3];
-                triangulate_pair(t.p64 + 12 * c1, t.p64 + 12 * c2, ux[c1], uy[c1], ux[c2], uy[c2], X);
-                const double d = median_axis == 0 ? X[0] : (median_axis == 1 ? X[1] : X[2]);
-                if (small) vals[n] = d;
-                ++n;
-            }
-        }
-        if (small) {
-            for (int i = 0; i < npairs; ++i) {
-                int less = 0, eq_before = 0;
-                for (int k = 0; k < npairs; ++k) {
-                    less += vals[k] < vals[i];
-                    eq_before += (vals[k] == vals[i]) && (k < i);
-                }
-                if (less + eq_before == target) med = vals[i];
-            }
-        } else {
-            // more than 64 pairs (> 11 cameras seeing the joint): selection by repeated recomputation
-            double lo = -1e300;
-            int taken = 0;
-            while (true) {
-                double best = 1e300; int cnt = 0;
-                for (int c1 = 0; c1 < C; ++c1) {
-                    if (!((have >> c1) & 1u)) continue;
-                    for (int c2 = c1 + 1; c2 < C; ++c2) {
-                        if (!((have >> c2) & 1u)) continue;
-                        double X[3];
-                        triangulate_pair(t.p64 + 12 * c1, t.p64 + 12 * c2, ux[c1], uy[c1], ux[c2], uy[c2], X);
-                        const double d = median_axis == 0 ? X[0] : (median_axis == 1 ? X[1] : X[2]);
-                        if (d > lo) { if (d < best) { best = d; cnt = 1; } else if (d == best) ++cnt; }
-                    }
-                }
-                if (taken + cnt > target) { med = best; break; }
-                taken += cnt; lo = best;
-            }
-        }
-    }
-    double acc[3] = {0, 0, 0};
-    int kept = 0;
-    for (int c1 = 0; c1 < C; ++c1) {
-        if (!((have >> c1) & 1u)) continue;
-        for (int c2 = c1 + 1; c2 < C; ++c2) {
-            if (!((have >> c2) & 1u)) continue;
-            double X[3];
-            triangulate_pair(t.p64 + 12 * c1, t.p64 + 12 * c2, ux[c1], uy[c1], ux[c2], uy[c2], X);
-            const double d = median_axis == 0 ? X[0] : (median_axis == 1 ? X[1] : X[2]);
-            if (fabs(d - med) < 0.05) { acc[0] += X[0]; acc[1] += X[1]; acc[2] += X[2]; ++kept; }
-        }
-    }
-    out[0] = acc[0] / kept; out[1] = acc[1] / kept; out[2] = acc[2] / kept;
-    mask[(size_t)person * kJ + j] = 1;
 }
 
 }  // namespace b200pose
@@ -337,9 +361,11 @@ extern "C" __attribute__((visibility("default"))) int b200pose_encode_persons(in
     if (x_f32) B2_CHECK_ARG(ld_f32 >= row_len, "encode_persons: ld_f32 too small");
     if (x_hi) B2_CHECK_ARG(ld_planes % 64 == 0 && ld_planes >= row_len, "encode_persons: bad ld_planes");
     if (n_persons == 0) return B200POSE_OK;
-    encode_persons_kernel<<<ceil_div(n_persons, 4), 128, 0, (cudaStream_t)stream>>>(
-        n_persons, person_sk, sk_xy, sk_vp, sk_mask, make_tables(cams), x_f32, ld_f32,
-        reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), ld_planes, valid);
+    const LiftSmem L = lift_smem(cams->v_pe, row_len);
+    B2_CHECK_CUDA(cudaFuncSetAttribute(lift_person_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    lift_person_kernel<true><<<n_persons, kLiftThreads, L.total, (cudaStream_t)stream>>>(
+        n_persons, person_sk, sk_xy, sk_vp, sk_mask, make_tables(cams), cams->v_pe, 0, x_f32, ld_f32,
+        reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), ld_planes, valid, nullptr, nullptr);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }
@@ -352,8 +378,11 @@ extern "C" __attribute__((visibility("default"))) int b200pose_triangulate(int32
     B2_CHECK_ARG(median_axis >= 0 && median_axis < 3, "triangulate: median_axis must be 0..2");
     B2_CHECK_ARG(cams->n_cameras <= B200POSE_MAX_CAMERAS, "triangulate: too many cameras");
     if (n_persons == 0) return B200POSE_OK;
-    triangulate_kernel<<<ceil_div(n_persons, 4), 128, 0, (cudaStream_t)stream>>>(
-        n_persons, person_sk, sk_xy, sk_mask, make_tables(cams), median_axis, xyz, mask);
+    const LiftSmem L = lift_smem(cams->n_cameras, 0);
+    B2_CHECK_CUDA(cudaFuncSetAttribute(lift_person_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    lift_person_kernel<false><<<n_persons, kLiftThreads, L.total, (cudaStream_t)stream>>>(
+        n_persons, person_sk, sk_xy, nullptr, sk_mask, make_tables(cams), cams->n_cameras, median_axis, nullptr, 0,
+        nullptr, nullptr, 0, nullptr, xyz, mask);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

@@ -53,7 +53,7 @@ def full(path):
         vals = []
         for name, _, scale in COLS:
             i = idx[name]
-            if i is None or r[i] == '':
+            if i is None or r[i] in ('', 'no data', 'n/a'):
                 vals.append('-')
                 continue
             v = float(r[i].replace(',', ''))
