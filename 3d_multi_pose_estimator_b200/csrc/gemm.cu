@@ -299,25 +299,26 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 struct GemmParams2 {
     int M, N, num_kb;
-    int tiles_m, tiles_n, panels_total;      // 64-column output panels
-    int group_n;                             // consecutive n-tiles of one m-tile a CTA processes per visit
+    int tiles_m, tiles_n, panels_total;      // 64-column output panels; tiles_m counts (128 * NCTA)-row tiles
+    int group_n;                             // consecutive n-tiles of one m-tile a CTA (pair) processes per visit
     int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
     const float* bias; float slope, out_scale;
     int has_f32, has_planes;
-    unsigned long long* dbg;                 // optional per-CTA timestamps (kernel bring-up)
 };
 
 struct TileInfo { int m0, n0, bn; };
-// Tile walk of one CTA. Work is dealt out in "visits": visit s covers group_n consecutive n-tiles of one
-// m-tile, and CTA c takes visits c, c + grid, ... With group_n == tiles_n (tall GEMMs: many m-tiles) a CTA
-// sweeps every n-tile of an m-tile back to back, so the A tile is fetched from HBM once and re-read from L2
-// microseconds later; with group_n == 1 (wide GEMMs: few m-tiles) the walk is the plain n-fastest order.
+// Tile walk of one CTA (or CTA pair). Work is dealt out in "visits": visit s covers group_n consecutive
+// n-tiles of one m-tile, and worker c takes visits c, c + workers, ... With group_n == tiles_n (tall GEMMs:
+// many m-tiles) a worker sweeps every n-tile of an m-tile back to back, so the A tile is fetched from HBM once
+// and re-read from L2 microseconds later; with group_n == 1 (wide GEMMs: few m-tiles) the walk is the plain
+// n-fastest order.
+template <int NCTA>
 struct TileWalk {
     int visit, j, groups_per_m, total_visits;
     __device__ __forceinline__ TileWalk(const GemmParams2& p) {
         groups_per_m = (p.tiles_n + p.group_n - 1) / p.group_n;
         total_visits = p.tiles_m * groups_per_m;
-        visit = blockIdx.x; j = 0;
+        visit = blockIdx.x / NCTA; j = 0;
     }
     __device__ __forceinline__ bool valid() const { return visit < total_visits; }
     __device__ __forceinline__ int tile(const GemmParams2& p) const {
@@ -327,19 +328,77 @@ struct TileWalk {
     __device__ __forceinline__ void next(const GemmParams2& p) {
         const int g = visit % groups_per_m;
         ++j;
-        if (j >= p.group_n || g * p.group_n + j >= p.tiles_n) { j = 0; visit += gridDim.x; }
+        if (j >= p.group_n || g * p.group_n + j >= p.tiles_n) { j = 0; visit += gridDim.x / NCTA; }
     }
 };
+template <int NCTA>
 __device__ __forceinline__ TileInfo tile_info(const GemmParams2& p, int tile) {
     const int nb = tile % p.tiles_n, mb = tile / p.tiles_n;
     const int base = p.panels_total / p.tiles_n, rem = p.panels_total % p.tiles_n;
     TileInfo t;
-    t.m0 = mb * kBM;
+    t.m0 = mb * kBM * NCTA;
     t.n0 = 64 * (nb * base + min(nb, rem));
     t.bn = 64 * (base + (nb < rem ? 1 : 0));
     return t;
 }
 
+// ---- CTA-pair (cta_group::2) primitives ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same smem offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+template <int NCTA> __device__ __forceinline__ void tmem_alloc_n(uint32_t slot_smem, uint32_t ncols) {
+    if constexpr (NCTA == 1) {
+        tmem_alloc(slot_smem, ncols);
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int NCTA> __device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, uint32_t ncols) {
+    if constexpr (NCTA == 1) tmem_dealloc(taddr, ncols);
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128*NCTA, N=bn
+template <int NCTA> __device__ __forceinline__ uint32_t make_idesc_n(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((kBM * NCTA) >> 4) << 24);
+}
+
+// NCTA == 1: one CTA per SM computes 128 x bn tiles.
+// NCTA == 2: the two CTAs of a cluster (one TPC) compute 256 x bn tiles with tcgen05.mma.cta_group::2: each CTA
+//   loads its own 128 rows of A and HALF of the W tile (bn/2 rows), the leader CTA issues the MMAs, which read both
+//   CTAs' shared memory and write both CTAs' TMEM; each CTA runs the epilogue of its own 128 rows. Per flop this
+//   halves the W bytes every SM pulls through the L2->SM fabric, which is what bounds the 128 x 256 single-CTA
+//   tiles of the tall GAT projections (profiles/r01_v2_ncu_summary.md).
+template <int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -354,59 +413,75 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t a_bytes = kBM * kBK * 2;                                  // 16 KB per plane
-    const uint32_t b_bytes = (uint32_t)p.stage_bn * kBK * 2;
+    const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const uint32_t a_bytes = kBM * kBK * 2;                                  // 16 KB per plane (this CTA's 128 rows)
+    const uint32_t b_rows_stage = (uint32_t)p.stage_bn / NCTA;               // W rows this CTA holds per stage
+    const uint32_t b_bytes = b_rows_stage * kBK * 2;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     const uint32_t staging_base = tiles_base + (uint32_t)p.stages * stage_bytes;   // 1024-aligned
     const uint32_t acc_cols = tmem_cols_for(p.stage_bn);
     const uint32_t ncols = 2 * acc_cols;
+    constexpr int kBoxW = (NCTA == 1) ? 64 : 32;                             // W rows per TMA box
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4 * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
         if (p.has_f32) prefetch_tmap(&map_o_f32);
         if (p.has_planes) { prefetch_tmap(&map_o_hi); prefetch_tmap(&map_o_lo); }
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), ncols);
+    if (warp == 1) tmem_alloc_n<NCTA>(smem_u32(&tmem_slot), ncols);
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();       // barriers of BOTH CTAs are initialised past this point
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 4 + 0] = globaltimer_ns();
 
     if (warp == 0) {
-        // ================= TMA producer =================
+        // ================= TMA producer (every CTA loads its own operand halves) =================
         if (lane == 0) {
             int it = 0;
-            for (TileWalk w(p); w.valid(); w.next(p)) {
-                const TileInfo t = tile_info(p, w.tile(p));
-                const uint32_t tx = 2 * a_bytes + 2 * (uint32_t)t.bn * kBK * 2;
+            for (TileWalk<NCTA> w(p); w.valid(); w.next(p)) {
+                const TileInfo t = tile_info<NCTA>(p, w.tile(p));
+                const int b_rows = t.bn / NCTA;                               // this CTA's share of the W tile
+                const int m_cta = t.m0 + (int)rank * kBM, n_cta = t.n0 + (int)rank * b_rows;
+                const uint32_t tx = NCTA * (2 * a_bytes + 2 * (uint32_t)b_rows * kBK * 2);   // bytes landing for the whole pair
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bar_full[s]);
-                    mbar_expect_tx(full, tx);
                     const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
-                    tma_load_2d(base, &map_a_hi, kb * kBK, t.m0, full);
-                    tma_load_2d(base + a_bytes, &map_a_lo, kb * kBK, t.m0, full);
-                    for (int j = 0; j < t.bn / 64; ++j) {
-                        tma_load_2d(base + 2 * a_bytes + j * 8192, &map_w_hi, kb * kBK, t.n0 + 64 * j, full);
-                        tma_load_2d(base + 2 * a_bytes + b_bytes + j * 8192, &map_w_lo, kb * kBK, t.n0 + 64 * j, full);
+                    if constexpr (NCTA == 1) {
+                        mbar_expect_tx(full, tx);
+                        tma_load_2d(base, &map_a_hi, kb * kBK, m_cta, full);
+                        tma_load_2d(base + a_bytes, &map_a_lo, kb * kBK, m_cta, full);
+                        for (int j = 0; j < b_rows / kBoxW; ++j) {
+                            tma_load_2d(base + 2 * a_bytes + j * (kBoxW * 128), &map_w_hi, kb * kBK, n_cta + kBoxW * j, full);
+                            tma_load_2d(base + 2 * a_bytes + b_bytes + j * (kBoxW * 128), &map_w_lo, kb * kBK, n_cta + kBoxW * j, full);
+                        }
+                    } else {
+                        if (leader) mbar_expect_tx(full, tx);                 // the leader's barrier counts both CTAs' bytes
+                        const uint32_t full0 = mapa_shared(full, 0);
+                        tma_load_2d_pair(base, &map_a_hi, kb * kBK, m_cta, full0);
+                        tma_load_2d_pair(base + a_bytes, &map_a_lo, kb * kBK, m_cta, full0);
+                        for (int j = 0; j < b_rows / kBoxW; ++j) {
+                            tma_load_2d_pair(base + 2 * a_bytes + j * (kBoxW * 128), &map_w_hi, kb * kBK, n_cta + kBoxW * j, full0);
+                            tma_load_2d_pair(base + 2 * a_bytes + b_bytes + j * (kBoxW * 128), &map_w_lo, kb * kBK, n_cta + kBoxW * j, full0);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (leader CTA only when paired) =================
+        if (lane == 0 && leader) {
             int it = 0, i = 0;
-            for (TileWalk w(p); w.valid(); w.next(p), ++i) {
-                const TileInfo t = tile_info(p, w.tile(p));
-                const uint32_t idesc = make_idesc(t.bn);
+            for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
+                const TileInfo t = tile_info<NCTA>(p, w.tile(p));
+                const uint32_t idesc = make_idesc_n<NCTA>(t.bn);
                 const int a = i & 1;
                 mbar_wait(smem_u32(&bar_acc_empty[a]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
@@ -417,14 +492,32 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     mbar_wait(smem_u32(&bar_full[s]), ph);
                     tcgen05_fence_after();
                     const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
-                    issue_kblock(base, base + a_bytes, base + 2 * a_bytes, base + 2 * a_bytes + b_bytes, tmem_d, idesc, kb == 0);
-                    umma_commit(smem_u32(&bar_empty[s]));
+                    const uint32_t sa_hi = base, sa_lo = base + a_bytes, sb_hi = base + 2 * a_bytes, sb_lo = base + 2 * a_bytes + b_bytes;
+#pragma unroll
+                    for (int k4 = 0; k4 < kBK / kUmmaK; ++k4) {              // hi*hi, lo*hi, hi*lo per 16-wide k step
+                        const uint32_t off = k4 * kUmmaK * 2;
+                        const uint64_t dah = make_sw128_desc(sa_hi + off), dal = make_sw128_desc(sa_lo + off);
+                        const uint64_t dbh = make_sw128_desc(sb_hi + off), dbl = make_sw128_desc(sb_lo + off);
+                        const uint32_t first = (kb == 0 && k4 == 0) ? 0u : 1u;
+                        if constexpr (NCTA == 1) {
+                            umma_bf16(tmem_d, dah, dbh, idesc, first);
+                            umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+                            umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                        } else {
+                            umma_bf16_pair(tmem_d, dah, dbh, idesc, first);
+                            umma_bf16_pair(tmem_d, dal, dbh, idesc, 1u);
+                            umma_bf16_pair(tmem_d, dah, dbl, idesc, 1u);
+                        }
+                    }
+                    if constexpr (NCTA == 1) umma_commit(smem_u32(&bar_empty[s]));
+                    else umma_commit_pair(smem_u32(&bar_empty[s]));           // frees the slot in both CTAs
                 }
-                umma_commit(smem_u32(&bar_acc_full[a]));
+                if constexpr (NCTA == 1) umma_commit(smem_u32(&bar_acc_full[a]));
+                else umma_commit_pair(smem_u32(&bar_acc_full[a]));
             }
         }
     } else {
-        // ================= epilogue =================
+        // ================= epilogue (each CTA drains its own 128 accumulator rows) =================
         const int q = warp & 3;                                   // TMEM lane quarter of this warp
         const uint32_t stage_f32 = staging_base + (uint32_t)(warp - 2) * (uint32_t)((p.has_f32 ? 8192 : 0) + (p.has_planes ? 8192 : 0));
         const uint32_t stage_hi = stage_f32 + (p.has_f32 ? 8192u : 0u);
@@ -434,8 +527,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         int i = 0;
         bool stores_pending = false;
         const bool slope_le1 = p.slope >= 0.f && p.slope <= 1.f;
-        for (TileWalk w(p); w.valid(); w.next(p), ++i) {
-            const TileInfo t = tile_info(p, w.tile(p));
+        for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
+            const TileInfo t = tile_info<NCTA>(p, w.tile(p));
             const int a = i & 1;
             mbar_wait(smem_u32(&bar_acc_full[a]), (uint32_t)(i >> 1) & 1u);
             tcgen05_fence_after();
@@ -449,7 +542,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                 if (j == npanels - 1) {                           // accumulator drained: hand it back to the MMA warp
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[a]));
+                    if (lane == 0) {
+                        if constexpr (NCTA == 1) mbar_arrive(smem_u32(&bar_acc_empty[a]));
+                        else mbar_arrive_cluster(mapa_shared(smem_u32(&bar_acc_empty[a]), 0));
+                    }
                 }
                 // bias of the panel: lane l holds columns col0+l and col0+32+l
                 float b0 = 0.f, b1 = 0.f;
@@ -501,7 +597,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    const int row0 = t.m0 + q * 32;
+                    const int row0 = t.m0 + (int)rank * kBM + q * 32;
                     if (row0 < p.M) {
                         if (p.has_f32) {
                             if (col0 < p.N) tma_store_2d(&map_o_f32, stage_f32, col0, row0);
@@ -518,11 +614,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
             }
         }
         if (lane == 0) bulk_wait0();
-        if (p.dbg && threadIdx.x == 64) p.dbg[blockIdx.x * 4 + 1] = globaltimer_ns();
     }
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();       // the peer still arrives on the leader's barriers until here
+    if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -759,18 +854,21 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
-    B2_CHECK_ARG(impl == 0, "linear: impl must be 0 (tcgen05 persistent), 1 (simt self-test), 2 (manual-fill self-test) or 3 (v1)");
+    B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5, "linear: impl must be 0 (tcgen05 persistent, auto), 1 (simt self-test), "
+                 "2 (manual-fill self-test), 3 (v1), 4 (persistent, single CTA) or 5 (persistent, CTA pairs)");
     // ---- persistent kernel ----
     if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
     if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");
+    // CTA pairs (cta_group::2, 256-row tiles) whenever there are enough rows to fill the machine with pair tiles
+    const int ncta = (impl == 5) ? 2 : (impl == 4) ? 1 : (m >= 2 * kBM * (num_sms() / 2) ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
-    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = nullptr;
+    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0;
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
     q.tiles_n = ceil_div(q.panels_total, 4);
-    q.tiles_m = ceil_div(m, kBM);
+    q.tiles_m = ceil_div(m, kBM * ncta);
     q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
-    const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)q.stage_bn * kBK * 2;
+    const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)(q.stage_bn / ncta) * kBK * 2;
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
     int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -781,20 +879,32 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     int rc;
     if ((rc = make_map(&ma_hi, a_hi, m, kpad, lda, kBM))) return rc;
     if ((rc = make_map(&ma_lo, a_lo, m, kpad, lda, kBM))) return rc;
-    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, 64))) return rc;
-    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, 64))) return rc;
+    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, ncta == 1 ? 64 : 32))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, ncta == 1 ? 64 : 32))) return rc;
     mo_f32 = ma_hi; mo_hi = ma_hi; mo_lo = ma_hi;                              // placeholders when unused
     if (out_f32 && (rc = make_map_ex(&mo_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, m, n, ld_out, 32, 32))) return rc;
     if (out_hi) {
         if ((rc = make_map_ex(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, m, ld_planes, ld_planes, 64, 32))) return rc;
         if ((rc = make_map_ex(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, m, ld_planes, ld_planes, 64, 32))) return rc;
     }
-    // tall GEMMs (GAT projections: thousands of m-tiles, 1-2 n-tiles): sweep the n-tiles of an m-tile inside one CTA
-    q.group_n = (q.tiles_m >= 2 * num_sms()) ? q.tiles_n : 1;
+    // tall GEMMs (GAT projections: thousands of m-tiles, 1-2 n-tiles): sweep the n-tiles of an m-tile inside one worker
+    const int workers_max = num_sms() / ncta;
+    q.group_n = (q.tiles_m >= 2 * workers_max) ? q.tiles_n : 1;
     const int total_visits = q.tiles_m * ceil_div(q.tiles_n, q.group_n);
-    const int grid2 = total_visits < num_sms() ? total_visits : num_sms();
-    B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_split_tc2_kernel<<<grid2, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q);
-    B2_CHECK_LAUNCH();
+    const int workers = total_visits < workers_max ? total_visits : workers_max;
+    if (ncta == 1) {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_split_tc2_kernel<1><<<workers, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q);
+        B2_CHECK_LAUNCH();
+    } else {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * workers); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_tc2_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q));
+    }
     return B200POSE_OK;
 }

@@ -105,8 +105,10 @@ int b200pose_node_features(int32_t n_frames, int32_t n_heads_total, int32_t n_no
  * padding columns (>= N) are only ever written as zero; the caller zero-initialises plane buffers once
  * so the padding can be consumed as K padding by the next GEMM.
  * out_scale multiplies the result after the activation (x10 of metrics_from_model.py:282).
- * impl: 0 = tcgen05 + TMA tensor-core kernel (the product path); 1 = fp32 SIMT kernel and 2 = tcgen05
- * kernel with tiles filled by ordinary stores - both exist only for the kernel self-test.
+ * impl: 0 = persistent tcgen05 + TMA tensor-core kernel (the product path; CTA pairs with cta_group::2 MMAs and
+ * 256-row tiles when m is large, single CTAs otherwise); 4 / 5 force single CTAs / CTA pairs (A/B runs);
+ * 1 = fp32 SIMT kernel, 2 = tcgen05 kernel with tiles filled by ordinary stores, 3 = first one-tile-per-CTA
+ * kernel - these three exist only for the kernel self-test.
  * ------------------------------------------------------------------------------------------- */
 int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                     const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
