@@ -117,6 +117,50 @@ class HostBatch:
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.sk_xy, self.sk_vp, self.sk_mask, self.sk_cam, self.head_off, self.node_off))
 
+    frame_range = None       # (first, last+1) frame of the parent batch, set on chunks
+    head_range = None
+
+    def split(self, n_chunks: int):
+        """Contiguous runs of frames as HostBatch views that share this batch's pinned memory (offset arrays are
+        rebased copies). Cached: the split is part of packing, not of inference."""
+        n_chunks = max(1, min(int(n_chunks), max(self.pb.n_frames, 1)))
+        cache = self.__dict__.setdefault('_splits', {})
+        if n_chunks in cache:
+            return cache[n_chunks]
+        B = self.pb.n_frames
+        out = []
+        for k in range(n_chunks):
+            f0, f1 = (B * k) // n_chunks, (B * (k + 1)) // n_chunks
+            if n_chunks == 1:
+                ch = self
+            else:
+                sub = self.pb.slice(f0, f1)
+                h0, h1 = int(self.pb.head_off[f0]), int(self.pb.head_off[f1])
+                ch = HostBatch.__new__(HostBatch)
+                ch.pb = sub
+                ch.sk_xy, ch.sk_vp = self.sk_xy[h0:h1], self.sk_vp[h0:h1]
+                ch.sk_mask, ch.sk_cam = self.sk_mask[h0:h1], self.sk_cam[h0:h1]
+                pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+                ch.head_off = pin(torch.from_numpy(np.ascontiguousarray(sub.head_off)))
+                ch.node_off = pin(torch.from_numpy(np.ascontiguousarray(sub.node_off)))
+            ch.frame_range = (f0, f1)
+            ch.head_range = (int(self.pb.head_off[f0]), int(self.pb.head_off[f1]))
+            out.append(ch)
+        cache[n_chunks] = out
+        return out
+
+    def result_buffers(self, n_cameras: int, n_out: int):
+        """Pinned host buffers for the results of this batch (persons <= heads / 2: a person needs two views)."""
+        key = (n_cameras, n_out)
+        cache = self.__dict__.setdefault('_results', {})
+        if key not in cache:
+            B, Pmax = self.pb.n_frames, max(self.pb.n_heads // 2, 1)
+            mk = lambda shape, dt: (torch.empty(shape, dtype=dt).pin_memory() if torch.cuda.is_available() else torch.empty(shape, dtype=dt))
+            cache[key] = dict(n_persons=mk((B,), torch.int32), person_off=mk((B + 1,), torch.int32),
+                              person_sk=mk((Pmax, n_cameras), torch.int32), joints=mk((Pmax, max(n_out, 1)), torch.float32),
+                              valid=mk((Pmax,), torch.uint8))
+        return cache[key]
+
     def to_device(self, device) -> DeviceBatch:
         pb = self.pb
         cp = lambda t: t.to(device, non_blocking=True)
@@ -412,33 +456,156 @@ class PosePipeline:
         return out[:P, :n_out]
 
     # ------------------------------------------------------------------ whole path
-    def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):
-        """graph build -> GAT -> clustering -> encoder -> MLP for every frame of the batch."""
+    def stage_a(self, db: DeviceBatch, with_coo: bool = False):
+        """Stages 1-2 of a batch, enqueued without any host synchronisation: graph build, GAT, clustering and the
+        exclusive scan of the person counts."""
         g = self.build_graph(db, with_coo=with_coo)
-        scores = self.gat_forward(db, g)
+        scores = self.gat_forward(db, g) if db.n_nodes > 0 else torch.zeros(1, dtype=torch.float32, device=self.device)
         person_heads, n_persons = self.cluster(db, g, scores)
-        P, person_off, person_sk, person_frame = self.gather_persons(db, person_heads, n_persons)
-        res = dict(graph=g, scores=scores, person_heads=person_heads, n_persons=n_persons, person_off=person_off,
-                   person_sk=person_sk, person_frame=person_frame, n_persons_total=P)
+        person_off = torch.empty(db.n_frames + 1, dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(person_heads), ptr(n_persons), ptr(person_off), 1,
+                                             ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref, None, None, self._stream()), 'scan')
+        return dict(graph=g, scores=scores, person_heads=person_heads, n_persons=n_persons, person_off=person_off)
+
+    def stage_b(self, db: DeviceBatch, res: dict, want_triangulation: bool = False):
+        """Stage 3 of a batch. Reads the person count back (one 4-byte device->host copy: it sizes the launches),
+        then person list, MLP-input encoder and MLP."""
+        P = int(res['person_off'][db.n_frames].item())
+        Cn = self.cfg.n_cameras
+        person_sk = torch.empty((max(P, 1), Cn), dtype=torch.int32, device=self.device)
+        person_frame = torch.empty(max(P, 1), dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
+                                             ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
+                                             ptr(person_sk), ptr(person_frame), self._stream()), 'gather_persons')
+        res.update(person_sk=person_sk[:P], person_frame=person_frame[:P], n_persons_total=P)
         if self.mlp is not None:
             if P > 0:
-                x, valid, _ = self.encode_persons(db, P, person_sk)
+                x, valid, _ = self.encode_persons(db, P, res['person_sk'])
                 res['valid'] = valid
                 res['joints'] = self.mlp_forward(x, P)
             else:
                 res['valid'] = torch.zeros(0, dtype=torch.uint8, device=self.device)
                 res['joints'] = torch.zeros((0, self.mlp[-1]['n']), dtype=torch.float32, device=self.device)
         if want_triangulation and P > 0:
-            res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, person_sk)
+            res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, res['person_sk'])
         return res
 
-    def infer_host(self, hb: HostBatch, **kw):
-        """The public end-to-end call: pinned host buffers in, host results out."""
-        db = hb.to_device(self.device)
-        res = self.infer(db, **kw)
-        out = dict(n_persons=res['n_persons'].cpu(), person_off=res['person_off'].cpu(),
-                   person_sk=res['person_sk'].cpu(), n_persons_total=res['n_persons_total'])
-        if 'joints' in res:
-            out['joints'] = res['joints'].cpu()
-            out['valid'] = res['valid'].cpu()
+    def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):
+        """graph build -> GAT -> clustering -> encoder -> MLP for every frame of a batch resident in HBM."""
+        return self.stage_b(db, self.stage_a(db, with_coo=with_coo), want_triangulation=want_triangulation)
+
+    def infer_host(self, hb: HostBatch, n_chunks: int = 1):
+        """The public end-to-end call: pinned host buffers in, host results out.
+
+        With n_chunks > 1 the batch is cut into runs of frames: all host->device copies are enqueued up front on a
+        copy stream and the compute stream runs stage A of chunk i+1 before it waits for the person count of chunk i.
+        Measured on B200 (scripts/e2e_probe.py) this does NOT pay for the reference-sized batch: every extra chunk
+        costs ~0.8 ms of fixed work (the MLP re-streams its 116 MB of weights per chunk, persistent GEMMs refill
+        their pipelines) against 0.36 ms of copy time to hide, so the default is one chunk; to overlap copies with
+        compute use infer_host_stream(), which prefetches the NEXT batch instead. Results are in frame order."""
+        chunks = hb.split(n_chunks)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        dbs, evs = [], []
+        with torch.cuda.stream(cs):
+            for ch in chunks:
+                db = ch.to_device(self.device)
+                for t in (db.sk_xy, db.sk_vp, db.sk_mask, db.sk_cam, db.head_off, db.node_off):
+                    t.record_stream(cur)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                dbs.append(db); evs.append(ev)
+        out_bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0)
+        parts = []
+        p_base = 0
+
+        def finish(i):
+            nonlocal p_base
+            db, ch = dbs[i], chunks[i]
+            res = self.stage_b(db, staged[i])
+            P = res['n_persons_total']
+            f0, f1 = ch.frame_range
+            out_bufs['n_persons'][f0:f1].copy_(res['n_persons'], non_blocking=True)
+            out_bufs['person_off'][f0:f1 + 1].copy_(res['person_off'], non_blocking=True)
+            if P > 0:
+                out_bufs['person_sk'][p_base:p_base + P].copy_(res['person_sk'], non_blocking=True)
+                if 'joints' in res:
+                    out_bufs['joints'][p_base:p_base + P].copy_(res['joints'], non_blocking=True)
+                    out_bufs['valid'][p_base:p_base + P].copy_(res['valid'], non_blocking=True)
+            parts.append((f0, f1, p_base, P, ch.head_range[0]))
+            p_base += P
+
+        staged = []
+        for i, db in enumerate(dbs):
+            cur.wait_event(evs[i])
+            staged.append(self.stage_a(db))
+            if i >= 1:
+                finish(i - 1)
+        finish(len(dbs) - 1)
+        cur.synchronize()
+        # chunk-local -> batch-global indices (host side, a few KB)
+        P_tot = p_base
+        person_off = out_bufs['person_off'].numpy()
+        person_sk = out_bufs['person_sk'].numpy()
+        for f0, f1, pb0, P, h0 in parts:
+            person_off[f0:f1 + 1] += pb0 if f0 > 0 else 0
+            if h0:
+                blk = person_sk[pb0:pb0 + P]
+                blk[blk >= 0] += h0
+        # person_off of chunk k > 0 was written over [f0, f1]: entry f0 equals the previous chunk's total by construction
+        out = dict(n_persons=out_bufs['n_persons'], person_off=out_bufs['person_off'], person_sk=out_bufs['person_sk'][:P_tot],
+                   n_persons_total=P_tot)
+        if self.mlp is not None:
+            out['joints'] = out_bufs['joints'][:P_tot]
+            out['valid'] = out_bufs['valid'][:P_tot]
         return out
+
+    def infer_host_stream(self, batches):
+        """Generator over host batches: yields the host results of each batch, in order. The host->device copy of
+        batch i+1 is enqueued on a copy stream before batch i is computed, so in steady state the copies ride under
+        the compute of the previous batch (the serving loop of a camera rig: pack frames -> infer -> consume)."""
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        it = iter(batches)
+
+        def prefetch():
+            try:
+                hb = next(it)
+            except StopIteration:
+                return None
+            with torch.cuda.stream(cs):
+                db = hb.to_device(self.device)
+                for t in (db.sk_xy, db.sk_vp, db.sk_mask, db.sk_cam, db.head_off, db.node_off):
+                    t.record_stream(cur)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return hb, db, ev
+
+        nxt = prefetch()
+        while nxt is not None:
+            hb, db, ev = nxt
+            nxt = prefetch()                                   # the next batch's copy is in flight during this compute
+            cur.wait_event(ev)
+            res = self.infer(db)
+            P = res['n_persons_total']
+            bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0)
+            bufs['n_persons'].copy_(res['n_persons'], non_blocking=True)
+            bufs['person_off'].copy_(res['person_off'], non_blocking=True)
+            if P > 0:
+                bufs['person_sk'][:P].copy_(res['person_sk'], non_blocking=True)
+                if 'joints' in res:
+                    bufs['joints'][:P].copy_(res['joints'], non_blocking=True)
+                    bufs['valid'][:P].copy_(res['valid'], non_blocking=True)
+            cur.synchronize()
+            out = dict(n_persons=bufs['n_persons'], person_off=bufs['person_off'], person_sk=bufs['person_sk'][:P], n_persons_total=P)
+            if self.mlp is not None:
+                out['joints'] = bufs['joints'][:P]
+                out['valid'] = bufs['valid'][:P]
+            yield out

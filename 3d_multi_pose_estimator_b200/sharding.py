@@ -1,0 +1,78 @@
+"""Frame sharding across the GPUs of one box.
+
+Frames are independent (the reference keeps no cross-frame state, test/metrics_from_model.py:120-300), so a batch
+is cut into contiguous blocks of frames, one block per rank, with weights and camera tables replicated. There is no
+collective on the hot path; the only exchange is ONE all-gather of fixed-size result records at the end of a step.
+The record layout is plain int32 words so it travels through NCCL (device tensors) and gloo (CPU tensors, tests)
+alike: [n_persons_total | n_persons[F] | person_sk[Pcap, C] | joints[Pcap, J] as raw fp32 bits].
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+
+def shard_range(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of `rank`: ceil(n_frames / world) frames per rank, the tail ranks may be short/empty."""
+    per = -(-n_frames // world) if world > 0 else n_frames
+    lo = min(n_frames, rank * per)
+    return lo, min(n_frames, lo + per)
+
+
+def record_words(frames_cap: int, persons_cap: int, n_cameras: int, n_out: int) -> int:
+    return 1 + frames_cap + persons_cap * n_cameras + persons_cap * n_out
+
+
+def pack_record(n_persons: torch.Tensor, person_sk: torch.Tensor, joints: torch.Tensor, frames_cap: int, persons_cap: int,
+                n_cameras: int, n_out: int, head_base: int = 0) -> torch.Tensor:
+    """One rank's results as a fixed-size int32 record (padded with -1 / 0). `head_base` turns the rank-local
+    skeleton indices of person_sk into indices of the whole batch."""
+    dev = n_persons.device
+    F, P = int(n_persons.numel()), int(person_sk.shape[0])
+    if F > frames_cap or P > persons_cap:
+        raise ValueError('result does not fit the record (%d/%d frames, %d/%d persons)' % (F, frames_cap, P, persons_cap))
+    rec = torch.zeros(record_words(frames_cap, persons_cap, n_cameras, n_out), dtype=torch.int32, device=dev)
+    rec[0] = P
+    rec[1:1 + F] = n_persons.to(torch.int32)
+    o = 1 + frames_cap
+    sk = torch.full((persons_cap, n_cameras), -1, dtype=torch.int32, device=dev)
+    if P:
+        psk = person_sk.to(torch.int32)
+        sk[:P] = torch.where(psk >= 0, psk + head_base, psk)
+    rec[o:o + persons_cap * n_cameras] = sk.reshape(-1)
+    o += persons_cap * n_cameras
+    if P and n_out:
+        rec[o:o + P * n_out] = joints.to(torch.float32).contiguous().view(torch.int32).reshape(-1)
+    return rec
+
+
+def all_gather_records(rec: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """The single collective of a step: [world, words] records of every rank (identity for world == 1)."""
+    if world == 1:
+        return rec.reshape(1, -1)
+    import torch.distributed as dist
+    out = torch.empty(world * rec.numel(), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    return out.reshape(world, -1)
+
+
+def unpack_records(gathered: torch.Tensor, frames_per_rank: List[int], frames_cap: int, persons_cap: int, n_cameras: int,
+                   n_out: int) -> Dict[str, np.ndarray]:
+    """Concatenates the ranks' results in frame order: n_persons[F_total], person_off[F_total+1], person_sk[P_total, C],
+    joints[P_total, n_out]."""
+    g = gathered.cpu()
+    n_persons, sks, joints = [], [], []
+    for r, F in enumerate(frames_per_rank):
+        rec = g[r]
+        P = int(rec[0])
+        n_persons.append(rec[1:1 + F].numpy())
+        o = 1 + frames_cap
+        sks.append(rec[o:o + persons_cap * n_cameras].reshape(persons_cap, n_cameras)[:P].numpy())
+        o += persons_cap * n_cameras
+        joints.append(rec[o:o + P * n_out].contiguous().view(torch.float32).reshape(P, n_out).numpy())
+    n_persons = np.concatenate(n_persons) if n_persons else np.zeros(0, np.int32)
+    return dict(n_persons=n_persons, person_off=np.concatenate([[0], np.cumsum(n_persons)]).astype(np.int32),
+                person_sk=np.concatenate(sks) if sks else np.zeros((0, n_cameras), np.int32),
+                joints=np.concatenate(joints) if joints else np.zeros((0, n_out), np.float32))
