@@ -178,6 +178,8 @@ def main():
     ap.add_argument('--config', default='panoptic')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
+    ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation'],
+                    help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
     ap.add_argument('--latency-frames', type=int, default=200, help='single-frame calls timed for p50_frame_latency_ms')
     args = ap.parse_args()
@@ -190,6 +192,8 @@ def main():
                    'persons_per_frame': args.persons, 'weights': 'random-init (seeded) + last-layer bias calibration',
                    'l2': 'L2 flushed (256 MiB write) between timed iterations'}
 
+    if args.workload == 'triangulation':
+        return triangulation_workload(args, rank, world, local_rank)
     # ------------------------------------------------------------------ reference arm (CPU port)
     if args.impl == 'reference':
         if rank != 0:
@@ -353,8 +357,14 @@ def main():
                 entry['frac'] = entry['achieved'] / entry['peak']
             kernels.append(entry)
         dominant = max([k for k in kernels if 'frac' in k], key=lambda k: k['ms_per_step'])
+        traffic = None
+        try:                                      # DRAM bytes of the class from the committed ncu capture (per step)
+            traffic = json.load(open(os.path.join(REPO, 'profiles', 'r01_traffic.json'))).get(dominant['kernel'])
+        except Exception:
+            pass
         roofline = {'kernel': dominant['kernel'], 'bound': dominant['bound'], 'achieved': dominant['achieved'],
-                    'peak': dominant['peak'], 'unit': dominant['unit'], 'frac': dominant['frac'], 'traffic': None,
+                    'peak': dominant['peak'], 'unit': dominant['unit'], 'frac': dominant['frac'], 'traffic': traffic,
+                    'traffic_note': 'dram bytes read+written per step by this kernel class, ncu --set full (profiles/r01_traffic.json)',
                     'peak_source': peak_src + (' (bf16 sustained; achieved counts the 3 executed split-bf16 MMAs)'
                                                if dominant['bound'] == 'tensor' else '')}
         cpu_fps, cpu_n, cpu_dt, cpu_procs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=args.cpu_budget,
@@ -375,6 +385,74 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def triangulation_workload(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: triangulation-only path, batched DLT for 5 views x 18 joints x 65536 persons
+    (utils/pose_estimator_utils.py:52-75 fed as test/metrics_from_triangulation.py:237-249). Secondary workload:
+    its own metric, printed as one JSON line like the headline."""
+    import torch
+    pkg = importlib.import_module('3d_multi_pose_estimator_b200')
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    pm = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+    cfg = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
+    P, C = 65536, cfg.n_cameras
+    rng = np.random.default_rng(rank)
+    people = synth.random_people(cfg, rng, 256)
+    xy = np.zeros((256 * C, 18, 2)); mask = np.full(256 * C, (1 << 18) - 1, dtype=np.uint32)
+    for p in range(256):
+        for c in range(C):
+            xy[p * C + c] = synth.project_points(cfg, c, people[p])[0]
+    reps = P // 256
+    h_xy = torch.from_numpy(np.tile(xy, (reps, 1, 1))).pin_memory()
+    h_mask = torch.from_numpy(np.tile(mask, reps).view(np.int32)).pin_memory()
+    h_psk = torch.arange(P * C, dtype=torch.int32).reshape(P, C).pin_memory()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    pipe = pm.PosePipeline(cfg, None, None, device=dev)
+    mk = lambda: pm.DeviceBatch(0, P * C, P * C, 0, 0, h_xy.to(dev, non_blocking=True), None, h_mask.to(dev, non_blocking=True), None, None, None)
+    db, psk = mk(), h_psk.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(max(3, args.warmup)):
+        pipe.triangulate(db, P, psk)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1); a.record(); xyz, m = pipe.triangulate(db, P, psk); b.record()
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2, p2 = mk(), h_psk.to(dev, non_blocking=True)
+        xyz, m = pipe.triangulate(d2, P, p2)
+        hx, hm = xyz.cpu(), m.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    # CPU port on a bounded sample (one process)
+    from oracle import pose_oracle as O
+    tabs = O.CameraTables(cfg)
+    persons = [{cfg.camera_names[c]: {str(j): [j, xy[p * C + c, j, 0], xy[p * C + c, j, 1], 1, 1] for j in range(18)} for c in range(C)} for p in range(64)]
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < min(args.cpu_budget, 10.0):
+        O.triangulate_baseline(persons[n % 64], tabs, cfg.median_axis); n += 1
+    cpu = n / (time.perf_counter() - t0)
+    solves = P * 18 * C * (C - 1) // 2
+    in_bytes = P * C * (18 * 16 + 4 + 4); out_bytes = P * 18 * 25
+    line = {'metric': 'persons/sec (triangulation-only, %d views x 18 joints, 65536 persons)' % C, 'value': P / ms * 1e3, 'unit': 'persons/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64 (fp32 Jacobi start + fp64 Rayleigh-quotient refinement)', 'data': 'synthetic',
+            'config': {'workload': 'triangulation-only: batched pairwise DLT, %d views x 18 joints x %d persons' % (C, P), 'camera_config': args.config,
+                       'l2': 'L2 flushed (256 MiB write) between timed iterations'},
+            'pair_solves_per_s': solves / ms * 1e3,
+            'e2e': {'value': P / e2e_ms * 1e3, 'unit': 'persons/s', 'h2d_bytes_per_step': int(h_xy.numel() * 8 + h_mask.numel() * 4 + h_psk.numel() * 4),
+                    'd2h_bytes_per_step': int(out_bytes), 'ms_per_step': e2e_ms},
+            'gpu_launches': 1,
+            'roofline': {'kernel': 'lift_person_kernel<false>', 'bound': 'hbm', 'achieved': (in_bytes + out_bytes) / ms / 1e6, 'peak': 6471.1, 'unit': 'GB/s',
+                         'frac': (in_bytes + out_bytes) / ms / 1e6 / 6471.1, 'traffic': None,
+                         'note': 'ALU-bound kernel (pairwise 4x4 solves), HBM fraction reported for completeness'},
+            'cpu_baseline': {'value': cpu, 'unit': 'persons/s', 'cores': 1, 'kind': 'port', 'sample': '%d persons, one process' % n}}
+    if rank == 0:
+        print(json.dumps(line))
 
 
 def profile_classes(pipe, db, pm, torch):

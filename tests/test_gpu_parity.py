@@ -353,3 +353,55 @@ def test_empty_and_degenerate_batches():
     res = pipe.infer(db)
     assert res['n_persons'].cpu().numpy().tolist() == [0, 0]
     assert res['n_persons_total'] == 0
+
+
+def test_triangulation_full_size_properties():
+    """BASELINE config 4 (triangulation-only: 5 views x 18 joints x 65536 persons): exact projections of known 3D
+    points must come back (pairwise DLT is exact for consistent rays), a sample must equal the oracle's cv2-equivalent
+    result, and the result must not depend on the position of a person in the batch."""
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    rng = np.random.default_rng(7)
+    P, C = 65536, cfg.n_cameras
+    people = helpers.synth.random_people(cfg, rng, 64)                       # [64,18,3] metres
+    xy = np.zeros((64 * C, 18, 2))
+    mask = np.zeros(64 * C, dtype=np.uint32)
+    for p in range(64):
+        for c in range(C):
+            uv, z = helpers.synth.project_points(cfg, c, people[p])
+            xy[p * C + c] = uv
+            mask[p * C + c] = (1 << 18) - 1 if p % 5 else 0x3FFFE                # every 5th person lacks joint 0 in all views
+    reps = P // 64
+    sk_xy = torch.from_numpy(np.tile(xy, (reps, 1, 1))).cuda()
+    sk_mask = torch.from_numpy(np.tile(mask, reps).view(np.int32)).cuda()
+    person_sk = torch.arange(P * C, dtype=torch.int32, device='cuda').reshape(P, C)
+    # every 7th person is seen by cameras 1 and 3 only, every 11th by one camera only (no triangulation)
+    person_sk[::7, 0] = -1; person_sk[::7, 2] = -1; person_sk[::7, 4] = -1
+    person_sk[::11, 1:] = -1
+    db = pipeline_mod.DeviceBatch(0, P * C, P * C, 0, 0, sk_xy, None, sk_mask, None, None, None)
+    xyz, m = pipe.triangulate(db, P, person_sk)
+    xyz, m = xyz.cpu().numpy(), m.cpu().numpy()
+    psk = person_sk.cpu().numpy()
+    n_views = (psk >= 0).sum(1)
+    assert np.array_equal(m[n_views < 2], np.zeros_like(m[n_views < 2]))
+    seen = n_views >= 2
+    want_mask = np.ones((P, 18), np.uint8)
+    want_mask[np.arange(P) % 64 % 5 == 0, 0] = 0
+    assert np.array_equal(m[seen], want_mask[seen])
+    truth = np.tile(people, (reps, 1, 1))
+    err = np.abs(xyz - truth)[m.astype(bool)]
+    assert err.max() < 1e-4, err.max()                  # limited by the 5 fixed-point undistortion iterations (cv2 behaviour), not by the DLT
+    # position independence: identical persons give bit-identical joints
+    same = [i for i in range(64, P, 64 * 77) if np.array_equal(psk[i] >= 0, psk[i % 64] >= 0)]
+    for i in same[:50]:
+        assert np.array_equal(xyz[i], xyz[i % 64])
+    # a sample against the oracle
+    tabs = O.CameraTables(cfg)
+    for p in (1, 7, 14, 33):
+        person = {cfg.camera_names[c]: {str(j): [j, xy[(p % 64) * C + c, j, 0], xy[(p % 64) * C + c, j, 1], 1, 1]
+                                        for j in range(18) if (mask[(p % 64) * C + c] >> j) & 1}
+                  for c in range(C) if psk[p, c] >= 0}
+        ref, rm = O.triangulate_baseline(person, tabs, cfg.median_axis)
+        assert np.array_equal(rm, m[p])
+        assert np.abs(ref - xyz[p]).max() < 1e-9
