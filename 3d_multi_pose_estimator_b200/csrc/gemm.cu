@@ -859,8 +859,10 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     // ---- persistent kernel ----
     if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
     if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");
-    // CTA pairs (cta_group::2, 256-row tiles) whenever there are enough rows to fill the machine with pair tiles
-    const int ncta = (impl == 5) ? 2 : (impl == 4) ? 1 : (m >= 2 * kBM * (num_sms() / 2) ? 2 : 1);
+    // CTA pairs (cta_group::2, 256-row tiles) as soon as there is more than one pair tile of rows: per flop a pair pulls
+    // 1.5x fewer bytes through the L2->SM fabric, which bounds both the tall GAT projections and the MLP (every m-tile
+    // re-reads the whole weight matrix from L2)
+    const int ncta = (impl == 5) ? 2 : (impl == 4) ? 1 : (m > 2 * kBM ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
     q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0;
