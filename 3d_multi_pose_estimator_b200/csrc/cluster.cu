@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
     unsigned* cams_for = reinterpret_cast<unsigned*>(ip); ip += p.max_heads;
     int* flag = ip;             ip += p.max_heads;
     int* tab_a = ip;            ip += p.table_cap;
-    int* tab_b = ip;
+    int* tab_b = ip;            ip += p.table_cap;
+    int* prs = ip;                                                  // (h1, h2) of every edge-node: read once, coalesced
 
     if (H > p.max_heads || M > p.max_keys || H == 0) {              // outside the sized limits: no persons
         if (lane == 0) p.n_persons[b] = 0;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
         if (k < M) {
             h1 = p.pairs[2 * (m0 + k)];
             h2 = p.pairs[2 * (m0 + k) + 1];
+            prs[2 * k] = h1; prs[2 * k + 1] = h2;
             const float s = p.scores[n0 + H + k];
             if ((double)s > p.threshold)
                 key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
         if (key == 0ull) break;
         __syncwarp();
         const int k = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-        const int h1 = p.pairs[2 * (m0 + k)], h2 = p.pairs[2 * (m0 + k) + 1];
+        const int h1 = prs[2 * k], h2 = prs[2 * k + 1];
         int a, c;
         pair_order(h1, h2, a, c);
         const unsigned ca = 1u << cam[a], cc = 1u << cam[c];
@@ -317,7 +319,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
     while (keys < max_enodes_per_frame) keys <<= 1;
     p.max_keys = keys;
     p.table_cap = set_table_capacity(p.max_heads);
-    const size_t smem = (size_t)p.max_keys * 8 + (size_t)p.max_heads * 7 * 4 + (size_t)p.table_cap * 2 * 4;
+    const size_t smem = (size_t)p.max_keys * 8 + (size_t)p.max_heads * 7 * 4 + (size_t)p.table_cap * 2 * 4 + (size_t)p.max_keys * 2 * 4;
     if (smem > 200 * 1024) {
         set_error("cluster: frame too large for the shared-memory plan (%zu bytes: %d heads, %d edge-nodes)", smem,
                   max_heads_per_frame, max_enodes_per_frame);

@@ -190,6 +190,28 @@ int b200pose_gather_persons(int32_t n_frames, const int32_t* head_off, const int
                             const int32_t* sk_cam, int32_t v_sm, const b200pose_cameras* cams_host,
                             int32_t* person_sk, int32_t* person_frame, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host-side frame packer (no GPU work): the reference's frame JSON - a list of frames
+ * {camera: [json.dumps([skeleton, ...]), timestamp, ...]} as read by test/metrics_from_model.py:117-191, or one such
+ * frame - parsed in parallel into the packed skeleton batch above. Replaces json.loads + the per-joint Python loops of
+ * graph_generator.py:573-605. cam_names[i] -> cam_index[i] lists the cameras of used_cameras_skeleton_matching;
+ * other cameras are skipped. Numbers are converted exactly like Python's float().
+ *   b200pose_pack_json   : parses; *out_handle owns the result until b200pose_packed_free
+ *   b200pose_packed_sizes: frame / head / node counts and the per-frame maxima the kernels are sized with
+ *   b200pose_packed_copy : writes the arrays into caller-provided HOST buffers (pinned memory works best):
+ *                          sk_xy [S,18,2] f64, sk_vp [S,18,2] f32, sk_mask [S] u32, sk_cam [S] i32, head_off/node_off [B+1] i32,
+ *                          skeleton_index [S] i32 (position of the skeleton in its camera's list; may be null)
+ * n_threads <= 0 uses every hardware thread.
+ * ------------------------------------------------------------------------------------------- */
+int b200pose_pack_json(const char* json_host, int64_t len, int32_t n_cams, const char* const* cam_names_host,
+                       const int32_t* cam_index_host, int32_t n_threads, void** out_handle);
+int b200pose_packed_sizes(const void* handle, int32_t* n_frames, int32_t* n_heads, int32_t* n_nodes,
+                          int32_t* max_heads, int32_t* max_enodes);
+int b200pose_packed_copy(const void* handle, double* sk_xy_host, float* sk_vp_host, uint32_t* sk_mask_host,
+                         int32_t* sk_cam_host, int32_t* head_off_host, int32_t* node_off_host,
+                         int32_t* skeleton_index_host, int32_t n_threads);
+void b200pose_packed_free(void* handle);
+
 #ifdef __cplusplus
 }
 #endif
