@@ -185,26 +185,29 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
 // ------------------------------------------------------------------------------------------------
 // Frame-resident kernel (the product path whenever a frame's plan fits in shared memory).
 //
-// One CTA (16 warps) per frame; every z row of the frame leaves HBM exactly once per layer:
-//   * the head rows are staged in shared memory for the whole frame;
-//   * the edge-node rows - one contiguous block of M_b rows - stream through a double-buffered
-//     shared-memory ring in chunks of kChunkRows rows, fetched by 1-D bulk async copies (cp.async.bulk,
-//     mbarrier complete_tx), so the copy of chunk c+1 overlaps the arithmetic on chunk c and costs no
-//     registers or issue slots;
-//   * for every chunk, warps take (a) the edge-node destinations of the chunk - warp per destination,
-//     two head rows + the node's own row, all from shared memory - and (b) the contributions of the chunk's
-//     rows to the head destinations they own (warp w owns heads w and w+16; the accumulators of a head stay
-//     in registers across chunks, its in-edge list is walked in ascending edge id).
-// Lanes own VEC consecutive columns of KMAX column groups, so every row access is a coalesced vector sweep.
+// One CTA per frame: 16 consumer warps + 1 producer warp. Every z row of the frame leaves HBM exactly once
+// per layer:
+//   * the head rows (and their a1|a2 attention scalars) are staged in shared memory for the whole frame;
+//   * the edge-node rows - one contiguous block of M_b rows - stream through a kSlots-deep shared-memory ring
+//     in chunks of kChunkRows rows, fetched by 1-D bulk async copies (cp.async.bulk, mbarrier complete_tx)
+//     issued by the producer warp; consumer warps hand a slot back through an "empty" mbarrier, so there is
+//     no CTA-wide barrier in the steady state and the copies of later chunks overlap the arithmetic;
+//   * per chunk, consumer warp w takes (a) edge-node destination k0+w - warp per destination: two head rows +
+//     the node's own row from shared memory, its three softmax weights computed on the fly from the a1|a2
+//     columns of those rows - and (b) the contributions of the chunk's rows to the head destinations it owns
+//     (heads w and w+16; their accumulators stay in registers across chunks, their in-edge lists are walked in
+//     ascending edge id with weights precomputed in phase 1).
+// Lanes own VEC consecutive columns of KMAX column groups: every row access is a coalesced vector sweep.
 // The summation order per output element is ascending reference edge id, exactly as in the gather kernel.
-//   phase 1: stage a1|a2 of every node, head rows, in-edge lists; thread per (destination, attention head)
-//            computes the softmax weights of its in-edges (gat2.py:78-88) into shared memory
+//   phase 1: stage head rows, a1|a2 of heads, a1 of edge-nodes, in-edge lists of the heads; one thread per
+//            (head destination, attention head) computes the softmax weights of its in-edges (gat2.py:78-88)
 //   phase 2: chunk loop as above
 // ------------------------------------------------------------------------------------------------
-constexpr int kFrameWarps = 16;
-constexpr int kFrameThreads = kFrameWarps * 32;
-constexpr int kFrameOwn = 2;                                // head destinations per warp
-constexpr int kChunkRows = 32;
+constexpr int kFrameWarps = 16;                             // consumer warps
+constexpr int kFrameThreads = (kFrameWarps + 1) * 32;       // + the producer warp
+constexpr int kFrameOwn = 2;                                // head destinations per consumer warp
+constexpr int kChunkRows = kFrameWarps;                     // one edge-node destination per consumer warp and chunk
+constexpr int kSlots = 4;
 
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
@@ -212,6 +215,9 @@ __device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void agg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void agg_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -232,19 +238,22 @@ __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uin
 }
 
 struct FramePlan {          // shared-memory plan of one frame (element offsets into a float array)
-    int zh, ze, buf, w, a12, lists, total_floats;
+    int ring, zh, ze, ah, a1e, wh, lsth, prs, total_floats;
 };
 
 __host__ __device__ inline FramePlan frame_plan(int max_heads, int max_enodes, int HD, int H, int ldz) {
     FramePlan f;
     const int hd4 = (HD + 3) & ~3;
+    const int e_heads = max_heads + 2 * max_enodes;                     // in-edges of all head destinations of a frame
     int o = 0;
-    f.buf = o; o += 2 * kChunkRows * ldz;                               // bulk-copy destinations first: 16-byte aligned
+    f.ring = o; o += kSlots * kChunkRows * ldz;                         // bulk-copy destinations first: 16-byte aligned
     f.zh = o; o += max_heads * hd4;
-    f.ze = o; o += hd4;                                                 // layer 0: the shared edge-node row
-    f.w = o; o += ((max_heads + 5 * max_enodes) * H + 3) & ~3;          // softmax weight of every in-edge, CSR order
-    f.a12 = o; o += ((max_heads + max_enodes) * 2 * H + 3) & ~3;        // a1|a2 of every node (phase 1)
-    f.lists = o; o += (max_heads + 5 * max_enodes + 3) & ~3;            // frame-local CSR column indices
+    f.ze = o; o += ldz;                                                 // layer 0: the shared edge-node row, a1|a2 included
+    f.ah = o; o += (max_heads * 2 * H + 3) & ~3;                        // a1|a2 of the heads
+    f.a1e = o; o += (max_enodes * H + 3) & ~3;                          // a1 of the edge-nodes (phase 1)
+    f.wh = o; o += (e_heads * H + 3) & ~3;                              // softmax weights of the heads' in-edges, CSR order
+    f.lsth = o; o += (e_heads + 3) & ~3;                                // frame-local sources of the heads' in-edges
+    f.prs = o; o += (2 * max_enodes + 3) & ~3;                          // (h1, h2) of every edge-node
     f.total_floats = o;
     return f;
 }
@@ -294,7 +303,8 @@ template <int VEC, int KMAX>
 __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(AggParams p, int max_heads, int max_enodes)
 {
     extern __shared__ __align__(128) float smem_f[];
-    __shared__ __align__(8) uint64_t bar_full[2];
+    __shared__ __align__(8) uint64_t bar_full[kSlots];
+    __shared__ __align__(8) uint64_t bar_empty[kSlots];
     const int b = blockIdx.x;
     const int n0 = p.node_off[b];
     const int Nb = p.node_off[b + 1] - n0;
@@ -302,75 +312,81 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
     const int h0 = p.head_off[b];
     const int Hb = p.head_off[b + 1] - h0;
     const int Mb = Nb - Hb;
-    const int Eb = Hb + 5 * Mb;
+    const int Eh = Hb + 2 * Mb;                             // in-edges of the head destinations (CSR: head rows come first)
     const int e0 = h0 + 5 * (n0 - h0);                      // first edge (CSR position) of the frame
     const int H = p.heads, D = p.dim, HD = H * D, ldz = p.ldz;
     const int hd4 = (HD + 3) & ~3;
     const FramePlan f = frame_plan(max_heads, max_enodes, HD, H, ldz);
-    float* buf = smem_f + f.buf;
+    float* ring = smem_f + f.ring;
     float* zh = smem_f + f.zh;
     float* zE = smem_f + f.ze;
-    float* w = smem_f + f.w;
-    float* a12 = smem_f + f.a12;
-    int* lst = reinterpret_cast<int*>(smem_f + f.lists);    // col[e0 + i] - n0 for every in-edge position i of the frame
+    float* ah = smem_f + f.ah;
+    float* a1e = smem_f + f.a1e;
+    float* wh = smem_f + f.wh;
+    int* lsth = reinterpret_cast<int*>(smem_f + f.lsth);
+    int* prs = reinterpret_cast<int*>(smem_f + f.prs);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool streamed = !p.layer0 && Mb > 0;
     const int n_chunks = (Mb + kChunkRows - 1) / kChunkRows;
-    const uint32_t bar0 = agg_smem_u32(&bar_full[0]), bar1 = agg_smem_u32(&bar_full[1]);
     const float* zen = p.z + (size_t)(n0 + Hb) * ldz;       // first edge-node row of the frame (not layer 0)
-    auto issue_chunk = [&](int c) {                         // one thread: bulk copy of chunk c into ring slot c & 1
+    auto issue_chunk = [&](int c) {                         // one thread: bulk copy of chunk c into ring slot c % kSlots
         const int rows = min(kChunkRows, Mb - c * kChunkRows);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)ldz * 4u;
-        const uint32_t bar = (c & 1) ? bar1 : bar0;
+        const uint32_t bar = agg_smem_u32(&bar_full[c % kSlots]);
         agg_mbar_expect_tx(bar, bytes);
-        agg_bulk_load(agg_smem_u32(buf + (size_t)(c & 1) * kChunkRows * ldz), zen + (size_t)c * kChunkRows * ldz, bytes, bar);
+        agg_bulk_load(agg_smem_u32(ring + (size_t)(c % kSlots) * kChunkRows * ldz), zen + (size_t)c * kChunkRows * ldz, bytes, bar);
     };
-    if (tid == 0) {
-        agg_mbar_init(bar0, 1);
-        agg_mbar_init(bar1, 1);
+    if (tid == kFrameWarps * 32) {                          // lane 0 of the producer warp
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) { agg_mbar_init(agg_smem_u32(&bar_full[s]), 1); agg_mbar_init(agg_smem_u32(&bar_empty[s]), kFrameWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (streamed) {
-            issue_chunk(0);
-            if (n_chunks > 1) issue_chunk(1);
-        }
+        if (streamed)
+            for (int c = 0; c < kSlots && c < n_chunks; ++c) issue_chunk(c);
     }
     // z row of frame-local node l
     auto zrow = [&](int l) -> const float* {
         if (p.layer0) return p.z + (size_t)(l < Hb ? h0 + l : p.n_heads_total) * ldz;
         return p.z + (size_t)(n0 + l) * ldz;
     };
-    const int n_a12 = p.layer0 ? Hb + 1 : Nb;               // rows of a1|a2 staged (layer 0: heads + the shared row)
-    auto a12row = [&](int l) -> const float* { return a12 + (size_t)((p.layer0 && l > Hb) ? Hb : l) * 2 * H; };
-
-    // ---- phase 1a: stage a1|a2, the head rows, the shared row (layer 0) and the in-edge lists ----
-    for (int i = tid; i < n_a12 * 2 * H; i += kFrameThreads) {
-        const int r = i / (2 * H), c = i - r * 2 * H;
-        a12[i] = __ldg(zrow(r) + HD + c);
-    }
+    // ---- phase 1a: stage the head rows, a1|a2 of the heads, a1 of the edge-nodes, the heads' in-edge lists ----
     {
         const int vec_per_row = hd4 / 4;                    // ldz % 4 == 0 and columns [HD, hd4) exist in the row (a1 follows)
-        const int rows = Hb + (p.layer0 ? 1 : 0);
-        for (int i = tid; i < rows * vec_per_row; i += kFrameThreads) {
+        for (int i = tid; i < Hb * vec_per_row; i += kFrameThreads) {
             const int r = i / vec_per_row, c = i - r * vec_per_row;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(zrow(r)) + c);
-            float* dstp = (r < Hb) ? zh + (size_t)r * hd4 : zE;
-            reinterpret_cast<float4*>(dstp)[c] = v;
+            reinterpret_cast<float4*>(zh + (size_t)r * hd4)[c] = __ldg(reinterpret_cast<const float4*>(zrow(r)) + c);
         }
+        if (p.layer0)
+            for (int i = tid; i < ldz / 4; i += kFrameThreads)
+                reinterpret_cast<float4*>(zE)[i] = __ldg(reinterpret_cast<const float4*>(zrow(Hb)) + i);
     }
-    for (int i = tid; i < Eb; i += kFrameThreads) lst[i] = __ldg(p.col + e0 + i) - n0;
+    for (int i = tid; i < Hb * 2 * H; i += kFrameThreads) {
+        const int r = i / (2 * H), c = i - r * 2 * H;
+        ah[i] = __ldg(zrow(r) + HD + c);
+    }
+    if (!p.layer0)
+        for (int i = tid; i < Mb * H; i += kFrameThreads) {
+            const int r = i / H, c = i - r * H;
+            a1e[i] = __ldg(zen + (size_t)r * ldz + HD + c);
+        }
+    for (int i = tid; i < Eh; i += kFrameThreads) lsth[i] = __ldg(p.col + e0 + i) - n0;
+    for (int k = tid; k < Mb; k += kFrameThreads) {
+        const int q = e0 + Eh + 3 * k;                      // CSR: 3 in-edges per edge-node after the head rows: h1, h2, self
+        prs[2 * k] = __ldg(p.col + q) - n0;
+        prs[2 * k + 1] = __ldg(p.col + q + 1) - n0;
+    }
     __syncthreads();
-    // ---- phase 1b: softmax weights of every in-edge, per attention head (gat2.py:78-88) ----
-    const int enode_pos0 = Hb + 2 * Mb;                     // CSR: head rows first, then 3 in-edges per edge-node
-    for (int q = tid; q < Nb * H; q += kFrameThreads) {
+    // ---- phase 1b: softmax weights of the heads' in-edges, per attention head (gat2.py:78-88) ----
+    for (int q = tid; q < Hb * H; q += kFrameThreads) {
         const int v = q / H, hh = q - v * H;
-        int beg, deg;
-        if (v >= Hb) { beg = enode_pos0 + 3 * (v - Hb); deg = 3; }
-        else { beg = __ldg(p.row_ptr + n0 + v) - e0; deg = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg; }
-        const float a2v = a12row(v)[H + hh];
-        float* wv = w + (size_t)beg * H + hh;
+        const int beg = __ldg(p.row_ptr + n0 + v) - e0;
+        const int deg = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg;
+        const float a2v = ah[v * 2 * H + H + hh];
+        float* wv = wh + (size_t)beg * H + hh;
         float m = -INFINITY;
         for (int i = 0; i < deg; ++i) {
-            const float e = leaky(a12row(lst[beg + i])[hh] + a2v, p.alpha);
+            const int u = lsth[beg + i];
+            const float a1u = (u < Hb) ? ah[u * 2 * H + hh] : (p.layer0 ? zE[HD + hh] : a1e[(u - Hb) * H + hh]);
+            const float e = leaky(a1u + a2v, p.alpha);
             wv[i * H] = e;
             m = fmaxf(m, e);
         }
@@ -383,7 +399,18 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         for (int i = 0; i < deg; ++i) wv[i * H] = wv[i * H] / den;
     }
     __syncthreads();
-    // ---- phase 2: chunk loop ----
+    // ---- phase 2 ----
+    if (wid == kFrameWarps) {
+        // ===== producer warp: refill a slot as soon as all consumer warps have released it =====
+        if (lane == 0 && streamed) {
+            for (int c = kSlots; c < n_chunks; ++c) {
+                const int s = c % kSlots;
+                agg_mbar_wait(agg_smem_u32(&bar_empty[s]), (uint32_t)(c / kSlots - 1) & 1u);
+                issue_chunk(c);
+            }
+        }
+        return;
+    }
     const int n_vec = HD / VEC;
     using V = typename VecT<VEC>::type;
     const bool slope_le1 = p.act_slope >= 0.f && p.act_slope <= 1.f;
@@ -415,35 +442,47 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
             float a = 0.f;
             if (h < Hb && okj[j]) {
                 *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zh + (size_t)h * hd4 + cj[j]);
-                a = w[(size_t)hbeg[t] * H + hj[j]];
+                a = wh[(size_t)hbeg[t] * H + hj[j]];
             }
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
         }
     }
+    const int lh = lane < H ? lane : 0;                     // attention head whose edge-node softmax this lane computes
     for (int c = 0; c < n_chunks; ++c) {
         const int k0 = c * kChunkRows, k1 = min(Mb, k0 + kChunkRows);
+        const int slot = c % kSlots;
         const float* rows = zE;
         int rstride = 0;
         if (!p.layer0) {
-            agg_mbar_wait((c & 1) ? bar1 : bar0, (uint32_t)(c >> 1) & 1u);
-            rows = buf + (size_t)(c & 1) * kChunkRows * ldz;
+            agg_mbar_wait(agg_smem_u32(&bar_full[slot]), (uint32_t)(c / kSlots) & 1u);
+            rows = ring + (size_t)slot * kChunkRows * ldz;
             rstride = ldz;
         }
-        // (a) edge-node destinations of the chunk: in-edges (h1 -> e), (h2 -> e), (e -> e)
-        for (int k = k0 + wid; k < k1; k += kFrameWarps) {
-            const int q0 = enode_pos0 + 3 * k;
-            const int h1 = lst[q0], h2 = lst[q0 + 1];
-            const float* wk = w + (size_t)q0 * H;
+        // (a) the edge-node destination of this warp: in-edges (h1 -> e), (h2 -> e), (e -> e)
+        const int k = k0 + wid;
+        if (k < k1) {
+            const int h1 = prs[2 * k], h2 = prs[2 * k + 1];
             const float* re = rows + (size_t)(k - k0) * rstride;
+            // softmax of the three logits, attention head lh (lanes >= H repeat head 0; nobody reads them)
+            const float a2e = re[HD + H + lh];
+            const float e1 = leaky(ah[h1 * 2 * H + lh] + a2e, p.alpha);
+            const float e2 = leaky(ah[h2 * 2 * H + lh] + a2e, p.alpha);
+            const float e3 = leaky(re[HD + lh] + a2e, p.alpha);
+            const float m = fmaxf(fmaxf(e1, e2), e3);
+            const float x1 = expf(e1 - m), x2 = expf(e2 - m), x3 = expf(e3 - m);
+            const float den = (0.f + x1 + x2) + x3;
+            const float s1 = x1 / den, s2 = x2 / den, s3 = x3 / den;
 #pragma unroll
             for (int j = 0; j < KMAX; ++j) {
+                const float w1 = __shfl_sync(0xffffffffu, s1, hj[j]);
+                const float w2 = __shfl_sync(0xffffffffu, s2, hj[j]);
+                const float w3 = __shfl_sync(0xffffffffu, s3, hj[j]);
                 if (!okj[j]) continue;
                 float z1[VEC], z2[VEC], ze[VEC], o[VEC];
                 *reinterpret_cast<V*>(z1) = *reinterpret_cast<const V*>(zh + (size_t)h1 * hd4 + cj[j]);
                 *reinterpret_cast<V*>(z2) = *reinterpret_cast<const V*>(zh + (size_t)h2 * hd4 + cj[j]);
                 *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + cj[j]);
-                const float w1 = wk[hj[j]], w2 = wk[H + hj[j]], w3 = wk[2 * H + hj[j]];
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) o[q] = fmaf(w3, ze[q], fmaf(w2, z2[q], fmaf(w1, z1[q], 0.f)));
                 store_out<VEC>(p, slope_le1, n0 + Hb + k, cj[j], o);
@@ -454,10 +493,10 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         for (int t = 0; t < kFrameOwn; ++t) {
             while (hcur[t] < hdeg[t]) {
                 const int pos = hbeg[t] + hcur[t];
-                const int k = lst[pos] - Hb;
-                if (k >= k1) break;
-                const float* re = rows + (size_t)(k - k0) * rstride;
-                const float* wp = w + (size_t)pos * H;
+                const int kk = lsth[pos] - Hb;
+                if (kk >= k1) break;
+                const float* re = rows + (size_t)(kk - k0) * rstride;
+                const float* wp = wh + (size_t)pos * H;
 #pragma unroll
                 for (int j = 0; j < KMAX; ++j) {
                     if (!okj[j]) continue;
@@ -470,9 +509,9 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
                 ++hcur[t];
             }
         }
-        if (streamed) {
-            __syncthreads();                                // every warp is done with ring slot c & 1
-            if (tid == 0 && c + 2 < n_chunks) issue_chunk(c + 2);
+        if (streamed) {                                     // this warp is done with the slot
+            __syncwarp();
+            if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_empty[slot]));
         }
     }
 #pragma unroll
@@ -485,15 +524,16 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
     }
     if (p.act_hi && p.ld_planes > HD) {                     // K padding of the planes stays zero
         const int padc = p.ld_planes - HD;
+        const int nthr = kFrameWarps * 32;
         if ((HD & 7) == 0) {                                // 16-byte stores (ld_planes is a multiple of 64)
             const int pv = padc / 8;
-            for (int i = tid; i < Nb * pv; i += kFrameThreads) {
+            for (int i = tid; i < Nb * pv; i += nthr) {
                 const int r = i / pv, cc = HD + 8 * (i - r * pv);
                 *reinterpret_cast<uint4*>(p.act_hi + (size_t)(n0 + r) * p.ld_planes + cc) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(p.act_lo + (size_t)(n0 + r) * p.ld_planes + cc) = make_uint4(0, 0, 0, 0);
             }
         } else {
-            for (int i = tid; i < Nb * padc; i += kFrameThreads) {
+            for (int i = tid; i < Nb * padc; i += nthr) {
                 const int r = i / padc, cc = HD + (i - r * padc);
                 p.act_hi[(size_t)(n0 + r) * p.ld_planes + cc] = __float2bfloat16_rn(0.f);
                 p.act_lo[(size_t)(n0 + r) * p.ld_planes + cc] = __float2bfloat16_rn(0.f);
