@@ -304,6 +304,7 @@ struct GemmParams2 {
     int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
     const float* bias; float slope, out_scale;
     int has_f32, has_planes;
+    int dbg;                                 // kernel bring-up switches (b200pose_set_debug): 1 = no stores, 2 = hi*hi only, 4 = no epilogue math
 };
 
 struct TileInfo { int m0, n0, bn; };
@@ -402,6 +403,7 @@ template <int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
     const __grid_constant__ CUtensorMap map_o_f32, const __grid_constant__ CUtensorMap map_o_hi,
     const __grid_constant__ CUtensorMap map_o_lo, const GemmParams2 p)
 {
@@ -423,13 +425,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     const uint32_t staging_base = tiles_base + (uint32_t)p.stages * stage_bytes;   // 1024-aligned
     const uint32_t acc_cols = tmem_cols_for(p.stage_bn);
     const uint32_t ncols = 2 * acc_cols;
-    constexpr int kBoxW = (NCTA == 1) ? 64 : 32;                             // W rows per TMA box
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bar_acc_full[a]), 1); mbar_init(smem_u32(&bar_acc_empty[a]), 4 * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        prefetch_tmap(&map_w2_hi); prefetch_tmap(&map_w2_lo);
         if (p.has_f32) prefetch_tmap(&map_o_f32);
         if (p.has_planes) { prefetch_tmap(&map_o_hi); prefetch_tmap(&map_o_lo); }
     }
@@ -454,23 +456,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
                     const uint32_t full = smem_u32(&bar_full[s]);
                     const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
+                    // one box per operand plane: the W maps are encoded with exactly this CTA's share of a wide (map_w_*)
+                    // or a narrow (map_w2_*) tile as box height, so a k-block costs four TMA instructions
+                    const CUtensorMap* mwh = (t.bn == p.stage_bn) ? &map_w_hi : &map_w2_hi;
+                    const CUtensorMap* mwl = (t.bn == p.stage_bn) ? &map_w_lo : &map_w2_lo;
                     if constexpr (NCTA == 1) {
                         mbar_expect_tx(full, tx);
                         tma_load_2d(base, &map_a_hi, kb * kBK, m_cta, full);
                         tma_load_2d(base + a_bytes, &map_a_lo, kb * kBK, m_cta, full);
-                        for (int j = 0; j < b_rows / kBoxW; ++j) {
-                            tma_load_2d(base + 2 * a_bytes + j * (kBoxW * 128), &map_w_hi, kb * kBK, n_cta + kBoxW * j, full);
-                            tma_load_2d(base + 2 * a_bytes + b_bytes + j * (kBoxW * 128), &map_w_lo, kb * kBK, n_cta + kBoxW * j, full);
-                        }
+                        tma_load_2d(base + 2 * a_bytes, mwh, kb * kBK, n_cta, full);
+                        tma_load_2d(base + 2 * a_bytes + b_bytes, mwl, kb * kBK, n_cta, full);
                     } else {
                         if (leader) mbar_expect_tx(full, tx);                 // the leader's barrier counts both CTAs' bytes
                         const uint32_t full0 = mapa_shared(full, 0);
                         tma_load_2d_pair(base, &map_a_hi, kb * kBK, m_cta, full0);
                         tma_load_2d_pair(base + a_bytes, &map_a_lo, kb * kBK, m_cta, full0);
-                        for (int j = 0; j < b_rows / kBoxW; ++j) {
-                            tma_load_2d_pair(base + 2 * a_bytes + j * (kBoxW * 128), &map_w_hi, kb * kBK, n_cta + kBoxW * j, full0);
-                            tma_load_2d_pair(base + 2 * a_bytes + b_bytes + j * (kBoxW * 128), &map_w_lo, kb * kBK, n_cta + kBoxW * j, full0);
-                        }
+                        tma_load_2d_pair(base + 2 * a_bytes, mwh, kb * kBK, n_cta, full0);
+                        tma_load_2d_pair(base + 2 * a_bytes + b_bytes, mwl, kb * kBK, n_cta, full0);
                     }
                 }
             }
@@ -505,8 +507,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                             umma_bf16(tmem_d, dah, dbl, idesc, 1u);
                         } else {
                             umma_bf16_pair(tmem_d, dah, dbh, idesc, first);
-                            umma_bf16_pair(tmem_d, dal, dbh, idesc, 1u);
-                            umma_bf16_pair(tmem_d, dah, dbl, idesc, 1u);
+                            if (!(p.dbg & 2)) {
+                                umma_bf16_pair(tmem_d, dal, dbh, idesc, 1u);
+                                umma_bf16_pair(tmem_d, dah, dbl, idesc, 1u);
+                            }
                         }
                     }
                     if constexpr (NCTA == 1) umma_commit(smem_u32(&bar_empty[s]));
@@ -547,6 +551,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                         else mbar_arrive_cluster(mapa_shared(smem_u32(&bar_acc_empty[a]), 0));
                     }
                 }
+                if (p.dbg & 4) continue;
                 // bias of the panel: lane l holds columns col0+l and col0+32+l
                 float b0 = 0.f, b1 = 0.f;
                 if (p.bias) {
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                 __syncwarp();
                 if (lane == 0) {
                     const int row0 = t.m0 + (int)rank * kBM + q * 32;
-                    if (row0 < p.M) {
+                    if (row0 < p.M && !(p.dbg & 1)) {
                         if (p.has_f32) {
                             if (col0 < p.N) tma_store_2d(&map_o_f32, stage_f32, col0, row0);
                             if (col0 + 32 < p.N) tma_store_2d(&map_o_f32, stage_f32 + 4096u, col0 + 32, row0);
@@ -618,6 +623,227 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     tcgen05_fence_before();
     if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();       // the peer still arrives on the leader's barriers until here
     if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide variant of the CTA-pair kernel for tall projections whose whole output width fits TMEM
+// (256 < N <= 512, i.e. 5..8 panels: the 400/420/320/336-wide GAT projections).
+//
+// The pair kernel above cuts such an N into two n-tiles and therefore streams the A tile through shared
+// memory twice per m-tile; measured with everything but the loads switched off (scripts/gemm_probe.py) the
+// L2->SM traffic alone costs 106 us of the 188 us of a 184320 x 400 x 400 projection. Here one tile spans the
+// full width: per k-block each CTA loads its 128 rows of A once and its share of BOTH halves of W, and the
+// leader issues two MMA groups per k-step - N=256 into TMEM columns [0,256) and N=bn-256 into [256,bn). The
+// accumulator is single-buffered (2 x 448 columns do not fit the 512 of TMEM), so the epilogue hands the two
+// column halves back separately: the MMAs of the next tile's lower half start while panels 4.. are still
+// being drained.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_wide_kernel(
+    const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,      // box: 128 W rows
+    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,    // box: (bn-256)/2 W rows
+    const __grid_constant__ CUtensorMap map_o_f32, const __grid_constant__ CUtensorMap map_o_hi,
+    const __grid_constant__ CUtensorMap map_o_lo, const GemmParams2 p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+    __shared__ __align__(8) uint64_t bar_acc_full;
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];          // [0]: columns < 256 drained, [1]: columns >= 256 drained
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int bn = p.stage_bn;                                   // full padded width, 320..512
+    const int bn_hi = bn - 256;                                  // width of the upper MMA group
+    const uint32_t a_bytes = kBM * kBK * 2;
+    const uint32_t blo_bytes = 128u * kBK * 2;                   // this CTA's 128 W rows of the lower group, per plane
+    const uint32_t bhi_bytes = (uint32_t)(bn_hi / 2) * kBK * 2;  // and its share of the upper group
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * blo_bytes + 2 * bhi_bytes;
+    const uint32_t tiles_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t staging_base = tiles_base + (uint32_t)p.stages * stage_bytes;
+    const int workers = gridDim.x / 2, worker = blockIdx.x / 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc_full), 1);
+        mbar_init(smem_u32(&bar_acc_empty[0]), 8);
+        mbar_init(smem_u32(&bar_acc_empty[1]), 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        prefetch_tmap(&map_w2_hi); prefetch_tmap(&map_w2_lo);
+        if (p.has_f32) prefetch_tmap(&map_o_f32);
+        if (p.has_planes) { prefetch_tmap(&map_o_hi); prefetch_tmap(&map_o_lo); }
+    }
+    if (warp == 1) tmem_alloc_n<2>(smem_u32(&tmem_slot), 512);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int it = 0;
+            const uint32_t tx = 2 * stage_bytes;                 // both CTAs' bytes land on the leader's barrier
+            for (int mb = worker; mb < p.tiles_m; mb += workers) {
+                const int m_cta = mb * 2 * kBM + (int)rank * kBM;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
+                    if (leader) mbar_expect_tx(full, tx);
+                    const uint32_t full0 = mapa_shared(full, 0);
+                    tma_load_2d_pair(base, &map_a_hi, kb * kBK, m_cta, full0);
+                    tma_load_2d_pair(base + a_bytes, &map_a_lo, kb * kBK, m_cta, full0);
+                    const uint32_t b0 = base + 2 * a_bytes;
+                    tma_load_2d_pair(b0, &map_w_hi, kb * kBK, (int)rank * 128, full0);
+                    tma_load_2d_pair(b0 + blo_bytes, &map_w_lo, kb * kBK, (int)rank * 128, full0);
+                    tma_load_2d_pair(b0 + 2 * blo_bytes, &map_w2_hi, kb * kBK, 256 + (int)rank * (bn_hi / 2), full0);
+                    tma_load_2d_pair(b0 + 2 * blo_bytes + bhi_bytes, &map_w2_lo, kb * kBK, 256 + (int)rank * (bn_hi / 2), full0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA) =================
+        if (lane == 0 && leader) {
+            const uint32_t idesc_lo = make_idesc_n<2>(256), idesc_hi = make_idesc_n<2>(bn_hi);
+            int it = 0, i = 0;
+            for (int mb = worker; mb < p.tiles_m; mb += workers, ++i) {
+                const uint32_t pe = ((uint32_t)i & 1u) ^ 1u;     // phase i-1 of the drained barriers (fresh barrier: passes)
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(smem_u32(&bar_full[s]), ph);
+                    tcgen05_fence_after();
+                    const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
+                    const uint32_t sa_hi = base, sa_lo = base + a_bytes, b0 = base + 2 * a_bytes;
+                    if (kb == 0) { mbar_wait(smem_u32(&bar_acc_empty[0]), pe); tcgen05_fence_after(); }
+#pragma unroll
+                    for (int k4 = 0; k4 < kBK / kUmmaK; ++k4) {
+                        const uint32_t off = k4 * kUmmaK * 2;
+                        const uint64_t dah = make_sw128_desc(sa_hi + off), dal = make_sw128_desc(sa_lo + off);
+                        const uint64_t dbh = make_sw128_desc(b0 + off), dbl = make_sw128_desc(b0 + blo_bytes + off);
+                        const uint32_t first = (kb == 0 && k4 == 0) ? 0u : 1u;
+                        umma_bf16_pair(tmem_base, dah, dbh, idesc_lo, first);
+                        umma_bf16_pair(tmem_base, dal, dbh, idesc_lo, 1u);
+                        umma_bf16_pair(tmem_base, dah, dbl, idesc_lo, 1u);
+                    }
+                    if (kb == 0) { mbar_wait(smem_u32(&bar_acc_empty[1]), pe); tcgen05_fence_after(); }
+#pragma unroll
+                    for (int k4 = 0; k4 < kBK / kUmmaK; ++k4) {
+                        const uint32_t off = k4 * kUmmaK * 2;
+                        const uint64_t dah = make_sw128_desc(sa_hi + off), dal = make_sw128_desc(sa_lo + off);
+                        const uint64_t dbh = make_sw128_desc(b0 + 2 * blo_bytes + off), dbl = make_sw128_desc(b0 + 2 * blo_bytes + bhi_bytes + off);
+                        const uint32_t first = (kb == 0 && k4 == 0) ? 0u : 1u;
+                        umma_bf16_pair(tmem_base + 256u, dah, dbh, idesc_hi, first);
+                        umma_bf16_pair(tmem_base + 256u, dal, dbh, idesc_hi, 1u);
+                        umma_bf16_pair(tmem_base + 256u, dah, dbl, idesc_hi, 1u);
+                    }
+                    umma_commit_pair(smem_u32(&bar_empty[s]));
+                }
+                umma_commit_pair(smem_u32(&bar_acc_full));
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;
+        const uint32_t stage_f32 = staging_base + (uint32_t)(warp - 2) * (uint32_t)((p.has_f32 ? 8192 : 0) + (p.has_planes ? 8192 : 0));
+        const uint32_t stage_hi = stage_f32 + (p.has_f32 ? 8192u : 0u);
+        const uint32_t stage_lo = stage_hi + 4096u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const uint32_t tmem_t = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int npanels = bn / 64;
+        bool stores_pending = false;
+        const bool slope_le1 = p.slope >= 0.f && p.slope <= 1.f;
+        int i = 0;
+        for (int mb = worker; mb < p.tiles_m; mb += workers, ++i) {
+            mbar_wait(smem_u32(&bar_acc_full), (uint32_t)i & 1u);
+            tcgen05_fence_after();
+            for (int j = 0; j < npanels; ++j) {
+                const int col0 = 64 * j;
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(tmem_t + (uint32_t)(64 * j), r0);
+                tmem_ld_32x32(tmem_t + (uint32_t)(64 * j + 32), r1);
+                if (j == 3 || j == npanels - 1) {                 // a column half is drained: hand it back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&bar_acc_empty[j == 3 ? 0 : 1]), 0));
+                }
+                float b0 = 0.f, b1 = 0.f;
+                if (p.bias) {
+                    if (col0 + lane < p.N) b0 = __ldg(p.bias + col0 + lane);
+                    if (col0 + 32 + lane < p.N) b1 = __ldg(p.bias + col0 + 32 + lane);
+                }
+                float v[64];
+                if (slope_le1) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
+                        v[c] = (col0 + c < p.N) ? leaky_le1(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
+                        v[32 + c] = (col0 + 32 + c < p.N) ? leaky_le1(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float bb0 = __shfl_sync(0xffffffffu, b0, c), bb1 = __shfl_sync(0xffffffffu, b1, c);
+                        v[c] = (col0 + c < p.N) ? leaky(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
+                        v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
+                    }
+                }
+                if (stores_pending) {
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
+                if (p.has_f32) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t addr = stage_f32 + (uint32_t)half * 4096u + row_off + (((uint32_t)c ^ sw) << 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[half * 32 + 4 * c]),
+                                         "f"(v[half * 32 + 4 * c + 1]), "f"(v[half * 32 + 4 * c + 2]), "f"(v[half * 32 + 4 * c + 3]) : "memory");
+                        }
+                }
+                if (p.has_planes) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) split_pack2(v[8 * c + 2 * u], v[8 * c + 2 * u + 1], h[u], l[u]);
+                        const uint32_t off = row_off + (((uint32_t)c ^ sw) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int row0 = mb * 2 * kBM + (int)rank * kBM + q * 32;
+                    if (row0 < p.M && !(p.dbg & 1)) {
+                        if (p.has_f32) {
+                            if (col0 < p.N) tma_store_2d(&map_o_f32, stage_f32, col0, row0);
+                            if (col0 + 32 < p.N) tma_store_2d(&map_o_f32, stage_f32 + 4096u, col0 + 32, row0);
+                        }
+                        if (p.has_planes) {
+                            tma_store_2d(&map_o_hi, stage_hi, col0, row0);
+                            tma_store_2d(&map_o_lo, stage_lo, col0, row0);
+                        }
+                    }
+                    bulk_commit();
+                }
+                stores_pending = true;
+            }
+        }
+        if (lane == 0) bulk_wait0();
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_n<2>(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -794,6 +1020,9 @@ static int choose_bn(int n) {
 
 using namespace b200pose;
 
+static int g_gemm_debug = 0;
+extern "C" __attribute__((visibility("default"))) int b200pose_set_debug(int flags) { const int old = g_gemm_debug; g_gemm_debug = flags; return old; }
+
 extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                                const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
                                const float* bias, int32_t m, int32_t n, int32_t k, float slope, float out_scale,
@@ -854,41 +1083,79 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
-    B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5, "linear: impl must be 0 (tcgen05 persistent, auto), 1 (simt self-test), "
-                 "2 (manual-fill self-test), 3 (v1), 4 (persistent, single CTA) or 5 (persistent, CTA pairs)");
+    B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5 || impl == 6, "linear: impl must be 0 (tcgen05 persistent, auto), 1 (simt self-test), "
+                 "2 (manual-fill self-test), 3 (v1), 4 (persistent, single CTA), 5 (persistent, CTA pairs) or 6 (wide CTA pairs)");
     // ---- persistent kernel ----
     if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
     if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");
     // CTA pairs (cta_group::2, 256-row tiles) as soon as there is more than one pair tile of rows: per flop a pair pulls
     // 1.5x fewer bytes through the L2->SM fabric, which bounds both the tall GAT projections and the MLP (every m-tile
     // re-reads the whole weight matrix from L2)
-    const int ncta = (impl == 5) ? 2 : (impl == 4) ? 1 : (m > 2 * kBM ? 2 : 1);
+    const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 2 * kBM ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
-    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0;
+    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_gemm_debug;
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
-    q.tiles_n = ceil_div(q.panels_total, 4);
-    q.tiles_m = ceil_div(m, kBM * ncta);
-    q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
-    const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)(q.stage_bn / ncta) * kBK * 2;
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
-    int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 1) { set_error("linear: tile does not fit in shared memory"); return B200POSE_E_UNSUPPORTED; }
-    q.stages = stages;
-    const size_t smem = (size_t)stages * stage2 + staging + 1024;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo;
     int rc;
     if ((rc = make_map(&ma_hi, a_hi, m, kpad, lda, kBM))) return rc;
     if ((rc = make_map(&ma_lo, a_lo, m, kpad, lda, kBM))) return rc;
-    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, ncta == 1 ? 64 : 32))) return rc;
-    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, ncta == 1 ? 64 : 32))) return rc;
     mo_f32 = ma_hi; mo_hi = ma_hi; mo_lo = ma_hi;                              // placeholders when unused
     if (out_f32 && (rc = make_map_ex(&mo_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out_f32, m, n, ld_out, 32, 32))) return rc;
     if (out_hi) {
         if ((rc = make_map_ex(&mo_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_hi, m, ld_planes, ld_planes, 64, 32))) return rc;
         if ((rc = make_map_ex(&mo_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_lo, m, ld_planes, ld_planes, 64, 32))) return rc;
     }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    // ---- wide pair kernel: tall projections whose whole width fits TMEM (5..8 panels): A streamed once per m-tile ----
+    // Measured on B200 (GAT projections, 184320 rows): 1.43 ms per step against 1.20 ms for the two-n-tile pair kernel -
+    // the 88 KB stages leave room for only two of them and the single-buffered accumulator exposes the epilogue, which
+    // costs more than streaming A twice. Kept selectable (impl 6) for A/B runs; not on the product path.
+    const bool wide = impl == 6 && q.panels_total > 4 && q.panels_total <= 8;
+    if (wide) {
+        q.tiles_m = ceil_div(m, 2 * kBM);
+        q.tiles_n = 1;
+        q.group_n = 1;
+        q.stage_bn = 64 * q.panels_total;
+        const int bn_hi = q.stage_bn - 256;
+        const size_t stage_w = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)128 * kBK * 2 + 2 * (size_t)(bn_hi / 2) * kBK * 2;
+        int stages = (int)((227 * 1024 - 2048 - staging) / stage_w);
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages >= 2) {
+            q.stages = stages;
+            const size_t smem = (size_t)stages * stage_w + staging + 1024;
+            if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, 128))) return rc;
+            if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, 128))) return rc;
+            if ((rc = make_map(&mw2_hi, w_hi, n, kpad, ldw, bn_hi / 2))) return rc;
+            if ((rc = make_map(&mw2_lo, w_lo, n, kpad, ldw, bn_hi / 2))) return rc;
+            const int workers = q.tiles_m < num_sms() / 2 ? q.tiles_m : num_sms() / 2;
+            B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * workers); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_wide_kernel, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo, q));
+            return B200POSE_OK;
+        }
+    }
+    q.tiles_n = ceil_div(q.panels_total, 4);
+    q.tiles_m = ceil_div(m, kBM * ncta);
+    q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
+    const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)(q.stage_bn / ncta) * kBK * 2;
+    int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 1) { set_error("linear: tile does not fit in shared memory"); return B200POSE_E_UNSUPPORTED; }
+    q.stages = stages;
+    const size_t smem = (size_t)stages * stage2 + staging + 1024;
+    // n-tiles are `base` or `base + 1` panels wide (tile_info): one W map per width, box height = one CTA's share
+    const int panels_narrow = q.panels_total / q.tiles_n;
+    const int bn_narrow = 64 * (panels_narrow < 1 ? 1 : panels_narrow);
+    if ((rc = make_map(&mw_hi, w_hi, n, kpad, ldw, q.stage_bn / ncta))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, n, kpad, ldw, q.stage_bn / ncta))) return rc;
+    if ((rc = make_map(&mw2_hi, w_hi, n, kpad, ldw, bn_narrow / ncta))) return rc;
+    if ((rc = make_map(&mw2_lo, w_lo, n, kpad, ldw, bn_narrow / ncta))) return rc;
     // tall GEMMs (GAT projections: thousands of m-tiles, 1-2 n-tiles): sweep the n-tiles of an m-tile inside one worker
     const int workers_max = num_sms() / ncta;
     q.group_n = (q.tiles_m >= 2 * workers_max) ? q.tiles_n : 1;
@@ -896,17 +1163,14 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     const int workers = total_visits < workers_max ? total_visits : workers_max;
     if (ncta == 1) {
         B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_split_tc2_kernel<1><<<workers, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q);
+        gemm_split_tc2_kernel<1><<<workers, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo, q);
         B2_CHECK_LAUNCH();
     } else {
         B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_split_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * workers); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_tc2_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, mo_f32, mo_hi, mo_lo, q));
+        B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_tc2_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo, q));
     }
     return B200POSE_OK;
 }

@@ -106,7 +106,8 @@ int b200pose_node_features(int32_t n_frames, int32_t n_heads_total, int32_t n_no
  * so the padding can be consumed as K padding by the next GEMM.
  * out_scale multiplies the result after the activation (x10 of metrics_from_model.py:282).
  * impl: 0 = persistent tcgen05 + TMA tensor-core kernel (the product path; CTA pairs with cta_group::2 MMAs and
- * 256-row tiles when m is large, single CTAs otherwise); 4 / 5 force single CTAs / CTA pairs (A/B runs);
+ * 256-row tiles, single CTAs for tiny m; full-width single-tile pairs for tall projections with 256 < n <= 512);
+ * 4 / 5 / 6 force single CTAs / CTA pairs / wide CTA pairs (A/B runs);
  * 1 = fp32 SIMT kernel, 2 = tcgen05 kernel with tiles filled by ordinary stores, 3 = first one-tile-per-CTA
  * kernel - these three exist only for the kernel self-test.
  * ------------------------------------------------------------------------------------------- */
@@ -116,6 +117,10 @@ int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                     float* out_f32, int32_t ld_out,
                     uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
                     int32_t impl, void* stream);
+
+/* Kernel bring-up switches for the persistent GEMM (results become WRONG; used by scripts/gemm_probe.py to attribute time):
+ * bit 0 = skip the output stores, bit 1 = issue only the hi*hi MMA, bit 2 = skip the epilogue arithmetic. Returns the old value. */
+int b200pose_set_debug(int flags);
 
 /* fp32 [rows, ld_in] -> planes [rows, ld_planes] (used once per weight matrix at load time, and by tests) */
 int b200pose_split_planes(const float* x, int32_t rows, int32_t cols, int32_t ld_in,

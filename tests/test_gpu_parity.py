@@ -81,10 +81,10 @@ def test_graph_and_features_bit_exact(config):
     assert row_ptr[pb.n_nodes] == pb.n_edges
 
 
-@pytest.mark.parametrize('impl', [1, 2, 3, 4, 5, 0])
+@pytest.mark.parametrize('impl', [1, 2, 3, 4, 5, 6, 0])
 def test_linear_kernels(impl):
     """out = act(A W^T + b): SIMT self-test kernel (1), tcgen05 with manual tile fill (2), the v1 one-tile-per-CTA
-    TMA kernel (3), the persistent kernel with single CTAs (4) / CTA pairs + cta_group::2 MMAs (5) and the product
+    TMA kernel (3), the persistent kernel with single CTAs (4) / CTA pairs + cta_group::2 MMAs (5) / wide CTA pairs (6) and the product
     dispatch (0) against a float64 reference of the same split operands."""
     pipe = get_pipe('panoptic')
     L = pipe.L
