@@ -963,6 +963,81 @@ __global__ void __launch_bounds__(256) gemm_split_simt_kernel(const GemmParams p
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small-M kernel (m <= 8 rows: the pose MLP of a single frame). With a handful of rows the projection is a
+// weight-streaming problem - the MLP holds 116 MB of hi/lo weights - and the tensor-core kernel would read them
+// through the 12-48 CTAs its tiling yields. Here every warp owns output columns: it streams the hi/lo weight
+// rows of a column with 16-byte loads (each weight read exactly once, all SMs pulling), keeps the A rows as fp32
+// in shared memory, and reduces across lanes. Evaluates (a_hi + a_lo) . (w_hi + w_lo) in fp32, i.e. the same
+// product as the 3-term tensor-core path plus the (negligible) lo*lo term.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallM = 8;
+constexpr int kSmallWarps = 8;
+
+__global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
+    const __nv_bfloat16* __restrict__ a_hi, const __nv_bfloat16* __restrict__ a_lo, int lda,
+    const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo, int ldw,
+    const float* __restrict__ bias, int M, int N, int kpad, float slope, float out_scale,
+    float* __restrict__ out_f32, int ld_out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ld_planes)
+{
+    extern __shared__ __align__(16) float As[];              // [M][kpad]
+    for (int i = threadIdx.x; i < M * kpad; i += blockDim.x) {
+        const int m = i / kpad, k = i - m * kpad;
+        As[i] = __bfloat162float(a_hi[(size_t)m * lda + k]) + __bfloat162float(a_lo[(size_t)m * lda + k]);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_cols = out_hi ? ld_planes : N;               // plane padding columns are written as zeros
+    for (int n = blockIdx.x * kSmallWarps + warp; n < n_cols; n += gridDim.x * kSmallWarps) {
+        float acc[kSmallM];
+#pragma unroll
+        for (int m = 0; m < kSmallM; ++m) acc[m] = 0.f;
+        if (n < N) {
+            const uint4* wh = reinterpret_cast<const uint4*>(w_hi + (size_t)n * ldw);
+            const uint4* wl = reinterpret_cast<const uint4*>(w_lo + (size_t)n * ldw);
+#pragma unroll 4
+            for (int k0 = lane * 8; k0 < kpad; k0 += 256) {
+                const uint4 h = __ldg(wh + (k0 >> 3)), l = __ldg(wl + (k0 >> 3));
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                float wv[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    wv[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                    wv[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int m = 0; m < kSmallM; ++m) {
+                    if (m < M) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(As + (size_t)m * kpad + k0);
+                        const float4 x1 = *reinterpret_cast<const float4*>(As + (size_t)m * kpad + k0 + 4);
+                        acc[m] = fmaf(x0.x, wv[0], acc[m]); acc[m] = fmaf(x0.y, wv[1], acc[m]);
+                        acc[m] = fmaf(x0.z, wv[2], acc[m]); acc[m] = fmaf(x0.w, wv[3], acc[m]);
+                        acc[m] = fmaf(x1.x, wv[4], acc[m]); acc[m] = fmaf(x1.y, wv[5], acc[m]);
+                        acc[m] = fmaf(x1.z, wv[6], acc[m]); acc[m] = fmaf(x1.w, wv[7], acc[m]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kSmallM; ++m)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+        if (lane < M) {
+            float v = 0.f;
+#pragma unroll
+            for (int m = 0; m < kSmallM; ++m) if (m == lane) v = acc[m];
+            if (n < N) v = leaky(v + (bias ? __ldg(bias + n) : 0.f), slope) * out_scale; else v = 0.f;
+            if (out_f32 && n < N) out_f32[(size_t)lane * ld_out + n] = v;
+            if (out_hi) {
+                __nv_bfloat16 hh, ll;
+                split_bf16(v, hh, ll);
+                out_hi[(size_t)lane * ld_planes + n] = hh;
+                out_lo[(size_t)lane * ld_planes + n] = ll;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -1083,8 +1158,20 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
-    B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5 || impl == 6, "linear: impl must be 0 (tcgen05 persistent, auto), 1 (simt self-test), "
-                 "2 (manual-fill self-test), 3 (v1), 4 (persistent, single CTA), 5 (persistent, CTA pairs) or 6 (wide CTA pairs)");
+    if ((impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 160 * 1024) {   // weight-streaming small-M kernel
+        const size_t smem = (size_t)m * kpad * sizeof(float);
+        const int cols = out_hi ? ld_planes : n;
+        int ctas = ceil_div(cols, kSmallWarps);
+        const int cap = num_sms() * 4;
+        if (ctas > cap) ctas = cap;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_small_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_small_m_kernel<<<ctas, kSmallWarps * 32, smem, st>>>(p.a_hi, p.a_lo, lda, p.w_hi, p.w_lo, ldw, bias, m, n, kpad, slope, out_scale,
+                                                                  out_f32, ld_out, p.out_hi, p.out_lo, ld_planes);
+        B2_CHECK_LAUNCH();
+        return B200POSE_OK;
+    }
+    B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5 || impl == 6 || impl == 7, "linear: impl must be 0 (auto), 1 (simt self-test), 2 (manual-fill "
+                 "self-test), 3 (v1), 4 (persistent, single CTA), 5 (CTA pairs), 6 (wide CTA pairs) or 7 (small-m kernel when m <= 8)");
     // ---- persistent kernel ----
     if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
     if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");

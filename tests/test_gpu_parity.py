@@ -81,7 +81,7 @@ def test_graph_and_features_bit_exact(config):
     assert row_ptr[pb.n_nodes] == pb.n_edges
 
 
-@pytest.mark.parametrize('impl', [1, 2, 3, 4, 5, 6, 0])
+@pytest.mark.parametrize('impl', [1, 2, 3, 4, 5, 6, 7, 0])
 def test_linear_kernels(impl):
     """out = act(A W^T + b): SIMT self-test kernel (1), tcgen05 with manual tile fill (2), the v1 one-tile-per-CTA
     TMA kernel (3), the persistent kernel with single CTAs (4) / CTA pairs + cta_group::2 MMAs (5) / wide CTA pairs (6) and the product
@@ -89,7 +89,7 @@ def test_linear_kernels(impl):
     pipe = get_pipe('panoptic')
     L = pipe.L
     torch.manual_seed(5)
-    shapes = [(128, 64, 64), (200, 48, 150), (77, 902, 902), (300, 420, 400), (1000, 3, 150), (260, 336, 400),
+    shapes = [(1, 54, 1024), (4, 3072, 1260), (8, 1024, 1024), (3, 20, 150), (128, 64, 64), (200, 48, 150), (77, 902, 902), (300, 420, 400), (1000, 3, 150), (260, 336, 400),
               (129, 160, 320), (500, 3072, 1260), (64, 54, 1024), (40000, 400, 400), (20481, 902, 902)]
     for (m, n, k) in shapes:
         A = torch.randn(m, k, device='cuda') * 0.7
