@@ -33,18 +33,19 @@ def pack_record(n_persons: torch.Tensor, person_sk: torch.Tensor, joints: torch.
     F, P = int(n_persons.numel()), int(person_sk.shape[0])
     if F > frames_cap or P > persons_cap:
         raise ValueError('result does not fit the record (%d/%d frames, %d/%d persons)' % (F, frames_cap, P, persons_cap))
-    rec = torch.zeros(record_words(frames_cap, persons_cap, n_cameras, n_out), dtype=torch.int32, device=dev)
+    # padding words are never read back (unpack_records slices by the counts), so the record is not cleared
+    rec = torch.empty(record_words(frames_cap, persons_cap, n_cameras, n_out), dtype=torch.int32, device=dev)
     rec[0] = P
-    rec[1:1 + F] = n_persons.to(torch.int32)
+    rec[1:1 + F] = n_persons
     o = 1 + frames_cap
-    sk = torch.full((persons_cap, n_cameras), -1, dtype=torch.int32, device=dev)
     if P:
-        psk = person_sk.to(torch.int32)
-        sk[:P] = torch.where(psk >= 0, psk + head_base, psk)
-    rec[o:o + persons_cap * n_cameras] = sk.reshape(-1)
+        sk = rec[o:o + P * n_cameras].view(P, n_cameras)
+        sk.copy_(person_sk)
+        if head_base:
+            sk.add_((sk >= 0).to(torch.int32) * int(head_base))
     o += persons_cap * n_cameras
     if P and n_out:
-        rec[o:o + P * n_out] = joints.to(torch.float32).contiguous().view(torch.int32).reshape(-1)
+        rec[o:o + P * n_out].view(torch.float32).view(P, n_out).copy_(joints)
     return rec
 
 
