@@ -86,10 +86,16 @@ struct ClusterParams {
     int max_heads, max_keys, table_cap;
 };
 
-__global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
+// blockDim = 32 (frames of a few hundred edge-nodes: everything is warp-synchronous) or 256 (large frames: the sort
+// and the table passes use the whole CTA; the order-dependent parts still run on one lane).
+__global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    __shared__ int n_seen_s;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool one_warp = nt == 32;
+    auto bsync = [&]() { if (one_warp) __syncwarp(); else __syncthreads(); };
     const int b = blockIdx.x;
     const int h0 = p.head_off[b];
     const int H = p.head_off[b + 1] - h0;
@@ -108,57 +114,59 @@ __global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
     unsigned* cams_for = reinterpret_cast<unsigned*>(ip); ip += p.max_heads;
     int* flag = ip;             ip += p.max_heads;
     int* tab_a = ip;            ip += p.table_cap;
-    int* tab_b = ip;            ip += p.table_cap;
-    int* prs = ip;                                                  // (h1, h2) of every edge-node: read once, coalesced
+    int* tab_b = ip;
 
     if (H > p.max_heads || M > p.max_keys || H == 0) {              // outside the sized limits: no persons
-        if (lane == 0) p.n_persons[b] = 0;
+        if (tid == 0) p.n_persons[b] = 0;
         return;
     }
     int Mpad = 1;
     while (Mpad < M) Mpad <<= 1;
 
-    for (int h = lane; h < H; h += 32) {
+    for (int h = tid; h < H; h += nt) {
         cam[h] = p.node_cam[n0 + h];
         group[h] = -1;
         linked[h] = 1u << cam[h];
         flag[h] = 0;
     }
-    __syncwarp();
-
-    // ---- edge walk: first-seen order of the heads + matchings above the threshold (:32-55) ----
-    int n_seen = 0;
-    for (int k0 = 0; k0 < M; k0 += 32) {
-        const int k = k0 + lane;
-        int h1 = -1, h2 = -1;
+    // ---- matchings above the threshold (:49-55): sort key = (score, edge-node index descending) ----
+    for (int k = tid; k < Mpad; k += nt) {
         unsigned long long key = 0ull;
         if (k < M) {
-            h1 = p.pairs[2 * (m0 + k)];
-            h2 = p.pairs[2 * (m0 + k) + 1];
-            prs[2 * k] = h1; prs[2 * k + 1] = h2;
             const float s = p.scores[n0 + H + k];
             if ((double)s > p.threshold)
                 key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
         }
-        if (k < Mpad) keys[k] = key;
-        const int cnt = min(32, M - k0);
-        for (int t = 0; t < cnt; ++t) {
-            const int a = __shfl_sync(0xffffffffu, h1, t);
-            const int c = __shfl_sync(0xffffffffu, h2, t);
-            if (lane == 0) {
-                if (!flag[a]) { flag[a] = 1; first_seen[n_seen++] = a; }
-                if (!flag[c]) { flag[c] = 1; first_seen[n_seen++] = c; }
-            }
-        }
+        keys[k] = key;
     }
-    for (int k = M + lane; k < Mpad; k += 32) keys[k] = 0ull;
-    n_seen = __shfl_sync(0xffffffffu, n_seen, 0);
-    __syncwarp();
+    bsync();
+    // ---- edge walk: first-seen order of the heads (:32-47), one warp, order-dependent ----
+    if (warp == 0) {
+        int n_seen = 0;
+        for (int k0 = 0; k0 < M; k0 += 32) {
+            const int k = k0 + lane;
+            int h1 = -1, h2 = -1;
+            if (k < M) { h1 = p.pairs[2 * (m0 + k)]; h2 = p.pairs[2 * (m0 + k) + 1]; }
+            const int cnt = min(32, M - k0);
+            for (int t = 0; t < cnt; ++t) {
+                const int a = __shfl_sync(0xffffffffu, h1, t);
+                const int c = __shfl_sync(0xffffffffu, h2, t);
+                if (lane == 0) {
+                    if (!flag[a]) { flag[a] = 1; first_seen[n_seen++] = a; }
+                    if (!flag[c]) { flag[c] = 1; first_seen[n_seen++] = c; }
+                }
+            }
+            if (__shfl_sync(0xffffffffu, n_seen, 0) == H) break;       // every head has been seen
+        }
+        if (lane == 0) n_seen_s = n_seen;
+    }
+    bsync();
+    const int n_seen = n_seen_s;
 
     // ---- bitonic sort, descending: score desc, edge-node index asc (:60) ----
     for (int size = 2; size <= Mpad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = lane; i < Mpad; i += 32) {
+            for (int i = tid; i < Mpad; i += nt) {
                 const int j = i ^ stride;
                 if (j > i) {
                     const unsigned long long x = keys[i], y = keys[j];
@@ -166,51 +174,61 @@ __global__ void __launch_bounds__(32) cluster_kernel(ClusterParams p)
                     if (desc ? (x < y) : (x > y)) { keys[i] = y; keys[j] = x; }
                 }
             }
-            __syncwarp();
+            bsync();
         }
     }
-
-    // ---- greedy merge (:61-108); every lane runs the same scalar control flow ----
-    int n_links = 0, cur = 0;
-    for (int t = 0; t < M; ++t) {
+    // ---- replace every sorted key by its (h1, h2) pair: one parallel pass of coalesced-ish global reads, so the
+    // sequential merge below touches shared memory only ----
+    for (int t = tid; t < Mpad; t += nt) {
         const unsigned long long key = keys[t];
-        if (key == 0ull) break;
-        __syncwarp();
-        const int k = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
-        const int h1 = prs[2 * k], h2 = prs[2 * k + 1];
-        int a, c;
-        pair_order(h1, h2, a, c);
-        const unsigned ca = 1u << cam[a], cc = 1u << cam[c];
-        if ((ca & linked[c]) || (cc & linked[a])) continue;                      // :67
-        const int ga = group[a], gc = group[c];
-        if (ga >= 0 && (cc & cams_for[ga])) continue;                            // :70-72
-        if (gc >= 0 && (ca & cams_for[gc])) continue;                            // :73-75
-        if (ga < 0 && gc < 0) {                                                  // :77-83
-            if (lane == 0) { group[a] = cur; group[c] = cur; cams_for[cur] = ca | cc; }
-            ++cur;
-        } else if (ga >= 0 && gc < 0) {                                          // :84-86
-            if (lane == 0) { group[c] = ga; cams_for[ga] |= cc; }
-        } else if (gc >= 0 && ga < 0) {                                          // :87-89
-            if (lane == 0) { group[a] = gc; cams_for[gc] |= ca; }
-        } else {                                                                 // :90-104
-            if (cams_for[gc] & cams_for[ga]) continue;
-            for (int h = lane; h < H; h += 32)
-                if (group[h] == gc) group[h] = ga;                               // absorbed cameras are forgotten
+        if (key != 0ull) {
+            const int k = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+            const unsigned long long h1 = (unsigned long long)p.pairs[2 * (m0 + k)], h2 = (unsigned long long)p.pairs[2 * (m0 + k) + 1];
+            keys[t] = (1ull << 63) | (h1 << 31) | h2;
         }
-        if (lane == 0) {                                                         // :106-108
-            link_a[2 * n_links] = a; link_a[2 * n_links + 1] = c;
-            linked[a] |= cc; linked[c] |= ca;
-        }
-        ++n_links;
-        __syncwarp();
     }
-    __syncwarp();
+    bsync();
+
+    // ---- greedy merge (:61-108): inherently sequential in score order, so one lane walks the sorted matchings
+    // (no synchronisation per matching); the state it touches is a few hundred bytes of shared memory ----
+    int n_links = 0;
+    if (tid == 0) {
+        int cur = 0;
+        for (int t = 0; t < M; ++t) {
+            const unsigned long long key = keys[t];
+            if (key == 0ull) break;
+            const int h1 = (int)((key >> 31) & 0x7FFFFFFFull), h2 = (int)(key & 0x7FFFFFFFull);
+            int a, c;
+            pair_order(h1, h2, a, c);
+            const unsigned ca = 1u << cam[a], cc = 1u << cam[c];
+            if ((ca & linked[c]) || (cc & linked[a])) continue;                      // :67
+            const int ga = group[a], gc = group[c];
+            if (ga >= 0 && (cc & cams_for[ga])) continue;                            // :70-72
+            if (gc >= 0 && (ca & cams_for[gc])) continue;                            // :73-75
+            if (ga < 0 && gc < 0) {                                                  // :77-83
+                group[a] = cur; group[c] = cur; cams_for[cur] = ca | cc;
+                ++cur;
+            } else if (ga >= 0 && gc < 0) {                                          // :84-86
+                group[c] = ga; cams_for[ga] |= cc;
+            } else if (gc >= 0 && ga < 0) {                                          // :87-89
+                group[a] = gc; cams_for[gc] |= ca;
+            } else {                                                                 // :90-104
+                if (cams_for[gc] & cams_for[ga]) continue;
+                for (int h = 0; h < H; ++h)
+                    if (group[h] == gc) group[h] = ga;                               // absorbed cameras are forgotten
+            }
+            link_a[2 * n_links] = a; link_a[2 * n_links + 1] = c;                    // :106-108
+            linked[a] |= cc; linked[c] |= ca;
+            ++n_links;
+        }
+    }
+    bsync();
 
     // ---- connected components in first-seen order, BFS by levels (:117-130) ----
-    for (int h = lane; h < H; h += 32) flag[h] = 0;                              // reuse as "done"
-    __syncwarp();
+    for (int h = tid; h < H; h += nt) flag[h] = 0;                               // reuse as "done"
+    bsync();
     int n_out = 0;
-    if (lane == 0) {
+    if (tid == 0) {
         IntSet comp;
         for (int f = 0; f < n_seen; ++f) {
             const int v = first_seen[f];
@@ -319,14 +337,14 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
     while (keys < max_enodes_per_frame) keys <<= 1;
     p.max_keys = keys;
     p.table_cap = set_table_capacity(p.max_heads);
-    const size_t smem = (size_t)p.max_keys * 8 + (size_t)p.max_heads * 7 * 4 + (size_t)p.table_cap * 2 * 4 + (size_t)p.max_keys * 2 * 4;
+    const size_t smem = (size_t)p.max_keys * 8 + (size_t)p.max_heads * 7 * 4 + (size_t)p.table_cap * 2 * 4;
     if (smem > 200 * 1024) {
         set_error("cluster: frame too large for the shared-memory plan (%zu bytes: %d heads, %d edge-nodes)", smem,
                   max_heads_per_frame, max_enodes_per_frame);
         return B200POSE_E_UNSUPPORTED;
     }
     B2_CHECK_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cluster_kernel<<<n_frames, 32, smem, (cudaStream_t)stream>>>(p);
+    cluster_kernel<<<n_frames, p.max_keys > 1024 ? 256 : 32, smem, (cudaStream_t)stream>>>(p);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

@@ -129,18 +129,36 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         for (int k = 0; k < KMAX; ++k)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[k][i] = 0.f;
-        for (int i = 0; i < deg; ++i) {
-            const float* ru = row_of(__ldg(p.col + beg + i));
-            const float* w = att + i * H;
+        // neighbours in batches of 4: the row loads of a batch are independent and issued together (a head of a
+        // 10-view frame has ~145 in-edges; one L2 round trip per neighbour would serialise them), the FMAs keep the
+        // ascending-edge order
+        for (int i0 = 0; i0 < deg; i0 += 4) {
+            const float* ru[4];
+            float f[4][KMAX][VEC];
 #pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                const int cv = lane + 32 * k;
-                if (cv < n_vec) {
-                    float f[VEC];
-                    load_vec<VEC>(ru + cv * VEC, f);
-                    const float a = w[head_of[k]];
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + u, deg - 1);
+                ru[u] = row_of(__ldg(p.col + beg + i));
+            }
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(a, f[q], acc[k][q]);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const int cv = lane + 32 * k;
+                    if (cv < n_vec) load_vec<VEC>(ru[u] + cv * VEC, f[u][k]);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u >= deg) break;
+                const float* w = att + (i0 + u) * H;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const int cv = lane + 32 * k;
+                    if (cv < n_vec) {
+                        const float a = w[head_of[k]];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(a, f[u][k][q], acc[k][q]);
+                    }
                 }
             }
         }
@@ -629,6 +647,10 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     int stage_rows = (int)((96 * 1024) / row_bytes);
     const int want = max_heads_per_frame > 0 ? max_heads_per_frame + (layer0 ? 1 : 0) : 0;
     if (stage_rows > want) stage_rows = want;
+    // Staging pays only while a frame's heads fit: every CTA of a frame (one per 48 destinations) re-loads the staged
+    // rows, so for a 10-view x 16-person frame (160 heads, 244 CTAs) 55 staged rows would cost 97 KB of L2 reads per CTA
+    // for 6 destinations per warp. Large frames gather everything through L2 instead.
+    if (want > stage_rows || stage_rows > 48) stage_rows = 0;
     p.stage_rows = stage_rows;
     const size_t smem = (size_t)stage_rows * row_bytes + (size_t)kAggWarps * p.max_deg * heads * sizeof(float);
     if (smem > 200 * 1024) {

@@ -405,3 +405,36 @@ def test_triangulation_full_size_properties():
         ref, rm = O.triangulate_baseline(person, tabs, cfg.median_axis)
         assert np.array_equal(rm, m[p])
         assert np.abs(ref - xyz[p]).max() < 1e-9
+
+
+def test_stress_frame_10_views_16_persons():
+    """BASELINE config 5 shape: one 10-view frame with 16 persons (160 heads, 11520 edge-nodes, 57760 edges) next to
+    small frames in the same batch - exercises the gather aggregation kernel and the large-frame clustering plan."""
+    config = 'ring10'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    gat_w, mlp_w = helpers.golden_weights(config)
+    gat_w, mlp_w = helpers.np_state(gat_w), helpers.np_state(mlp_w)
+    tabs = O.CameraTables(cfg)
+    frames = [helpers.synth.make_frame(cfg, 4242, 16), helpers.synth.make_frame(cfg, 4243, 2)]
+    frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+    pb = pack_mod.pack_frames(frames, cfg)
+    assert pb.max_heads >= 140 and pb.max_enodes >= 9000
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    res = pipe.infer(db, with_coo=True)
+    scores = res['scores'].cpu().numpy()
+    ph, npers = res['person_heads'].cpu().numpy(), res['n_persons'].cpu().numpy()
+    g = res['graph']
+    src, dst = g.src.cpu().numpy(), g.dst.cpu().numpy()
+    for b, f in enumerate(frames):
+        og = O.build_graph(f, tabs)
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        e0 = pb.head_off[b] + 5 * (n0 - pb.head_off[b])
+        assert np.array_equal(src[e0:e0 + len(og['src'])], og['src']) and np.array_equal(dst[e0:e0 + len(og['dst'])], og['dst'])
+        ref = O.gat_forward(gat_w, og['feats'], og['src'], og['dst'])
+        idx = og['indices']
+        rel = np.abs(scores[n0:n1][idx] - ref[idx]) / np.abs(ref[idx])
+        assert rel.max() <= SCORE_RTOL, (b, rel.max())
+        props = O.cluster(scores[n0:n1], og['pairs'], og['nodes_camera'][:og['n_heads']], cfg.V_sm, og['n_heads'])
+        assert np.array_equal(ph[pb.head_off[b]:pb.head_off[b] + npers[b]], props), b
+    assert np.isfinite(res['joints'].cpu().numpy()).all()
