@@ -459,6 +459,11 @@ class PosePipeline:
     def stage_a(self, db: DeviceBatch, with_coo: bool = False):
         """Stages 1-2 of a batch, enqueued without any host synchronisation: graph build, GAT, clustering and the
         exclusive scan of the person counts."""
+        if db.n_heads == 0:                                     # no detections at all (empty frames only): nothing to launch
+            i32 = dict(dtype=torch.int32, device=self.device)
+            return dict(graph=None, scores=torch.zeros(1, dtype=torch.float32, device=self.device),
+                        person_heads=torch.zeros((1, self.cfg.V_sm), **i32), n_persons=torch.zeros(db.n_frames, **i32),
+                        person_off=torch.zeros(db.n_frames + 1, **i32))
         g = self.build_graph(db, with_coo=with_coo)
         scores = self.gat_forward(db, g) if db.n_nodes > 0 else torch.zeros(1, dtype=torch.float32, device=self.device)
         person_heads, n_persons = self.cluster(db, g, scores)
@@ -471,14 +476,15 @@ class PosePipeline:
     def stage_b(self, db: DeviceBatch, res: dict, want_triangulation: bool = False):
         """Stage 3 of a batch. Reads the person count back (one 4-byte device->host copy: it sizes the launches),
         then person list, MLP-input encoder and MLP."""
-        P = int(res['person_off'][db.n_frames].item())
+        P = int(res['person_off'][db.n_frames].item()) if db.n_heads > 0 else 0
         Cn = self.cfg.n_cameras
         person_sk = torch.empty((max(P, 1), Cn), dtype=torch.int32, device=self.device)
         person_frame = torch.empty(max(P, 1), dtype=torch.int32, device=self.device)
-        self.launches += 1
-        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
-                                             ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
-                                             ptr(person_sk), ptr(person_frame), self._stream()), 'gather_persons')
+        if P > 0:
+            self.launches += 1
+            check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
+                                                 ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
+                                                 ptr(person_sk), ptr(person_frame), self._stream()), 'gather_persons')
         res.update(person_sk=person_sk[:P], person_frame=person_frame[:P], n_persons_total=P)
         if self.mlp is not None:
             if P > 0:
@@ -553,11 +559,13 @@ class PosePipeline:
         person_off = out_bufs['person_off'].numpy()
         person_sk = out_bufs['person_sk'].numpy()
         for f0, f1, pb0, P, h0 in parts:
-            person_off[f0:f1 + 1] += pb0 if f0 > 0 else 0
+            # every chunk wrote its local offsets over [f0, f1]; entry f0 is shared with the previous chunk (its total,
+            # then this chunk's 0), so it is set explicitly and only (f0, f1] is shifted
+            person_off[f0] = pb0
+            person_off[f0 + 1:f1 + 1] += pb0
             if h0:
                 blk = person_sk[pb0:pb0 + P]
                 blk[blk >= 0] += h0
-        # person_off of chunk k > 0 was written over [f0, f1]: entry f0 equals the previous chunk's total by construction
         out = dict(n_persons=out_bufs['n_persons'], person_off=out_bufs['person_off'], person_sk=out_bufs['person_sk'][:P_tot],
                    n_persons_total=P_tot)
         if self.mlp is not None:

@@ -438,3 +438,42 @@ def test_stress_frame_10_views_16_persons():
         props = O.cluster(scores[n0:n1], og['pairs'], og['nodes_camera'][:og['n_heads']], cfg.V_sm, og['n_heads'])
         assert np.array_equal(ph[pb.head_off[b]:pb.head_off[b] + npers[b]], props), b
     assert np.isfinite(res['joints'].cpu().numpy()).all()
+
+
+def test_host_api_variants_agree():
+    """The public host entry points - infer_host (one chunk and several), infer_host_stream, and the native JSON packer
+    feeding them - return exactly what infer() computes on the same frames, in frame order with batch-global indices."""
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    pipe = get_pipe(config)
+    frames = [helpers.synth.make_frame(cfg, 7000 + i, 1 + i % 5, drop_view_p=0.15 * (i % 3)) for i in range(37)]
+    frames[5] = {}                                                          # an empty frame in the middle
+    frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+    pb = pack_mod.pack_frames(frames, cfg, keep_json=False)
+    hb = pipeline_mod.HostBatch(pb)
+    ref = pipe.infer(hb.to_device('cuda:0'))
+    want = dict(n_persons=ref['n_persons'].cpu().numpy(), person_off=ref['person_off'].cpu().numpy(),
+                person_sk=ref['person_sk'].cpu().numpy(), joints=ref['joints'].cpu().numpy(), valid=ref['valid'].cpu().numpy())
+
+    def check(out, exact=True):
+        assert out['n_persons_total'] == ref['n_persons_total']
+        for k, v in want.items():
+            if k == 'joints' and not exact:      # few-person chunks take the small-m projection kernel: other summation order
+                assert np.abs(np.asarray(out[k]) - v).max() <= 1e-5, k
+            else:
+                assert np.array_equal(np.asarray(out[k]), v), k
+
+    check(pipe.infer_host(hb))
+    for n_chunks in (2, 3, 37):
+        check(pipe.infer_host(hb, n_chunks=n_chunks), exact=False)
+    outs = list(pipe.infer_host_stream([hb, hb, hb]))
+    assert len(outs) == 3
+    check(outs[-1])
+    # native packer + pinned buffers
+    pb2 = pack_mod.pack_json(json.dumps(frames), cfg, pinned=True)
+    check(pipe.infer_host(pipeline_mod.HostBatch(pb2)))
+    # a stream of different batches comes back in order
+    halves = [pipeline_mod.HostBatch(pb.slice(0, 20)), pipeline_mod.HostBatch(pb.slice(20, 37))]
+    a, b2 = [dict(n_persons=np.asarray(o['n_persons']).copy(), joints=np.asarray(o['joints']).copy()) for o in pipe.infer_host_stream(halves)]
+    assert np.array_equal(np.concatenate([a['n_persons'], b2['n_persons']]), want['n_persons'])
+    assert np.abs(np.concatenate([a['joints'], b2['joints']]) - want['joints']).max() <= 1e-5
