@@ -250,6 +250,12 @@ __device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();      // a lost copy becomes an error, not a hang
     }
 }
+__device__ __forceinline__ void agg_cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void agg_cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -367,31 +373,34 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         return p.z + (size_t)(n0 + l) * ldz;
     };
     // ---- phase 1a: stage the head rows, a1|a2 of the heads, a1 of the edge-nodes, the heads' in-edge lists ----
+    // Everything goes through cp.async (global -> shared without a register round trip): the five tables are issued
+    // back to back and waited for once, instead of paying one global-memory latency per table. The CSR columns are
+    // staged raw (global node ids); n0 is subtracted where they are used.
     {
         const int vec_per_row = hd4 / 4;                    // ldz % 4 == 0 and columns [HD, hd4) exist in the row (a1 follows)
         for (int i = tid; i < Hb * vec_per_row; i += kFrameThreads) {
             const int r = i / vec_per_row, c = i - r * vec_per_row;
-            reinterpret_cast<float4*>(zh + (size_t)r * hd4)[c] = __ldg(reinterpret_cast<const float4*>(zrow(r)) + c);
+            agg_cp_async16(agg_smem_u32(zh + (size_t)r * hd4 + 4 * c), zrow(r) + 4 * c);
         }
         if (p.layer0)
-            for (int i = tid; i < ldz / 4; i += kFrameThreads)
-                reinterpret_cast<float4*>(zE)[i] = __ldg(reinterpret_cast<const float4*>(zrow(Hb)) + i);
+            for (int i = tid; i < ldz / 4; i += kFrameThreads) agg_cp_async16(agg_smem_u32(zE + 4 * i), zrow(Hb) + 4 * i);
     }
     for (int i = tid; i < Hb * 2 * H; i += kFrameThreads) {
         const int r = i / (2 * H), c = i - r * 2 * H;
-        ah[i] = __ldg(zrow(r) + HD + c);
+        agg_cp_async4(agg_smem_u32(ah + i), zrow(r) + HD + c);
     }
     if (!p.layer0)
         for (int i = tid; i < Mb * H; i += kFrameThreads) {
             const int r = i / H, c = i - r * H;
-            a1e[i] = __ldg(zen + (size_t)r * ldz + HD + c);
+            agg_cp_async4(agg_smem_u32(a1e + i), zen + (size_t)r * ldz + HD + c);
         }
-    for (int i = tid; i < Eh; i += kFrameThreads) lsth[i] = __ldg(p.col + e0 + i) - n0;
+    for (int i = tid; i < Eh; i += kFrameThreads) agg_cp_async4(agg_smem_u32(lsth + i), p.col + e0 + i);
     for (int k = tid; k < Mb; k += kFrameThreads) {
         const int q = e0 + Eh + 3 * k;                      // CSR: 3 in-edges per edge-node after the head rows: h1, h2, self
-        prs[2 * k] = __ldg(p.col + q) - n0;
-        prs[2 * k + 1] = __ldg(p.col + q + 1) - n0;
+        agg_cp_async4(agg_smem_u32(prs + 2 * k), p.col + q);
+        agg_cp_async4(agg_smem_u32(prs + 2 * k + 1), p.col + q + 1);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // ---- phase 1b: softmax weights of the heads' in-edges, per attention head (gat2.py:78-88) ----
     for (int q = tid; q < Hb * H; q += kFrameThreads) {
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         float* wv = wh + (size_t)beg * H + hh;
         float m = -INFINITY;
         for (int i = 0; i < deg; ++i) {
-            const int u = lsth[beg + i];
+            const int u = lsth[beg + i] - n0;
             const float a1u = (u < Hb) ? ah[u * 2 * H + hh] : (p.layer0 ? zE[HD + hh] : a1e[(u - Hb) * H + hh]);
             const float e = leaky(a1u + a2v, p.alpha);
             wv[i * H] = e;
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         // (a) the edge-node destination of this warp: in-edges (h1 -> e), (h2 -> e), (e -> e)
         const int k = k0 + wid;
         if (k < k1) {
-            const int h1 = prs[2 * k], h2 = prs[2 * k + 1];
+            const int h1 = prs[2 * k] - n0, h2 = prs[2 * k + 1] - n0;
             const float* re = rows + (size_t)(k - k0) * rstride;
             // softmax of the three logits, attention head lh (lanes >= H repeat head 0; nobody reads them)
             const float a2e = re[HD + H + lh];
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         for (int t = 0; t < kFrameOwn; ++t) {
             while (hcur[t] < hdeg[t]) {
                 const int pos = hbeg[t] + hcur[t];
-                const int kk = lsth[pos] - Hb;
+                const int kk = lsth[pos] - n0 - Hb;
                 if (kk >= k1) break;
                 const float* re = rows + (size_t)(kk - k0) * rstride;
                 const float* wp = wh + (size_t)pos * H;
