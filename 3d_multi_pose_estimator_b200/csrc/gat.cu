@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
     extern __shared__ __align__(128) float smem_f[];
     __shared__ __align__(8) uint64_t bar_full[kSlots];
     __shared__ __align__(8) uint64_t bar_empty[kSlots];
+    __shared__ __align__(8) uint64_t bar_wh;                  // the heads' softmax weights (phase 1b) are complete
     const int b = blockIdx.x;
     const int n0 = p.node_off[b];
     const int Nb = p.node_off[b + 1] - n0;
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
     if (tid == kFrameWarps * 32) {                          // lane 0 of the producer warp
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) { agg_mbar_init(agg_smem_u32(&bar_full[s]), 1); agg_mbar_init(agg_smem_u32(&bar_empty[s]), kFrameWarps); }
+        agg_mbar_init(agg_smem_u32(&bar_wh), kFrameWarps + 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (streamed)
             for (int c = 0; c < kSlots && c < n_chunks; ++c) issue_chunk(c);
@@ -425,7 +427,10 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         }
         for (int i = 0; i < deg; ++i) wv[i * H] = wv[i * H] / den;
     }
-    __syncthreads();
+    // no CTA barrier here: only part (b) of the chunk loop reads the heads' weights, so every warp just reports its share
+    // of phase 1b done and the consumers wait for all reports after the edge-node destinations of their first chunk
+    __syncwarp();
+    if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_wh));
     // ---- phase 2 ----
     if (wid == kFrameWarps) {
         // ===== producer warp: refill a slot as soon as all consumer warps have released it =====
@@ -450,7 +455,8 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         cj[j] = okj[j] ? cv * VEC : 0;
         hj[j] = cj[j] / D;
     }
-    // owned head destinations: accumulators in registers, initialised with the self loop (first in-edge of the row)
+    // owned head destinations: accumulators in registers, initialised with the self loop (first in-edge of the row) once the
+    // heads' weights are known
     float acc[kFrameOwn][KMAX][VEC];
     int hbeg[kFrameOwn], hdeg[kFrameOwn], hcur[kFrameOwn];
 #pragma unroll
@@ -461,20 +467,28 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
             hbeg[t] = __ldg(p.row_ptr + n0 + h) - e0;
             hdeg[t] = __ldg(p.row_ptr + n0 + h + 1) - e0 - hbeg[t];
         }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-            float zv[VEC];
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) zv[q] = 0.f;
-            float a = 0.f;
-            if (h < Hb && okj[j]) {
-                *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zh + (size_t)h * hd4 + cj[j]);
-                a = wh[(size_t)hbeg[t] * H + hj[j]];
-            }
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
-        }
     }
+    auto init_acc = [&]() {
+        agg_mbar_wait(agg_smem_u32(&bar_wh), 0u);
+#pragma unroll
+        for (int t = 0; t < kFrameOwn; ++t) {
+            const int h = wid + t * kFrameWarps;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+                float zv[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) zv[q] = 0.f;
+                float a = 0.f;
+                if (h < Hb && okj[j]) {
+                    *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zh + (size_t)h * hd4 + cj[j]);
+                    a = wh[(size_t)hbeg[t] * H + hj[j]];
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
+            }
+        }
+    };
+    if (n_chunks == 0) init_acc();
     const int lh = lane < H ? lane : 0;                     // attention head whose edge-node softmax this lane computes
     for (int c = 0; c < n_chunks; ++c) {
         const int k0 = c * kChunkRows, k1 = min(Mb, k0 + kChunkRows);
@@ -516,6 +530,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
             }
         }
         // (b) contributions of the chunk's rows to the owned heads, ascending edge id
+        if (c == 0) init_acc();
 #pragma unroll
         for (int t = 0; t < kFrameOwn; ++t) {
             while (hcur[t] < hdeg[t]) {
