@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         int i = 0;
         bool stores_pending = false;
         const bool slope_le1 = p.slope >= 0.f && p.slope <= 1.f;
+        const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
         for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
             const TileInfo t = tile_info<NCTA>(p, w.tile(p));
             const int a = i & 1;
@@ -552,13 +553,65 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     }
                 }
                 if (p.dbg & 4) continue;
+                float v[64];
+                // full panels with a 16-byte aligned bias: every lane reads the panel's 64 bias values with 16 broadcast
+                // vector loads (one L1 transaction each) instead of 128 shuffles - the epilogue warps share their
+                // schedulers with the TMA and MMA issuing threads, so every instruction less is tensor-pipe time
+                if (slope_le1 && bias_vec && col0 + 64 <= p.N) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                    // LeakyReLU(y) * s = max(y * s, y * slope * s) for s > 0 and slope <= 1; with s == 1 (every projection but the
+                    // last MLP layer) one multiply disappears
+                    const float s1 = p.out_scale, s2 = p.slope * p.out_scale;
+                    if (s1 == 1.f) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 ba = __ldg(b4 + c), bb = __ldg(b4 + 8 + c);
+                            const float ya[4] = {__uint_as_float(r0[4 * c]) + ba.x, __uint_as_float(r0[4 * c + 1]) + ba.y,
+                                                 __uint_as_float(r0[4 * c + 2]) + ba.z, __uint_as_float(r0[4 * c + 3]) + ba.w};
+                            const float yb[4] = {__uint_as_float(r1[4 * c]) + bb.x, __uint_as_float(r1[4 * c + 1]) + bb.y,
+                                                 __uint_as_float(r1[4 * c + 2]) + bb.z, __uint_as_float(r1[4 * c + 3]) + bb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[4 * c + e] = fmaxf(ya[e], ya[e] * s2);
+                                v[32 + 4 * c + e] = fmaxf(yb[e], yb[e] * s2);
+                            }
+                        }
+                    } else if (s1 > 0.f) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 ba = __ldg(b4 + c), bb = __ldg(b4 + 8 + c);
+                            const float ya[4] = {__uint_as_float(r0[4 * c]) + ba.x, __uint_as_float(r0[4 * c + 1]) + ba.y,
+                                                 __uint_as_float(r0[4 * c + 2]) + ba.z, __uint_as_float(r0[4 * c + 3]) + ba.w};
+                            const float yb[4] = {__uint_as_float(r1[4 * c]) + bb.x, __uint_as_float(r1[4 * c + 1]) + bb.y,
+                                                 __uint_as_float(r1[4 * c + 2]) + bb.z, __uint_as_float(r1[4 * c + 3]) + bb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[4 * c + e] = fmaxf(ya[e] * s1, ya[e] * s2);
+                                v[32 + 4 * c + e] = fmaxf(yb[e] * s1, yb[e] * s2);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 ba = __ldg(b4 + c), bb = __ldg(b4 + 8 + c);
+                            const float ya[4] = {__uint_as_float(r0[4 * c]) + ba.x, __uint_as_float(r0[4 * c + 1]) + ba.y,
+                                                 __uint_as_float(r0[4 * c + 2]) + ba.z, __uint_as_float(r0[4 * c + 3]) + ba.w};
+                            const float yb[4] = {__uint_as_float(r1[4 * c]) + bb.x, __uint_as_float(r1[4 * c + 1]) + bb.y,
+                                                 __uint_as_float(r1[4 * c + 2]) + bb.z, __uint_as_float(r1[4 * c + 3]) + bb.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[4 * c + e] = leaky_le1(ya[e], p.slope) * s1;
+                                v[32 + 4 * c + e] = leaky_le1(yb[e], p.slope) * s1;
+                            }
+                        }
+                    }
+                } else {
                 // bias of the panel: lane l holds columns col0+l and col0+32+l
                 float b0 = 0.f, b1 = 0.f;
                 if (p.bias) {
                     if (col0 + lane < p.N) b0 = __ldg(p.bias + col0 + lane);
                     if (col0 + 32 + lane < p.N) b1 = __ldg(p.bias + col0 + 32 + lane);
                 }
-                float v[64];
                 if (slope_le1) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
@@ -573,6 +626,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                         v[c] = (col0 + c < p.N) ? leaky(__uint_as_float(r0[c]) + bb0, p.slope) * p.out_scale : 0.f;
                         v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
                     }
+                }
                 }
                 if (stores_pending) {                             // staging buffers are about to be overwritten
                     if (lane == 0) bulk_wait_read0();
