@@ -25,6 +25,7 @@ struct AggParams {
     int chunk;          // destination nodes per CTA (work unit = frame x chunk)
     int n_chunks;       // chunks per frame (grid = n_frames * n_chunks)
     int max_deg;        // largest in-degree (sizes the per-warp attention scratch)
+    int dbg;            // b200pose_set_debug bits: 16 = no output stores, 32 = skip head contributions, 64 = skip edge-node destinations
 };
 
 template <int VEC> __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
@@ -32,6 +33,12 @@ template <int VEC> __device__ __forceinline__ void load_vec(const float* p, floa
     else if constexpr (VEC == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
     else v[0] = *p;
 }
+
+// Softmax arithmetic of both aggregation kernels: exp(x) for x <= 0 through the SFU (ex2.approx, ~2 ulp) and the
+// normalisation through the SFU reciprocal - a softmax weight that is off by 1e-7 relative moves a score by far less
+// than the 1e-4 tolerance, and the precise expf/IEEE division cost ~25 issue slots per weight in issue-bound kernels.
+__device__ __forceinline__ float soft_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float soft_div(float x, float d) { return __fdividef(x, d); }
 
 constexpr int kAggWarps = 8;
 
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         for (int t0 = 0; t0 < npair; t0 += 32) {                // uniform trip count: every lane takes part in the shuffle
             const int t = t0 + lane;
             const float m = __shfl_sync(0xffffffffu, mh, t % H);
-            if (t < npair) att[t] = expf(att[t] - m);
+            if (t < npair) att[t] = soft_exp(att[t] - m);
         }
         __syncwarp();
         float dh = 0.f;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         for (int t0 = 0; t0 < npair; t0 += 32) {
             const int t = t0 + lane;
             const float d = __shfl_sync(0xffffffffu, dh, t % H);
-            if (t < npair) att[t] = att[t] / d;
+            if (t < npair) att[t] = soft_div(att[t], d);
         }
         __syncwarp();
         // 3. out[v] = sum_i s[i][h] * ft2[u_i]                                        (gat2.py:66)
@@ -288,6 +295,7 @@ template <> struct VecT<2> { using type = float2; };
 template <> struct VecT<1> { using type = float; };
 
 template <int VEC> __device__ __forceinline__ void store_out(const AggParams& p, bool slope_le1, int gv, int c0, const float (&v)[VEC]) {
+    if (p.dbg & 16) return;
     if (p.raw_f32) {
         float* o = p.raw_f32 + (size_t)gv * (p.heads * p.dim) + c0;
 #pragma unroll
@@ -421,11 +429,11 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         }
         float den = 0.f;
         for (int i = 0; i < deg; ++i) {
-            const float e = expf(wv[i * H] - m);
+            const float e = soft_exp(wv[i * H] - m);
             wv[i * H] = e;
             den += e;
         }
-        for (int i = 0; i < deg; ++i) wv[i * H] = wv[i * H] / den;
+        for (int i = 0; i < deg; ++i) wv[i * H] = soft_div(wv[i * H], den);
     }
     // no CTA barrier here: only part (b) of the chunk loop reads the heads' weights, so every warp just reports its share
     // of phase 1b done and the consumers wait for all reports after the edge-node destinations of their first chunk
@@ -502,7 +510,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         }
         // (a) the edge-node destination of this warp: in-edges (h1 -> e), (h2 -> e), (e -> e)
         const int k = k0 + wid;
-        if (k < k1) {
+        if (k < k1 && !(p.dbg & 64)) {
             const int h1 = prs[2 * k] - n0, h2 = prs[2 * k + 1] - n0;
             const float* re = rows + (size_t)(k - k0) * rstride;
             // softmax of the three logits, attention head lh (lanes >= H repeat head 0; nobody reads them)
@@ -511,9 +519,9 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
             const float e2 = leaky(ah[h2 * 2 * H + lh] + a2e, p.alpha);
             const float e3 = leaky(re[HD + lh] + a2e, p.alpha);
             const float m = fmaxf(fmaxf(e1, e2), e3);
-            const float x1 = expf(e1 - m), x2 = expf(e2 - m), x3 = expf(e3 - m);
+            const float x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m), x3 = soft_exp(e3 - m);
             const float den = (0.f + x1 + x2) + x3;
-            const float s1 = x1 / den, s2 = x2 / den, s3 = x3 / den;
+            const float s1 = soft_div(x1, den), s2 = soft_div(x2, den), s3 = soft_div(x3, den);
 #pragma unroll
             for (int j = 0; j < KMAX; ++j) {
                 const float w1 = __shfl_sync(0xffffffffu, s1, hj[j]);
@@ -533,7 +541,7 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
         if (c == 0) init_acc();
 #pragma unroll
         for (int t = 0; t < kFrameOwn; ++t) {
-            while (hcur[t] < hdeg[t]) {
+            while (hcur[t] < hdeg[t] && !(p.dbg & 32)) {
                 const int pos = hbeg[t] + hcur[t];
                 const int kk = lsth[pos] - n0 - Hb;
                 if (kk >= k1) break;
@@ -641,6 +649,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.alpha = alpha; p.act_slope = act_slope; p.raw_f32 = raw_f32;
     p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
     p.ld_planes = ld_planes;
+    p.dbg = g_debug_flags;
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
     // ---- frame-resident kernel: one CTA per frame, whenever the frame plan fits in shared memory ----
     if (impl == 0 && max_heads_per_frame > 0 && max_enodes_per_frame > 0 && max_heads_per_frame <= kFrameOwn * kFrameWarps &&

@@ -1149,8 +1149,6 @@ static int choose_bn(int n) {
 
 using namespace b200pose;
 
-static int g_gemm_debug = 0;
-extern "C" __attribute__((visibility("default"))) int b200pose_set_debug(int flags) { const int old = g_gemm_debug; g_gemm_debug = flags; return old; }
 
 extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                                const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
@@ -1235,7 +1233,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 2 * kBM ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
-    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_gemm_debug;
+    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags;
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo;
