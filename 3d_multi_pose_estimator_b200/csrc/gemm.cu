@@ -1230,7 +1230,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     // CTA pairs (cta_group::2, 256-row tiles) as soon as there is more than one pair tile of rows: per flop a pair pulls
     // 1.5x fewer bytes through the L2->SM fabric, which bounds both the tall GAT projections and the MLP (every m-tile
     // re-reads the whole weight matrix from L2)
-    const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 2 * kBM ? 2 : 1);
+    const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 4 * kBM ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
     q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags;
@@ -1281,6 +1281,9 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     }
     q.tiles_n = ceil_div(q.panels_total, 4);
     q.tiles_m = ceil_div(m, kBM * ncta);
+    // a handful of m-tiles (single-frame calls: ~180 graph nodes): one 64-column panel per tile, so that the k-loops of
+    // an output row run side by side on many SMs instead of back to back on one - latency, not throughput, matters here
+    if (impl == 0 && ncta == 1 && q.tiles_m * q.tiles_n * 8 < num_sms()) q.tiles_n = q.panels_total;
     q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
     const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)(q.stage_bn / ncta) * kBK * 2;
     int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
