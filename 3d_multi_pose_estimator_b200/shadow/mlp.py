@@ -4,25 +4,21 @@ from torch import nn
 
 import _b200pose_runtime as rt
 
+HIDDEN_WIDTHS = (3072, 3072, 2048, 2048, 1024, 1024, 1024, 1024)     # the reference's layer widths (utils/mlp.py:11-27)
+
 
 class PoseEstimatorMLP(nn.Module):
     def __init__(self, input_dimensions, output_dimensions):
         super().__init__()
         print('MLP input size', input_dimensions)
-        negative_slope = 0.1
-        self.negative_slope = negative_slope
-        self.layers = nn.Sequential(
-            nn.Flatten(),
-            nn.Linear(input_dimensions, 3072), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(3072, 3072), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(3072, 2048), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(2048, 2048), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(2048, 1024), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(1024, 1024), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(1024, 1024), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(1024, 1024), nn.LeakyReLU(negative_slope=negative_slope),
-            nn.Linear(1024, output_dimensions),
-        )
+        self.negative_slope = 0.1                                   # LeakyReLU slope of every hidden layer (utils/mlp.py:7)
+        widths = (input_dimensions,) + HIDDEN_WIDTHS + (output_dimensions,)
+        modules = [nn.Flatten()]                                    # index 0, so the projections sit at 1, 3, ..., 17
+        for i in range(len(widths) - 1):
+            modules.append(nn.Linear(widths[i], widths[i + 1]))
+            if i < len(widths) - 2:
+                modules.append(nn.LeakyReLU(negative_slope=self.negative_slope))
+        self.layers = nn.Sequential(*modules)
         self._prepared = None
         self._prepared_key = None
 
