@@ -367,8 +367,13 @@ def main():
                     'traffic_note': 'dram bytes read+written per step by this kernel class, ncu --set full (profiles/r01_traffic.json)',
                     'peak_source': peak_src + (' (bf16 sustained; achieved counts the 3 executed split-bf16 MMAs)'
                                                if dominant['bound'] == 'tensor' else '')}
-        cpu_fps, cpu_n, cpu_dt, cpu_procs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=args.cpu_budget,
-                                                               n_frames=4 * (os.cpu_count() or 1))
+        cpu_line = None
+        if world == 1:                            # the CPU arm is timed on rank 0 of single-GPU runs only
+            cpu_fps, cpu_n, cpu_dt, cpu_procs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=args.cpu_budget,
+                                                                   n_frames=4 * (os.cpu_count() or 1))
+            cpu_line = {'value': cpu_fps, 'unit': UNIT, 'cores': cpu_procs, 'kind': 'port',
+                        'sample': '%d frames of the same workload over %d host processes, one frame at a time each, %.1f s'
+                                  % (cpu_n, cpu_procs, cpu_dt)}
         line = {'metric': METRIC, 'value': total_frames / ms_max * 1e3, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate; fp64 geometry', 'data': 'synthetic',
@@ -377,9 +382,7 @@ def main():
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_max, 'single_call_ms': single_ms,
                         'mode': 'streamed: copy of step i+1 overlaps compute of step i'},
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
-                'cpu_baseline': {'value': cpu_fps, 'unit': UNIT, 'cores': cpu_procs, 'kind': 'port',
-                                 'sample': '%d frames of the same workload over %d host processes, one frame at a time each, %.1f s'
-                                           % (cpu_n, cpu_procs, cpu_dt)},
+                'cpu_baseline': cpu_line,
                 'persons_found_per_frame': P / args.frames,
                 'p50_frame_latency_ms': p50_ms}
         print(json.dumps(line))
