@@ -130,14 +130,35 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
         flag[h] = 0;
     }
     // ---- matchings above the threshold (:49-55): sort key = (score, edge-node index descending) ----
-    for (int k = tid; k < Mpad; k += nt) {
-        unsigned long long key = 0ull;
-        if (k < M) {
-            const float s = p.scores[n0 + H + k];
-            if ((double)s > p.threshold)
-                key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+    // Small frames (one warp, <= 512 edge-nodes): the keys above the threshold are compacted with a ballot prefix and
+    // rank-sorted - every lane counts, for each of its keys, how many keys are greater (broadcast reads, no dependent
+    // chain) - instead of 36 dependent passes of a padded bitonic network, which took half of this kernel.
+    const bool rank_sort = one_warp && p.max_keys <= 512;
+    int n_valid = 0;
+    if (rank_sort) {
+        for (int k0 = 0; k0 < M; k0 += 32) {
+            const int k = k0 + lane;
+            unsigned long long key = 0ull;
+            if (k < M) {
+                const float s = p.scores[n0 + H + k];
+                if ((double)s > p.threshold)
+                    key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, key != 0ull);
+            if (key != 0ull) keys[n_valid + __popc(bal & ((1u << lane) - 1u))] = key;
+            n_valid += __popc(bal);
         }
-        keys[k] = key;
+        __syncwarp();
+    } else {
+        for (int k = tid; k < Mpad; k += nt) {
+            unsigned long long key = 0ull;
+            if (k < M) {
+                const float s = p.scores[n0 + H + k];
+                if ((double)s > p.threshold)
+                    key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
+            }
+            keys[k] = key;
+        }
     }
     bsync();
     // ---- edge walk: first-seen order of the heads (:32-47), one warp, order-dependent ----
@@ -163,6 +184,32 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     bsync();
     const int n_seen = n_seen_s;
 
+    if (rank_sort) {
+        // ---- rank sort, descending (keys are unique: the edge-node index is part of the key) ----
+        unsigned long long mine[16];
+        int rank[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int idx = lane + 32 * r;
+            mine[r] = idx < n_valid ? keys[idx] : 0ull;
+            rank[r] = 0;
+        }
+        const int R = (n_valid + 31) >> 5;                           // key slots in use per lane (uniform)
+        for (int j = 0; j < n_valid; ++j) {
+            const unsigned long long kj = keys[j];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                if (r >= R) break;
+                rank[r] += (kj > mine[r]) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (lane + 32 * r < n_valid) keys[rank[r]] = mine[r];
+        if (lane == 0 && n_valid < p.max_keys) keys[n_valid] = 0ull;     // terminates the merge walk
+        __syncwarp();
+    } else {
     // ---- bitonic sort, descending: score desc, edge-node index asc (:60) ----
     for (int size = 2; size <= Mpad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -177,9 +224,10 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
             bsync();
         }
     }
+    }
     // ---- replace every sorted key by its (h1, h2) pair: one parallel pass of coalesced-ish global reads, so the
     // sequential merge below touches shared memory only ----
-    for (int t = tid; t < Mpad; t += nt) {
+    for (int t = tid; t < (rank_sort ? n_valid : Mpad); t += nt) {
         const unsigned long long key = keys[t];
         if (key != 0ull) {
             const int k = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
@@ -194,7 +242,8 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     int n_links = 0;
     if (tid == 0) {
         int cur = 0;
-        for (int t = 0; t < M; ++t) {
+        const int n_match = rank_sort ? n_valid : M;
+        for (int t = 0; t < n_match; ++t) {
             const unsigned long long key = keys[t];
             if (key == 0ull) break;
             const int h1 = (int)((key >> 31) & 0x7FFFFFFFull), h2 = (int)(key & 0x7FFFFFFFull);
