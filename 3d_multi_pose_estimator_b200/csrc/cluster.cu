@@ -161,25 +161,25 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
         }
     }
     bsync();
-    // ---- edge walk: first-seen order of the heads (:32-47), one warp, order-dependent ----
-    if (warp == 0) {
+    // ---- first-seen order of the heads in the reference's edge walk (:32-47), in closed form. Edge-nodes are ordered
+    // by camera-group pair (g0,g1), (g0,g2), ..., (g1,g2), ... and, inside a pair, head1-major; an edge-node shows its
+    // head1 before its head2. With a = heads of g0 and b = heads of g1 the walk therefore meets a0, b0, b1, ..., then
+    // a1, a2, ..., then the heads of g2, g3, ... in index order; heads are numbered group by group, so
+    //     first_seen = [0, n0 .. n0+n1-1, 1 .. n0-1, n0+n1 .. H-1]          (n0, n1 = sizes of the first two groups)
+    // and a frame whose heads all sit in one camera has no edge-node and sees nothing. ----
+    if (tid == 0) {
+        int n0g = 1;
+        while (n0g < H && cam[n0g] == cam[0]) ++n0g;
         int n_seen = 0;
-        for (int k0 = 0; k0 < M; k0 += 32) {
-            const int k = k0 + lane;
-            int h1 = -1, h2 = -1;
-            if (k < M) { h1 = p.pairs[2 * (m0 + k)]; h2 = p.pairs[2 * (m0 + k) + 1]; }
-            const int cnt = min(32, M - k0);
-            for (int t = 0; t < cnt; ++t) {
-                const int a = __shfl_sync(0xffffffffu, h1, t);
-                const int c = __shfl_sync(0xffffffffu, h2, t);
-                if (lane == 0) {
-                    if (!flag[a]) { flag[a] = 1; first_seen[n_seen++] = a; }
-                    if (!flag[c]) { flag[c] = 1; first_seen[n_seen++] = c; }
-                }
-            }
-            if (__shfl_sync(0xffffffffu, n_seen, 0) == H) break;       // every head has been seen
+        if (n0g < H && M > 0) {
+            int n1g = 1;
+            while (n0g + n1g < H && cam[n0g + n1g] == cam[n0g]) ++n1g;
+            first_seen[n_seen++] = 0;
+            for (int i = 0; i < n1g; ++i) first_seen[n_seen++] = n0g + i;
+            for (int i = 1; i < n0g; ++i) first_seen[n_seen++] = i;
+            for (int i = n0g + n1g; i < H; ++i) first_seen[n_seen++] = i;
         }
-        if (lane == 0) n_seen_s = n_seen;
+        n_seen_s = n_seen;
     }
     bsync();
     const int n_seen = n_seen_s;
