@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_seen_s;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
     const bool one_warp = nt == 32;
     auto bsync = [&]() { if (one_warp) __syncwarp(); else __syncthreads(); };
     const int b = blockIdx.x;
