@@ -25,6 +25,9 @@ struct AggParams {
     int chunk;          // destination nodes per CTA (work unit = frame x chunk)
     int n_chunks;       // chunks per frame (grid = n_frames * n_chunks)
     int max_deg;        // largest in-degree (sizes the per-warp attention scratch)
+    int stage_cap;      // large-frame kernel: z rows of shared memory per CTA
+    int edge_units;     // large-frame kernel: edge-node work units per frame
+    int head_units;     // large-frame kernel: head work units per frame
     int dbg;            // b200pose_set_debug bits: 16 = no output stores, 32 = skip head contributions, 64 = skip edge-node destinations
 };
 
@@ -105,6 +108,42 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         const int beg = p.row_ptr[gv];
         const int deg = min(p.row_ptr[gv + 1] - beg, p.max_deg);
         const float* rowv = row_of(gv);
+        float acc[KMAX][VEC];
+        if (deg == 3 && 3 * H <= 32) {
+            // edge-node destination (two heads + self loop): lane t = i * H + h holds the logit and then the softmax
+            // weight of in-edge i, attention head h; the three rows are loaded together. Same operation order as below.
+            const int i = min(lane / H, 2), h = lane - (lane / H) * H;
+            const float* r3[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) r3[u] = row_of(__ldg(p.col + beg + u));
+            const float* rme = i == 0 ? r3[0] : (i == 1 ? r3[1] : r3[2]);
+            float f[3][KMAX][VEC];
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const int cv = lane + 32 * k;
+                    if (cv < n_vec) load_vec<VEC>(r3[u] + cv * VEC, f[u][k]);
+                }
+            const float e = lane < 3 * H ? leaky(rme[HD + h] + rowv[HD + H + h], p.alpha) : 0.f;
+            const float e0 = __shfl_sync(0xffffffffu, e, h), e1 = __shfl_sync(0xffffffffu, e, H + h), e2 = __shfl_sync(0xffffffffu, e, 2 * H + h);
+            const float m = fmaxf(fmaxf(e0, e1), e2);
+            const float x0 = soft_exp(e0 - m), x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m);
+            const float den = (x0 + x1) + x2;
+            const float wgt = soft_div(i == 0 ? x0 : (i == 1 ? x1 : x2), den);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                float a[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) a[u] = __shfl_sync(0xffffffffu, wgt, u * H + head_of[k]);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    float s = fmaf(a[0], f[0][k][q], 0.f);
+                    s = fmaf(a[1], f[1][k][q], s);
+                    acc[k][q] = fmaf(a[2], f[2][k][q], s);
+                }
+            }
+        } else {
         // 1. attention logits e[i][h] = LeakyReLU(a1[u_i][h] + a2[v][h])            (gat2.py:78-81)
         const int npair = deg * H;
         for (int t = lane; t < npair; t += 32) {
@@ -131,7 +170,6 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         }
         __syncwarp();
         // 3. out[v] = sum_i s[i][h] * ft2[u_i]                                        (gat2.py:66)
-        float acc[KMAX][VEC];
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
 #pragma unroll
@@ -170,6 +208,7 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
             }
         }
         __syncwarp();                                           // att is reused by the next destination
+        }
         // 4. outputs
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
@@ -614,6 +653,355 @@ __global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
     if (scores) scores[v] = 1.0f / (1.0f + expf(-acc));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large frames (more heads than the frame-resident plan holds: a 10-view x 16-person frame has 160 heads, 11520
+// edge-nodes and 19.6 MB of z rows). Work unit = (frame, u), the units of a frame adjacent in the grid:
+//   u <  edge_units : kLargeChunk consecutive edge-node destinations. Edge-nodes are ordered by pair block
+//                     (group gi < gj) and row-major inside it, so a chunk touches a handful of distinct head rows
+//                     (4 + 16 for 16-person views). The CTA marks the heads its destinations reference and stages
+//                     those rows in shared memory once; every warp streams the rows of its destinations' third
+//                     in-edge (the self loop - the only row that has to come from HBM) through a private
+//                     kEdgeRing-deep cp.async ring, and holds the 3-in-edge softmax in registers.
+//   u >= edge_units : kLargeHeads head destinations, kAggWarps / kLargeHeads warps each. A head's in-edges are its
+//                     self loop and one edge-node per head of every other view (145 rows) - rows the edge units of
+//                     the same frame have just pulled through L2. Each warp streams a contiguous part of the in-edges
+//                     through a kHeadRing-deep cp.async ring with a running-max softmax (one pass: no separate logit
+//                     sweep over 145 rows); the warps' partial (max, denominator, sum) triples are merged in warp
+//                     order. Mathematically the reference's edge_softmax + sum; fp32 rounding differs from the
+//                     one-warp gather by reassociation and the exp(m_w - M) rescale (~1e-7 relative).
+// Every z row is read from HBM once per layer and every output row written once.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLargeChunk = 64;        // edge-node destinations per edge unit
+constexpr int kLargeHeads = 4;         // head destinations per head unit
+constexpr int kLargeStageCap = 32;     // staged head rows per edge unit
+constexpr int kEdgeRing = 4;           // rows in flight per warp, edge units
+constexpr int kHeadRing = 6;           // rows in flight per warp, head units
+constexpr int kWarpsPerHead = kAggWarps / kLargeHeads;
+static_assert(kLargeChunk / kAggWarps * 3 <= 32, "edge units: one lane per (destination, in-edge)");
+static_assert(kLargeChunk / kAggWarps >= kEdgeRing, "edge ring deeper than a warp's destinations");
+
+template <int N> __device__ __forceinline__ void agg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void agg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// one z row (ldz floats, 16 B aligned) by the 32 lanes of a warp
+__device__ __forceinline__ void agg_row_async(float* dst, const float* src, int ldz, int lane) {
+    for (int c = lane; c < ldz / 4; c += 32) agg_cp_async16(agg_smem_u32(dst + 4 * c), src + 4 * c);
+}
+
+struct LargePlan { int stage, slots, idx, ring, part, pm, pd, shared, total_floats; };
+__host__ __device__ inline LargePlan large_plan(int max_heads, int HD, int ldz, int vec) {
+    LargePlan f;
+    int o = 0;
+    f.ring = o;                                    // edge: [kAggWarps][kEdgeRing][ldz]; head: [kAggWarps][kHeadRing][ldz]
+    const int ring_rows = kAggWarps * (kHeadRing > kEdgeRing ? kHeadRing : kEdgeRing);
+    // the head units have no staged rows: their deeper ring overlays the edge units' ring + stage area
+    f.stage = o + kAggWarps * kEdgeRing * ldz;     // [kLargeStageCap + 1][ldz]
+    int edge_end = f.stage + (kLargeStageCap + 1) * ldz;
+    f.slots = edge_end; edge_end += (max_heads + 1) / 2 + 1;          // short[max_heads]
+    f.idx = edge_end; edge_end += 3 * kLargeChunk;                    // int[kLargeChunk][3]
+    int head_end = o + ring_rows * ldz;
+    f.part = head_end; head_end += kAggWarps * HD;                    // [kAggWarps][HD]
+    f.pm = head_end; head_end += kAggWarps * (HD / vec);              // [kAggWarps][n_vec]
+    f.pd = head_end; head_end += kAggWarps * (HD / vec);
+    f.shared = head_end; head_end += ldz;                             // layer 0: the row all edge-nodes share
+    f.total_floats = (edge_end > head_end ? edge_end : head_end) + 4;
+    return f;
+}
+
+template <int VEC, int KMAX>
+__device__ __forceinline__ void store_row(const AggParams& p, int gv, int lane, int n_vec, int HD, const float (&acc)[KMAX][VEC])
+{
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int cv = lane + 32 * k;
+        if (cv >= n_vec) continue;
+        if (p.raw_f32) {
+            float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o[q] = acc[k][q];
+        }
+        if (p.act_hi) {
+            __nv_bfloat16 hi[VEC], lo[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) split_bf16(leaky(acc[k][q], p.act_slope), hi[q], lo[q]);
+            __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + cv * VEC;
+            __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + cv * VEC;
+            if constexpr (VEC == 4) {
+                *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+                *reinterpret_cast<uint2*>(ol) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+            } else if constexpr (VEC == 2) {
+                *reinterpret_cast<uint32_t*>(oh) = pack_bf16x2(hi[0], hi[1]);
+                *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(lo[0], lo[1]);
+            } else {
+                oh[0] = hi[0]; ol[0] = lo[0];
+            }
+        }
+    }
+    if (p.act_hi)                                               // K padding of the planes stays zero
+        for (int c = HD + lane; c < p.ld_planes; c += 32) {
+            p.act_hi[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
+            p.act_lo[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
+        }
+}
+
+template <int VEC, int KMAX>
+__global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(AggParams p, int max_heads)
+{
+    extern __shared__ __align__(16) float smem_l[];
+    const int units = p.edge_units + p.head_units;
+    const int b = blockIdx.x / units, u = blockIdx.x - b * units;
+    const int n0 = p.node_off[b], Nb = p.node_off[b + 1] - n0;
+    const int h0 = p.head_off[b], Hb = p.head_off[b + 1] - h0;
+    const int H = p.heads, D = p.dim, HD = H * D, ldz = p.ldz;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_vec = HD / VEC;
+    const LargePlan plan = large_plan(max_heads, HD, ldz, VEC);
+    int head_of[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) head_of[k] = min(H - 1, ((lane + 32 * k) * VEC) / D);
+    auto grow_of = [&](int l) -> const float* {                // z row of local node l, in global memory
+        if (p.layer0) return p.z + (size_t)(l < Hb ? h0 + l : p.n_heads_total) * ldz;
+        return p.z + (size_t)(n0 + l) * ldz;
+    };
+
+    if (u < p.edge_units) {
+        // ---------------- edge-node destinations ----------------
+        const int v_begin = Hb + u * kLargeChunk;
+        if (v_begin >= Nb || (p.dbg & 64)) return;
+        const int v_end = min(Nb, v_begin + kLargeChunk);
+        float* zs = smem_l + plan.stage;
+        float* ring = smem_l + plan.ring + (size_t)warp * kEdgeRing * ldz;
+        short* slot_of = reinterpret_cast<short*>(smem_l + plan.slots);
+        int* idx = reinterpret_cast<int*>(smem_l + plan.idx);                 // [kLargeChunk][3] local in-edge sources, -1 = skip
+        // in-edges of the chunk: thread t < 3 * kLargeChunk takes in-edge t % 3 of destination t / 3
+        int my_l = -1;
+        if (tid < 3 * kLargeChunk) {
+            const int j = tid / 3, e = tid - 3 * j;
+            if (v_begin + j < v_end) {
+                const int beg = p.row_ptr[n0 + v_begin + j];
+                if (p.row_ptr[n0 + v_begin + j + 1] - beg == 3) my_l = __ldg(p.col + beg + e) - n0;   // build_graph: 3 in-edges per edge-node
+            }
+        }
+        for (int l = tid; l < Hb; l += blockDim.x) slot_of[l] = -1;
+        __syncthreads();
+        if (tid < 3 * kLargeChunk) {
+            idx[tid] = my_l;
+            if (my_l >= 0 && my_l < Hb && tid % 3 != 2) slot_of[my_l] = 0;    // heads this chunk references
+        }
+        __syncthreads();
+        // every warp starts the stream of its destinations' third-in-edge rows (warp w takes destinations w, w + 8, ..)
+        const int n_mine = v_begin + warp < v_end ? (v_end - v_begin - warp + kAggWarps - 1) / kAggWarps : 0;
+        auto fetch = [&](int j) {                                            // row of in-edge 2 of my destination j -> ring slot j % kEdgeRing
+            if (j < n_mine && !p.layer0) {
+                const int l2 = idx[3 * (warp + kAggWarps * j) + 2];
+                if (l2 >= 0) agg_row_async(ring + (size_t)(j % kEdgeRing) * ldz, grow_of(l2), ldz, lane);
+            }
+            agg_cp_async_commit();
+        };
+#pragma unroll
+        for (int j = 0; j < kEdgeRing; ++j) fetch(j);
+        if (warp == 0) {                                                      // staging slots in head order, up to stage_cap
+            int base = 0;
+            for (int l0 = 0; l0 < Hb; l0 += 32) {
+                const int l = l0 + lane;
+                const bool need = l < Hb && slot_of[l] == 0;
+                const unsigned m = __ballot_sync(0xffffffffu, need);
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (l < Hb) slot_of[l] = (need && slot < p.stage_cap) ? (short)slot : (short)-1;
+                base += __popc(m);
+            }
+        }
+        __syncthreads();
+        for (int l = warp; l < Hb; l += kAggWarps) {
+            const int slot = slot_of[l];
+            if (slot >= 0) agg_row_async(zs + (size_t)slot * ldz, grow_of(l), ldz, lane);
+        }
+        if (p.layer0 && warp == kAggWarps - 1)                                // the row all edge-nodes share in layer 0
+            agg_row_async(zs + (size_t)p.stage_cap * ldz, p.z + (size_t)p.n_heads_total * ldz, ldz, lane);
+        agg_cp_async_commit();
+        agg_cp_async_wait<0>();
+        __syncthreads();
+        auto head_row = [&](int l) -> const float* {
+            if (l < Hb) { const int slot = slot_of[l]; return slot >= 0 ? zs + (size_t)slot * ldz : grow_of(l); }
+            return p.layer0 ? zs + (size_t)p.stage_cap * ldz : grow_of(l);
+        };
+        const int i_edge = min(lane / H, 2), h_att = lane - (lane / H) * H;
+        for (int j = 0; j < n_mine; ++j) {
+            // groups committed so far: kEdgeRing + 1 + j; row j is complete once at most kEdgeRing - 1 are pending
+            if (j > 0) { agg_cp_async_wait<kEdgeRing - 1>(); __syncwarp(); }
+            const int jj = warp + kAggWarps * j;
+            const int v = v_begin + jj;
+            const int l0 = idx[3 * jj], l1 = idx[3 * jj + 1], l2 = idx[3 * jj + 2];
+            if (l0 >= 0) {
+                const float* r0 = head_row(l0);
+                const float* r1 = head_row(l1);
+                const float* r2 = p.layer0 ? head_row(l2) : ring + (size_t)(j % kEdgeRing) * ldz;
+                const float a1 = (i_edge == 0 ? r0 : (i_edge == 1 ? r1 : r2))[HD + h_att];
+                const float a2 = (l2 == v) ? r2[HD + H + h_att] : head_row(v)[HD + H + h_att];    // the destination's own row
+                const float e_l = lane < 3 * H ? leaky(a1 + a2, p.alpha) : 0.f;
+                const float e0 = __shfl_sync(0xffffffffu, e_l, h_att), e1 = __shfl_sync(0xffffffffu, e_l, H + h_att),
+                            e2 = __shfl_sync(0xffffffffu, e_l, 2 * H + h_att);
+                const float m = fmaxf(fmaxf(e0, e1), e2);
+                const float x0 = soft_exp(e0 - m), x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m);
+                const float den = (x0 + x1) + x2;
+                const float wgt = soft_div(i_edge == 0 ? x0 : (i_edge == 1 ? x1 : x2), den);
+                float acc[KMAX][VEC];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const int cv = lane + 32 * k;
+                    float a[3];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) a[e] = __shfl_sync(0xffffffffu, wgt, e * H + head_of[k]);
+                    float f0[VEC], f1[VEC], f2[VEC];
+                    if (cv < n_vec) { load_vec<VEC>(r0 + cv * VEC, f0); load_vec<VEC>(r1 + cv * VEC, f1); load_vec<VEC>(r2 + cv * VEC, f2); }
+                    else {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) f0[q] = f1[q] = f2[q] = 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        float t = fmaf(a[0], f0[q], 0.f);
+                        t = fmaf(a[1], f1[q], t);
+                        acc[k][q] = fmaf(a[2], f2[q], t);
+                    }
+                }
+                store_row<VEC, KMAX>(p, n0 + v, lane, n_vec, HD, acc);
+            }
+            __syncwarp();                                                     // the slot is free: next row into it
+            fetch(j + kEdgeRing);
+        }
+        agg_cp_async_wait<0>();
+        return;
+    }
+
+    // ---------------- head destinations ----------------
+    if (p.dbg & 32) return;
+    const int hh = warp / kWarpsPerHead, part_w = warp - hh * kWarpsPerHead;
+    const int v = (u - p.edge_units) * kLargeHeads + hh;
+    float* ring = smem_l + plan.ring + (size_t)warp * kHeadRing * ldz;
+    float* part = smem_l + plan.part;
+    float* pm = smem_l + plan.pm;
+    float* pd = smem_l + plan.pd;
+    float m_run[KMAX], d_run[KMAX], acc[KMAX][VEC];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        m_run[k] = -INFINITY; d_run[k] = 0.f;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[k][q] = 0.f;
+    }
+    const float* zsh = smem_l + plan.shared;
+    if (p.layer0) {       // 145 of a head's 146 in-edges are this one row: one copy per CTA instead of one per in-edge
+        for (int c = tid; c < ldz / 4; c += kAggWarps * 32)
+            agg_cp_async16(agg_smem_u32(zsh + 4 * c), p.z + (size_t)p.n_heads_total * ldz + 4 * c);
+        agg_cp_async_commit();
+        agg_cp_async_wait<0>();
+        __syncthreads();
+    }
+    if (v < Hb) {
+        const int gv = n0 + v;
+        const int beg = p.row_ptr[gv];
+        const int deg = p.row_ptr[gv + 1] - beg;
+        const int seg = (deg + kWarpsPerHead - 1) / kWarpsPerHead;
+        const int i_beg = part_w * seg, i_end = min(deg, i_beg + seg);
+        const int n_rows = max(0, i_end - i_beg);
+        float a2v[KMAX];
+        {
+            const float* rowv = grow_of(v);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) a2v[k] = rowv[HD + H + head_of[k]];
+        }
+        // the sources of my in-edges, 96 at a time in three registers: no index load sits in front of a row copy
+        int c_idx[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) c_idx[c] = (32 * c + lane < n_rows) ? __ldg(p.col + beg + i_beg + 32 * c + lane) : 0;
+        auto fetch = [&](int i) {                                            // in-edge i_beg + i -> ring slot i % kHeadRing
+            if (i < n_rows) {
+                const int g = i < 32 ? __shfl_sync(0xffffffffu, c_idx[0], i) : i < 64 ? __shfl_sync(0xffffffffu, c_idx[1], i - 32)
+                            : i < 96 ? __shfl_sync(0xffffffffu, c_idx[2], i - 64) : __ldg(p.col + beg + i_beg + i);
+                const int l = g - n0;
+                if (!(p.layer0 && l >= Hb)) agg_row_async(ring + (size_t)(i % kHeadRing) * ldz, grow_of(l), ldz, lane);
+            }
+            agg_cp_async_commit();
+        };
+        auto src_local = [&](int i) -> int {
+            const int g = i < 32 ? __shfl_sync(0xffffffffu, c_idx[0], i) : i < 64 ? __shfl_sync(0xffffffffu, c_idx[1], i - 32)
+                        : i < 96 ? __shfl_sync(0xffffffffu, c_idx[2], i - 64) : __ldg(p.col + beg + i_beg + i);
+            return g - n0;
+        };
+#pragma unroll
+        for (int i = 0; i < kHeadRing; ++i) fetch(i);
+        for (int i = 0; i < n_rows; ++i) {
+            agg_cp_async_wait<kHeadRing - 1>();
+            __syncwarp();
+            const float* r = (p.layer0 && src_local(i) >= Hb) ? zsh : ring + (size_t)(i % kHeadRing) * ldz;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const int cv = lane + 32 * k;
+                if (cv < n_vec) {
+                    const float e = leaky(r[HD + head_of[k]] + a2v[k], p.alpha);     // gat2.py:78-81
+                    const float m_new = fmaxf(m_run[k], e);
+                    const float sc = soft_exp(m_run[k] - m_new), w = soft_exp(e - m_new);
+                    float f[VEC];
+                    load_vec<VEC>(r + cv * VEC, f);
+                    d_run[k] = fmaf(d_run[k], sc, w);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(acc[k][q], sc, w * f[q]);
+                    m_run[k] = m_new;
+                }
+            }
+            __syncwarp();
+            fetch(i + kHeadRing);
+        }
+        agg_cp_async_wait<0>();
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int cv = lane + 32 * k;
+        if (cv < n_vec) {
+            pm[warp * n_vec + cv] = m_run[k];
+            pd[warp * n_vec + cv] = d_run[k];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) part[(size_t)warp * HD + cv * VEC + q] = acc[k][q];
+        }
+    }
+    __syncthreads();
+    // merge the partial triples of a head's warps in warp order; outputs (gat2.py:66, :141-142)
+    for (int t = tid; t < kLargeHeads * HD; t += kAggWarps * 32) {
+        const int hq = t / HD, c = t - hq * HD, cv = c / VEC;
+        const int vq = (u - p.edge_units) * kLargeHeads + hq;
+        if (vq >= Hb) break;
+        const int w0 = hq * kWarpsPerHead;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerHead; ++w) M = fmaxf(M, pm[(w0 + w) * n_vec + cv]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerHead; ++w) {
+            const float sc = soft_exp(pm[(w0 + w) * n_vec + cv] - M);
+            num = fmaf(part[(size_t)(w0 + w) * HD + c], sc, num);
+            den = fmaf(pd[(w0 + w) * n_vec + cv], sc, den);
+        }
+        const float val = soft_div(num, den);
+        const int gq = n0 + vq;
+        if (p.raw_f32) p.raw_f32[(size_t)gq * HD + c] = val;
+        if (p.act_hi) {
+            __nv_bfloat16 hb, lb;
+            split_bf16(leaky(val, p.act_slope), hb, lb);
+            p.act_hi[(size_t)gq * p.ld_planes + c] = hb;
+            p.act_lo[(size_t)gq * p.ld_planes + c] = lb;
+        }
+    }
+    if (p.act_hi) {
+        const int pad = p.ld_planes - HD;
+        for (int t = tid; t < kLargeHeads * pad; t += kAggWarps * 32) {
+            const int hq = t / pad, c = HD + t - hq * pad;
+            const int vq = (u - p.edge_units) * kLargeHeads + hq;
+            if (vq >= Hb) break;
+            p.act_hi[(size_t)(n0 + vq) * p.ld_planes + c] = __float2bfloat16_rn(0.f);
+            p.act_lo[(size_t)(n0 + vq) * p.ld_planes + c] = __float2bfloat16_rn(0.f);
+        }
+    }
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -650,6 +1038,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
     p.ld_planes = ld_planes;
     p.dbg = g_debug_flags;
+    p.stage_cap = 0; p.edge_units = 0; p.head_units = 0;
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
     // ---- frame-resident kernel: one CTA per frame, whenever the frame plan fits in shared memory ----
     if (impl == 0 && max_heads_per_frame > 0 && max_enodes_per_frame > 0 && max_heads_per_frame <= kFrameOwn * kFrameWarps &&
@@ -674,6 +1063,27 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
+    // ---- large frames: fused edge-chunk + head units, every z row read from HBM once ----
+    if (impl == 0 && mh > 48 && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4) {
+        p.stage_cap = kLargeStageCap;
+        p.edge_units = ceil_div(max_enodes_per_frame, kLargeChunk);
+        p.head_units = ceil_div(mh, kLargeHeads);
+        const size_t smem_l = (size_t)large_plan(mh, HD, ldz, vec).total_floats * sizeof(float);
+        const long long n_cta = (long long)n_frames * (p.edge_units + p.head_units);
+        if (smem_l <= 113 * 1024 && n_cta < 2147483647LL) {                  // two CTAs per SM
+            auto launch_large = [&](auto kern) -> int {
+                B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+                B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                kern<<<(unsigned)n_cta, kAggWarps * 32, smem_l, st>>>(p, mh);
+                B2_CHECK_LAUNCH();
+                return B200POSE_OK;
+            };
+            const int n_vec_l = HD / vec;
+            if (vec == 4) return n_vec_l <= 64 ? launch_large(gat_aggregate_large_kernel<4, 2>) : launch_large(gat_aggregate_large_kernel<4, 4>);
+            if (vec == 2) return n_vec_l <= 64 ? launch_large(gat_aggregate_large_kernel<2, 2>) : launch_large(gat_aggregate_large_kernel<2, 4>);
+            return launch_large(gat_aggregate_large_kernel<1, 4>);
+        }
+    }
     // shared memory: the frame's head rows (+1 shared edge-node row for layer 0), capped at 96 KB, plus
     // one [max_deg][heads] attention scratch per warp
     const size_t row_bytes = (size_t)ldz * sizeof(float);

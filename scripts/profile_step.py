@@ -7,8 +7,10 @@ from bench import load_workload, load_weights
 pm = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
 pack = importlib.import_module('3d_multi_pose_estimator_b200.pack')
 frames_n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-cfg, frames = load_workload('panoptic', frames_n, 4, 0)
-gat, mlp = load_weights('panoptic', cfg)
+config = sys.argv[2] if len(sys.argv) > 2 else 'panoptic'
+persons = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+cfg, frames = load_workload(config, frames_n, persons, 0)
+gat, mlp = load_weights(config, cfg)
 pb = pack.pack_frames(frames, cfg, keep_json=False)
 pipe = pm.PosePipeline(cfg, gat, mlp, device='cuda:0')
 db = pm.HostBatch(pb).to_device('cuda:0')
