@@ -84,19 +84,22 @@ struct ClusterParams {
     int v_sm; double threshold; int min_views;
     int* person_heads; int* n_persons;
     int max_heads, max_keys, table_cap;
+    int dbg;        // b200pose_set_debug bit 128: frame 0 prints the clock of each phase
 };
 
-// blockDim = 32 (frames of a few hundred edge-nodes: everything is warp-synchronous) or 256 (large frames: the sort
+// blockDim = 32 (frames of a few hundred edge-nodes: everything is warp-synchronous) or 256 / 1024 (large frames: the sort
 // and the table passes use the whole CTA; the order-dependent parts still run on one lane).
-__global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) cluster_kernel(ClusterParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int n_seen_s;
+    __shared__ int n_seen_s, n_valid_s, n_links_s;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31;
     const bool one_warp = nt == 32;
     auto bsync = [&]() { if (one_warp) __syncwarp(); else __syncthreads(); };
     const int b = blockIdx.x;
+    const long long t_start = (p.dbg & 128) ? clock64() : 0;
     const int h0 = p.head_off[b];
     const int H = p.head_off[b + 1] - h0;
     const int n0 = p.node_off[b];
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     // Small frames (one warp, <= 512 edge-nodes): the keys above the threshold are compacted with a ballot prefix and
     // rank-sorted - every lane counts, for each of its keys, how many keys are greater (broadcast reads, no dependent
     // chain) - instead of 36 dependent passes of a padded bitonic network, which took half of this kernel.
-    const bool rank_sort = one_warp && p.max_keys <= 512;
+    const bool rank_sort = MAXT <= 256 && one_warp && p.max_keys <= 512;
     int n_valid = 0;
     if (rank_sort) {
         for (int k0 = 0; k0 < M; k0 += 32) {
@@ -150,15 +153,22 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
         }
         __syncwarp();
     } else {
-        for (int k = tid; k < Mpad; k += nt) {
-            unsigned long long key = 0ull;
-            if (k < M) {
-                const float s = p.scores[n0 + H + k];
-                if ((double)s > p.threshold)
-                    key = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
-            }
-            keys[k] = key;
+        // Large frames: only the matchings above the threshold are kept (a 10-view x 16-person frame has 11520
+        // edge-nodes and ~720 matchings), in any order - the keys are unique and the sort below orders them - so the
+        // bitonic network runs over the next power of two of the survivors instead of over every edge-node.
+        if (tid == 0) n_valid_s = 0;
+        __syncthreads();
+        for (int k = tid; k < M; k += nt) {
+            const float s = p.scores[n0 + H + k];
+            if ((double)s > p.threshold)
+                keys[atomicAdd(&n_valid_s, 1)] = ((unsigned long long)ordered_bits(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)k);
         }
+        __syncthreads();
+        n_valid = n_valid_s;
+        Mpad = 2;
+        while (Mpad < n_valid) Mpad <<= 1;
+        if (Mpad > p.max_keys) Mpad = p.max_keys;
+        for (int k = n_valid + tid; k < Mpad; k += nt) keys[k] = 0ull;
     }
     bsync();
     // ---- first-seen order of the heads in the reference's edge walk (:32-47), in closed form. Edge-nodes are ordered
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     bsync();
     const int n_seen = n_seen_s;
 
-    if (rank_sort) {
+    if constexpr (MAXT <= 256) if (rank_sort) {
         // ---- rank sort, descending (keys are unique: the edge-node index is part of the key) ----
         unsigned long long mine[16];
         int rank[16];
@@ -209,7 +219,8 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
             if (lane + 32 * r < n_valid) keys[rank[r]] = mine[r];
         if (lane == 0 && n_valid < p.max_keys) keys[n_valid] = 0ull;     // terminates the merge walk
         __syncwarp();
-    } else {
+    }
+    if (!rank_sort) {
     // ---- bitonic sort, descending: score desc, edge-node index asc (:60) ----
     for (int size = 2; size <= Mpad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -237,73 +248,145 @@ __global__ void __launch_bounds__(256) cluster_kernel(ClusterParams p)
     }
     bsync();
 
-    // ---- greedy merge (:61-108): inherently sequential in score order, so one lane walks the sorted matchings
-    // (no synchronisation per matching); the state it touches is a few hundred bytes of shared memory ----
+    // ---- greedy merge (:61-108): inherently sequential in score order. Warp 0 takes the sorted matchings 32 at a
+    // time: every lane runs the three rejection tests (:67, :70-75) on its matching against the state as it stands,
+    // and lane 0 then walks the survivors in order with the full set of tests. A rejected matching changes nothing,
+    // and between two group absorptions the state only grows (linked-camera masks and group camera masks gain bits, a
+    // head's group never changes once set), so a matching rejected now is rejected at its turn too. An absorption
+    // (:90-104) forgets the absorbed group's cameras, which can revive a matching: the rest of the batch is then
+    // tested again. A 10-view x 16-person frame has ~8000 matchings above the threshold and ~140 links; the walk used
+    // to be one lane over all of them. ----
+    long long t_merge0 = 0;
+    if (p.dbg & 128) t_merge0 = clock64();
     int n_links = 0;
-    if (tid == 0) {
+    if (tid < 32) {
         int cur = 0;
-        const int n_match = rank_sort ? n_valid : M;
-        for (int t = 0; t < n_match; ++t) {
-            const unsigned long long key = keys[t];
-            if (key == 0ull) break;
-            const int h1 = (int)((key >> 31) & 0x7FFFFFFFull), h2 = (int)(key & 0x7FFFFFFFull);
-            int a, c;
-            pair_order(h1, h2, a, c);
-            const unsigned ca = 1u << cam[a], cc = 1u << cam[c];
-            if ((ca & linked[c]) || (cc & linked[a])) continue;                      // :67
-            const int ga = group[a], gc = group[c];
-            if (ga >= 0 && (cc & cams_for[ga])) continue;                            // :70-72
-            if (gc >= 0 && (ca & cams_for[gc])) continue;                            // :73-75
-            if (ga < 0 && gc < 0) {                                                  // :77-83
-                group[a] = cur; group[c] = cur; cams_for[cur] = ca | cc;
-                ++cur;
-            } else if (ga >= 0 && gc < 0) {                                          // :84-86
-                group[c] = ga; cams_for[ga] |= cc;
-            } else if (gc >= 0 && ga < 0) {                                          // :87-89
-                group[a] = gc; cams_for[gc] |= ca;
-            } else {                                                                 // :90-104
-                if (cams_for[gc] & cams_for[ga]) continue;
-                for (int h = 0; h < H; ++h)
-                    if (group[h] == gc) group[h] = ga;                               // absorbed cameras are forgotten
+        bool done = false;
+        for (int t0 = 0; t0 < n_valid && !done; t0 += 32) {
+            const int t = t0 + lane;
+            const unsigned long long key = t < n_valid ? keys[t] : 0ull;
+            int a = 0, c = 0;
+            unsigned ca = 0, cc = 0;
+            if (key != 0ull) {
+                const int h1 = (int)((key >> 31) & 0x7FFFFFFFull), h2 = (int)(key & 0x7FFFFFFFull);
+                pair_order(h1, h2, a, c);
+                ca = 1u << cam[a]; cc = 1u << cam[c];
             }
-            link_a[2 * n_links] = a; link_a[2 * n_links + 1] = c;                    // :106-108
-            linked[a] |= cc; linked[c] |= ca;
-            ++n_links;
+            done = __any_sync(0xffffffffu, t < n_valid && key == 0ull);       // the zero key ends the walk
+            unsigned pending = __ballot_sync(0xffffffffu, key != 0ull);
+            while (pending) {
+                bool alive = false;
+                if ((pending >> lane) & 1u) {
+                    alive = !((ca & linked[c]) || (cc & linked[a]));                            // :67
+                    if (alive) {
+                        const int ga = group[a], gc = group[c];
+                        if (ga >= 0 && (cc & cams_for[ga])) alive = false;                      // :70-72
+                        else if (gc >= 0 && (ca & cams_for[gc])) alive = false;                 // :73-75
+                        else if (ga >= 0 && gc >= 0 && (cams_for[gc] & cams_for[ga])) alive = false;   // :91
+                    }
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, alive);
+                pending = 0u;
+                while (bal) {
+                    const int src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const int xa = __shfl_sync(0xffffffffu, a, src), xc = __shfl_sync(0xffffffffu, c, src);
+                    const unsigned xca = __shfl_sync(0xffffffffu, ca, src), xcc = __shfl_sync(0xffffffffu, cc, src);
+                    int absorbed = 0;
+                    if (lane == 0) {
+                        do {
+                            if ((xca & linked[xc]) || (xcc & linked[xa])) break;                  // :67
+                            const int ga = group[xa], gc = group[xc];
+                            if (ga >= 0 && (xcc & cams_for[ga])) break;                         // :70-72
+                            if (gc >= 0 && (xca & cams_for[gc])) break;                         // :73-75
+                            if (ga < 0 && gc < 0) {                                             // :77-83
+                                group[xa] = cur; group[xc] = cur; cams_for[cur] = xca | xcc;
+                                ++cur;
+                            } else if (ga >= 0 && gc < 0) {                                     // :84-86
+                                group[xc] = ga; cams_for[ga] |= xcc;
+                            } else if (gc >= 0 && ga < 0) {                                     // :87-89
+                                group[xa] = gc; cams_for[gc] |= xca;
+                            } else {                                                            // :90-104
+                                if (cams_for[gc] & cams_for[ga]) break;
+                                for (int h = 0; h < H; ++h)
+                                    if (group[h] == gc) group[h] = ga;                          // absorbed cameras are forgotten
+                                absorbed = 1;
+                            }
+                            link_a[2 * n_links] = xa; link_a[2 * n_links + 1] = xc;             // :106-108
+                            linked[xa] |= xcc; linked[xc] |= xca;
+                            ++n_links;
+                        } while (false);
+                    }
+                    absorbed = __shfl_sync(0xffffffffu, absorbed, 0);
+                    if (absorbed) {                                           // every matching after this one: test again
+                        pending = __ballot_sync(0xffffffffu, key != 0ull) & (src == 31 ? 0u : ~((2u << src) - 1u));
+                        break;
+                    }
+                }
+                __syncwarp();                                                 // lane 0's state before the next tests
+            }
         }
     }
     bsync();
+    const long long t_merged = (p.dbg & 128) ? clock64() : 0;
 
     // ---- connected components in first-seen order, BFS by levels (:117-130) ----
     for (int h = tid; h < H; h += nt) flag[h] = 0;                               // reuse as "done"
     bsync();
-    int n_out = 0;
-    if (tid == 0) {
+    if (tid == 0) n_links_s = n_links;
+    bsync();
+    // Warp 0 walks the components: the order-dependent steps (queue, set insertions) stay on lane 0, the scan of the
+    // link list for the links of the head being expanded is spread over the lanes - 32 links per step, matches
+    // taken in link order - which is what made a 160-head frame spend 2 ms here on one lane.
+    if (tid < 32) {
+        const int n_lk = n_links_s;
+        int n_out = 0;
         IntSet comp;
         for (int f = 0; f < n_seen; ++f) {
             const int v = first_seen[f];
-            if (flag[v]) continue;
-            comp.init(tab_a, tab_b);
-            comp.add(v);
-            flag[v] = 1;
-            int qb = 0, qe = 0, size = 1;
-            queue[qe++] = v;
+            if (flag[v]) continue;                                           // uniform: every lane reads the same word
+            if (lane == 0) {
+                comp.init(tab_a, tab_b);
+                comp.add(v);
+                flag[v] = 1;
+                queue[0] = v;
+            }
+            __syncwarp();
+            int qb = 0, qe = 1, size = 1;
             while (qb < qe) {
                 const int x = queue[qb++];
-                for (int i = 0; i < n_links; ++i) {
+                for (int i0 = 0; i0 < n_lk; i0 += 32) {
+                    const int i = i0 + lane;
                     int w = -1;
-                    if (link_a[2 * i] == x) w = link_a[2 * i + 1];
-                    else if (link_a[2 * i + 1] == x) w = link_a[2 * i];
-                    if (w >= 0 && !flag[w]) { flag[w] = 1; comp.add(w); queue[qe++] = w; ++size; }
+                    if (i < n_lk) {
+                        const int la = link_a[2 * i], lc = link_a[2 * i + 1];
+                        if (la == x) w = lc; else if (lc == x) w = la;
+                        if (w >= 0 && flag[w]) w = -1;
+                    }
+                    unsigned bal = __ballot_sync(0xffffffffu, w >= 0);
+                    while (bal) {                                            // a head is linked to x at most once
+                        const int src = __ffs(bal) - 1;
+                        bal &= bal - 1;
+                        const int wv = __shfl_sync(0xffffffffu, w, src);
+                        if (lane == 0) { flag[wv] = 1; comp.add(wv); queue[qe] = wv; }
+                        ++qe; ++size;
+                    }
                 }
+                __syncwarp();
             }
             if (size < p.min_views) continue;
-            int* person = p.person_heads + (size_t)(h0 + n_out) * p.v_sm;
-            for (int s = 0; s < p.v_sm; ++s) person[s] = -1;
-            for (int i = 0; i <= comp.mask; ++i)
-                if (comp.tab[i] >= 0) person[cam[comp.tab[i]]] = comp.tab[i];
+            if (lane == 0) {
+                int* person = p.person_heads + (size_t)(h0 + n_out) * p.v_sm;
+                for (int s = 0; s < p.v_sm; ++s) person[s] = -1;
+                for (int i = 0; i <= comp.mask; ++i)
+                    if (comp.tab[i] >= 0) person[cam[comp.tab[i]]] = comp.tab[i];
+            }
             ++n_out;
         }
-        p.n_persons[b] = n_out;
+        if (lane == 0) p.n_persons[b] = n_out;
+        if ((p.dbg & 128) && b == 0 && lane == 0)
+            printf("cluster frame 0: H %d M %d matchings %d links %d | clocks: threshold+sort %lld, merge %lld, components %lld\n", H, M, n_valid,
+                   n_lk, t_merge0 - t_start, t_merged - t_merge0, clock64() - t_merged);
     }
 }
 
@@ -381,6 +464,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
     ClusterParams p;
     p.head_off = head_off; p.node_off = node_off; p.pairs = pairs; p.node_cam = node_cam; p.scores = scores;
     p.v_sm = v_sm; p.threshold = threshold; p.min_views = min_views; p.person_heads = person_heads; p.n_persons = n_persons;
+    p.dbg = g_debug_flags;
     p.max_heads = max_heads_per_frame < 1 ? 1 : max_heads_per_frame;
     int keys = 1;
     while (keys < max_enodes_per_frame) keys <<= 1;
@@ -392,8 +476,13 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
                   max_heads_per_frame, max_enodes_per_frame);
         return B200POSE_E_UNSUPPORTED;
     }
-    B2_CHECK_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cluster_kernel<<<n_frames, p.max_keys > 1024 ? 256 : 32, smem, (cudaStream_t)stream>>>(p);
+    if (p.max_keys > 4096) {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(cluster_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cluster_kernel<1024><<<n_frames, 1024, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        B2_CHECK_CUDA(cudaFuncSetAttribute(cluster_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cluster_kernel<256><<<n_frames, p.max_keys > 1024 ? 256 : 32, smem, (cudaStream_t)stream>>>(p);
+    }
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

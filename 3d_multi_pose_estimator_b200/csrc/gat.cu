@@ -677,84 +677,116 @@ constexpr int kLargeStageCap = 32;     // staged head rows per edge unit
 constexpr int kEdgeRing = 4;           // rows in flight per warp, edge units
 constexpr int kHeadRing = 6;           // rows in flight per warp, head units
 constexpr int kWarpsPerHead = kAggWarps / kLargeHeads;
+constexpr int kRowIters = 5;           // 16-byte copies per lane and row: ldz <= 640
+constexpr float kRescaleAt = 30.f;     // head units: the running softmax reference moves when a logit exceeds it by this much
 static_assert(kLargeChunk / kAggWarps * 3 <= 32, "edge units: one lane per (destination, in-edge)");
 static_assert(kLargeChunk / kAggWarps >= kEdgeRing, "edge ring deeper than a warp's destinations");
 
 template <int N> __device__ __forceinline__ void agg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void agg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// one z row (ldz floats, 16 B aligned) by the 32 lanes of a warp
-__device__ __forceinline__ void agg_row_async(float* dst, const float* src, int ldz, int lane) {
-    for (int c = lane; c < ldz / 4; c += 32) agg_cp_async16(agg_smem_u32(dst + 4 * c), src + 4 * c);
+// one z row (ldz4 16-byte pieces) by the 32 lanes of a warp: constant strides, so the addresses fold into immediates
+__device__ __forceinline__ void agg_row_async(uint32_t dst_lane, const float* src_lane, int ldz4, int lane) {
+#pragma unroll
+    for (int it = 0; it < kRowIters; ++it)
+        if (lane + 32 * it < ldz4) agg_cp_async16(dst_lane + 512 * it, src_lane + 128 * it);
 }
+template <int VEC> __device__ __forceinline__ void lds_vec(uint32_t addr, float (&v)[VEC]) {
+    if constexpr (VEC == 4) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+    else if constexpr (VEC == 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 
-struct LargePlan { int stage, slots, idx, ring, part, pm, pd, shared, total_floats; };
+struct LargePlan { int stage, slots, idx, ring, part, pm, pd, shared, hidx, total_floats; };
 __host__ __device__ inline LargePlan large_plan(int max_heads, int HD, int ldz, int vec) {
     LargePlan f;
-    int o = 0;
-    f.ring = o;                                    // edge: [kAggWarps][kEdgeRing][ldz]; head: [kAggWarps][kHeadRing][ldz]
+    f.ring = 0;                                    // edge: [kAggWarps][kEdgeRing][ldz]; head: [kAggWarps][kHeadRing][ldz]
     const int ring_rows = kAggWarps * (kHeadRing > kEdgeRing ? kHeadRing : kEdgeRing);
     // the head units have no staged rows: their deeper ring overlays the edge units' ring + stage area
-    f.stage = o + kAggWarps * kEdgeRing * ldz;     // [kLargeStageCap + 1][ldz]
+    f.stage = kAggWarps * kEdgeRing * ldz;         // [kLargeStageCap + 1][ldz]
     int edge_end = f.stage + (kLargeStageCap + 1) * ldz;
     f.slots = edge_end; edge_end += (max_heads + 1) / 2 + 1;          // short[max_heads]
     f.idx = edge_end; edge_end += 3 * kLargeChunk;                    // int[kLargeChunk][3]
-    int head_end = o + ring_rows * ldz;
+    int head_end = ring_rows * ldz;
     f.part = head_end; head_end += kAggWarps * HD;                    // [kAggWarps][HD]
     f.pm = head_end; head_end += kAggWarps * (HD / vec);              // [kAggWarps][n_vec]
     f.pd = head_end; head_end += kAggWarps * (HD / vec);
     f.shared = head_end; head_end += ldz;                             // layer 0: the row all edge-nodes share
+    f.hidx = head_end; head_end += kAggWarps * (max_heads / kWarpsPerHead + 2);   // sources of each warp's in-edges
     f.total_floats = (edge_end > head_end ? edge_end : head_end) + 4;
     return f;
 }
 
+// outputs of one destination row held as KMAX vectors per lane; `last` = this lane's last vector exists
 template <int VEC, int KMAX>
-__device__ __forceinline__ void store_row(const AggParams& p, int gv, int lane, int n_vec, int HD, const float (&acc)[KMAX][VEC])
+__device__ __forceinline__ void store_row(const AggParams& p, bool slope_le1, int gv, int lane, bool last, int HD, const float (&acc)[KMAX][VEC])
 {
+    if (p.raw_f32) {
+        float* o = p.raw_f32 + (size_t)gv * HD + lane * VEC;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-        const int cv = lane + 32 * k;
-        if (cv >= n_vec) continue;
-        if (p.raw_f32) {
-            float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) o[q] = acc[k][q];
-        }
-        if (p.act_hi) {
-            __nv_bfloat16 hi[VEC], lo[VEC];
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) split_bf16(leaky(acc[k][q], p.act_slope), hi[q], lo[q]);
-            __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + cv * VEC;
-            __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + cv * VEC;
-            if constexpr (VEC == 4) {
-                *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
-                *reinterpret_cast<uint2*>(ol) = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
-            } else if constexpr (VEC == 2) {
-                *reinterpret_cast<uint32_t*>(oh) = pack_bf16x2(hi[0], hi[1]);
-                *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(lo[0], lo[1]);
-            } else {
-                oh[0] = hi[0]; ol[0] = lo[0];
+        for (int k = 0; k < KMAX; ++k)
+            if (k < KMAX - 1 || last) {
+                if constexpr (VEC == 4) *reinterpret_cast<float4*>(o + 128 * k) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                else if constexpr (VEC == 2) *reinterpret_cast<float2*>(o + 64 * k) = make_float2(acc[k][0], acc[k][1]);
+                else o[32 * k] = acc[k][0];
             }
+    }
+    if (p.act_hi) {
+        __nv_bfloat16* oh = p.act_hi + (size_t)gv * p.ld_planes + lane * VEC;
+        __nv_bfloat16* ol = p.act_lo + (size_t)gv * p.ld_planes + lane * VEC;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < KMAX - 1 || last) {
+                float a[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) a[q] = slope_le1 ? leaky_le1(acc[k][q], p.act_slope) : leaky(acc[k][q], p.act_slope);
+                if constexpr (VEC == 4) {
+                    uint32_t h0, l0, h1, l1;
+                    split_pack2(a[0], a[1], h0, l0);
+                    split_pack2(a[2], a[3], h1, l1);
+                    *reinterpret_cast<uint2*>(oh + 128 * k) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(ol + 128 * k) = make_uint2(l0, l1);
+                } else if constexpr (VEC == 2) {
+                    uint32_t h0, l0;
+                    split_pack2(a[0], a[1], h0, l0);
+                    *reinterpret_cast<uint32_t*>(oh + 64 * k) = h0;
+                    *reinterpret_cast<uint32_t*>(ol + 64 * k) = l0;
+                } else {
+                    __nv_bfloat16 h, l;
+                    split_bf16(a[0], h, l);
+                    oh[32 * k] = h; ol[32 * k] = l;
+                }
+            }
+        // K padding of the planes stays zero (HD and ld_planes even unless VEC == 1)
+        const int pad = p.ld_planes - HD;
+        __nv_bfloat16* zh = p.act_hi + (size_t)gv * p.ld_planes + HD;
+        __nv_bfloat16* zl = p.act_lo + (size_t)gv * p.ld_planes + HD;
+        if constexpr (VEC == 1) {
+            for (int c = lane; c < pad; c += 32) { zh[c] = __float2bfloat16_rn(0.f); zl[c] = __float2bfloat16_rn(0.f); }
+        } else {
+            for (int c = lane; 2 * c < pad; c += 32) { reinterpret_cast<uint32_t*>(zh)[c] = 0u; reinterpret_cast<uint32_t*>(zl)[c] = 0u; }
         }
     }
-    if (p.act_hi)                                               // K padding of the planes stays zero
-        for (int c = HD + lane; c < p.ld_planes; c += 32) {
-            p.act_hi[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
-            p.act_lo[(size_t)gv * p.ld_planes + c] = __float2bfloat16_rn(0.f);
-        }
 }
 
 template <int VEC, int KMAX>
 __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(AggParams p, int max_heads)
 {
     extern __shared__ __align__(16) float smem_l[];
+    __shared__ int s_all_staged;
     const int units = p.edge_units + p.head_units;
     const int b = blockIdx.x / units, u = blockIdx.x - b * units;
     const int n0 = p.node_off[b], Nb = p.node_off[b + 1] - n0;
     const int h0 = p.head_off[b], Hb = p.head_off[b + 1] - h0;
-    const int H = p.heads, D = p.dim, HD = H * D, ldz = p.ldz;
+    const int H = p.heads, D = p.dim, HD = H * D, ldz = p.ldz, ldz4 = ldz >> 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_vec = HD / VEC;
+    const bool last = lane + 32 * (KMAX - 1) < n_vec;          // 32 * (KMAX - 1) < n_vec <= 32 * KMAX (host)
+    const bool slope_le1 = p.act_slope >= 0.f && p.act_slope <= 1.f;
+    const bool alpha_le1 = p.alpha >= 0.f && p.alpha <= 1.f;
+    auto lrelu = [&](float x) { return alpha_le1 ? leaky_le1(x, p.alpha) : leaky(x, p.alpha); };
     const LargePlan plan = large_plan(max_heads, HD, ldz, VEC);
+    const uint32_t smem_base = agg_smem_u32(smem_l);
     int head_of[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) head_of[k] = min(H - 1, ((lane + 32 * k) * VEC) / D);
@@ -769,7 +801,8 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
         if (v_begin >= Nb || (p.dbg & 64)) return;
         const int v_end = min(Nb, v_begin + kLargeChunk);
         float* zs = smem_l + plan.stage;
-        float* ring = smem_l + plan.ring + (size_t)warp * kEdgeRing * ldz;
+        const uint32_t zs_u32 = smem_base + 4u * plan.stage;
+        const uint32_t ring_u32 = smem_base + 4u * (plan.ring + warp * kEdgeRing * ldz);
         short* slot_of = reinterpret_cast<short*>(smem_l + plan.slots);
         int* idx = reinterpret_cast<int*>(smem_l + plan.idx);                 // [kLargeChunk][3] local in-edge sources, -1 = skip
         // in-edges of the chunk: thread t < 3 * kLargeChunk takes in-edge t % 3 of destination t / 3
@@ -793,7 +826,7 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
         auto fetch = [&](int j) {                                            // row of in-edge 2 of my destination j -> ring slot j % kEdgeRing
             if (j < n_mine && !p.layer0) {
                 const int l2 = idx[3 * (warp + kAggWarps * j) + 2];
-                if (l2 >= 0) agg_row_async(ring + (size_t)(j % kEdgeRing) * ldz, grow_of(l2), ldz, lane);
+                if (l2 >= 0) agg_row_async(ring_u32 + 4u * ((j % kEdgeRing) * ldz) + 16u * lane, grow_of(l2) + 4 * lane, ldz4, lane);
             }
             agg_cp_async_commit();
         };
@@ -809,22 +842,25 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
                 if (l < Hb) slot_of[l] = (need && slot < p.stage_cap) ? (short)slot : (short)-1;
                 base += __popc(m);
             }
+            if (lane == 0) s_all_staged = base <= p.stage_cap;
         }
         __syncthreads();
         for (int l = warp; l < Hb; l += kAggWarps) {
             const int slot = slot_of[l];
-            if (slot >= 0) agg_row_async(zs + (size_t)slot * ldz, grow_of(l), ldz, lane);
+            if (slot >= 0) agg_row_async(zs_u32 + 4u * (slot * ldz) + 16u * lane, grow_of(l) + 4 * lane, ldz4, lane);
         }
         if (p.layer0 && warp == kAggWarps - 1)                                // the row all edge-nodes share in layer 0
-            agg_row_async(zs + (size_t)p.stage_cap * ldz, p.z + (size_t)p.n_heads_total * ldz, ldz, lane);
+            agg_row_async(zs_u32 + 4u * (p.stage_cap * ldz) + 16u * lane, p.z + (size_t)p.n_heads_total * ldz + 4 * lane, ldz4, lane);
         agg_cp_async_commit();
         agg_cp_async_wait<0>();
         __syncthreads();
-        auto head_row = [&](int l) -> const float* {
+        const bool all_staged = s_all_staged != 0;
+        auto head_row = [&](int l) -> const float* {                          // general path: staged or global
             if (l < Hb) { const int slot = slot_of[l]; return slot >= 0 ? zs + (size_t)slot * ldz : grow_of(l); }
             return p.layer0 ? zs + (size_t)p.stage_cap * ldz : grow_of(l);
         };
         const int i_edge = min(lane / H, 2), h_att = lane - (lane / H) * H;
+        const uint32_t col_b = 4u * VEC * lane;                               // byte offset of this lane's first vector in a row
         for (int j = 0; j < n_mine; ++j) {
             // groups committed so far: kEdgeRing + 1 + j; row j is complete once at most kEdgeRing - 1 are pending
             if (j > 0) { agg_cp_async_wait<kEdgeRing - 1>(); __syncwarp(); }
@@ -832,39 +868,70 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
             const int v = v_begin + jj;
             const int l0 = idx[3 * jj], l1 = idx[3 * jj + 1], l2 = idx[3 * jj + 2];
             if (l0 >= 0) {
-                const float* r0 = head_row(l0);
-                const float* r1 = head_row(l1);
-                const float* r2 = p.layer0 ? head_row(l2) : ring + (size_t)(j % kEdgeRing) * ldz;
-                const float a1 = (i_edge == 0 ? r0 : (i_edge == 1 ? r1 : r2))[HD + h_att];
-                const float a2 = (l2 == v) ? r2[HD + H + h_att] : head_row(v)[HD + H + h_att];    // the destination's own row
-                const float e_l = lane < 3 * H ? leaky(a1 + a2, p.alpha) : 0.f;
-                const float e0 = __shfl_sync(0xffffffffu, e_l, h_att), e1 = __shfl_sync(0xffffffffu, e_l, H + h_att),
-                            e2 = __shfl_sync(0xffffffffu, e_l, 2 * H + h_att);
-                const float m = fmaxf(fmaxf(e0, e1), e2);
-                const float x0 = soft_exp(e0 - m), x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m);
-                const float den = (x0 + x1) + x2;
-                const float wgt = soft_div(i_edge == 0 ? x0 : (i_edge == 1 ? x1 : x2), den);
                 float acc[KMAX][VEC];
+                if (all_staged && l0 < Hb && l1 < Hb && (p.layer0 ? l2 >= Hb : l2 == v)) {
+                    // the usual case: both heads staged, the third in-edge is the self loop - shared memory only
+                    const uint32_t r0 = zs_u32 + 4u * (slot_of[l0] * ldz), r1 = zs_u32 + 4u * (slot_of[l1] * ldz);
+                    const uint32_t r2 = p.layer0 ? zs_u32 + 4u * (p.stage_cap * ldz) : ring_u32 + 4u * ((j % kEdgeRing) * ldz);
+                    const float a1 = lds_f32((i_edge == 0 ? r0 : (i_edge == 1 ? r1 : r2)) + 4u * (HD + h_att));
+                    const float a2 = lds_f32(r2 + 4u * (HD + H + h_att));
+                    const float e_l = lrelu(a1 + a2);
+                    const float e0 = __shfl_sync(0xffffffffu, e_l, h_att), e1 = __shfl_sync(0xffffffffu, e_l, H + h_att),
+                                e2 = __shfl_sync(0xffffffffu, e_l, 2 * H + h_att);
+                    const float m = fmaxf(fmaxf(e0, e1), e2);
+                    const float x0 = soft_exp(e0 - m), x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m);
+                    const float den = (x0 + x1) + x2;
+                    const float wgt = soft_div(i_edge == 0 ? x0 : (i_edge == 1 ? x1 : x2), den);
 #pragma unroll
-                for (int k = 0; k < KMAX; ++k) {
-                    const int cv = lane + 32 * k;
-                    float a[3];
+                    for (int k = 0; k < KMAX; ++k) {
+                        float a[3];
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) a[e] = __shfl_sync(0xffffffffu, wgt, e * H + head_of[k]);
-                    float f0[VEC], f1[VEC], f2[VEC];
-                    if (cv < n_vec) { load_vec<VEC>(r0 + cv * VEC, f0); load_vec<VEC>(r1 + cv * VEC, f1); load_vec<VEC>(r2 + cv * VEC, f2); }
-                    else {
+                        for (int e = 0; e < 3; ++e) a[e] = __shfl_sync(0xffffffffu, wgt, e * H + head_of[k]);
+                        if (k < KMAX - 1 || last) {
+                            float f0[VEC], f1[VEC], f2[VEC];
+                            lds_vec<VEC>(r0 + col_b + 128u * VEC * k, f0);
+                            lds_vec<VEC>(r1 + col_b + 128u * VEC * k, f1);
+                            lds_vec<VEC>(r2 + col_b + 128u * VEC * k, f2);
 #pragma unroll
-                        for (int q = 0; q < VEC; ++q) f0[q] = f1[q] = f2[q] = 0.f;
+                            for (int q = 0; q < VEC; ++q) {
+                                float t = fmaf(a[0], f0[q], 0.f);
+                                t = fmaf(a[1], f1[q], t);
+                                acc[k][q] = fmaf(a[2], f2[q], t);
+                            }
+                        }
                     }
+                } else {
+                    const float* r0 = head_row(l0);
+                    const float* r1 = head_row(l1);
+                    const float* r2 = p.layer0 ? head_row(l2) : smem_l + plan.ring + (size_t)(warp * kEdgeRing + j % kEdgeRing) * ldz;
+                    const float a1 = (i_edge == 0 ? r0 : (i_edge == 1 ? r1 : r2))[HD + h_att];
+                    const float a2 = (l2 == v) ? r2[HD + H + h_att] : head_row(v)[HD + H + h_att];    // the destination's own row
+                    const float e_l = lrelu(a1 + a2);
+                    const float e0 = __shfl_sync(0xffffffffu, e_l, h_att), e1 = __shfl_sync(0xffffffffu, e_l, H + h_att),
+                                e2 = __shfl_sync(0xffffffffu, e_l, 2 * H + h_att);
+                    const float m = fmaxf(fmaxf(e0, e1), e2);
+                    const float x0 = soft_exp(e0 - m), x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m);
+                    const float den = (x0 + x1) + x2;
+                    const float wgt = soft_div(i_edge == 0 ? x0 : (i_edge == 1 ? x1 : x2), den);
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) {
-                        float t = fmaf(a[0], f0[q], 0.f);
-                        t = fmaf(a[1], f1[q], t);
-                        acc[k][q] = fmaf(a[2], f2[q], t);
+                    for (int k = 0; k < KMAX; ++k) {
+                        const int cv = lane + 32 * k;
+                        float a[3];
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) a[e] = __shfl_sync(0xffffffffu, wgt, e * H + head_of[k]);
+                        if (k < KMAX - 1 || last) {
+                            float f0[VEC], f1[VEC], f2[VEC];
+                            load_vec<VEC>(r0 + cv * VEC, f0); load_vec<VEC>(r1 + cv * VEC, f1); load_vec<VEC>(r2 + cv * VEC, f2);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) {
+                                float t = fmaf(a[0], f0[q], 0.f);
+                                t = fmaf(a[1], f1[q], t);
+                                acc[k][q] = fmaf(a[2], f2[q], t);
+                            }
+                        }
                     }
                 }
-                store_row<VEC, KMAX>(p, n0 + v, lane, n_vec, HD, acc);
+                store_row<VEC, KMAX>(p, slope_le1, n0 + v, lane, last, HD, acc);
             }
             __syncwarp();                                                     // the slot is free: next row into it
             fetch(j + kEdgeRing);
@@ -877,77 +944,93 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
     if (p.dbg & 32) return;
     const int hh = warp / kWarpsPerHead, part_w = warp - hh * kWarpsPerHead;
     const int v = (u - p.edge_units) * kLargeHeads + hh;
-    float* ring = smem_l + plan.ring + (size_t)warp * kHeadRing * ldz;
+    const uint32_t ring_u32 = smem_base + 4u * (plan.ring + warp * kHeadRing * ldz);
+    const uint32_t zsh_u32 = smem_base + 4u * plan.shared;
     float* part = smem_l + plan.part;
     float* pm = smem_l + plan.pm;
     float* pd = smem_l + plan.pd;
+    const int hidx_cap = max_heads / kWarpsPerHead + 2;
+    int* hidx = reinterpret_cast<int*>(smem_l + plan.hidx) + warp * hidx_cap;
     float m_run[KMAX], d_run[KMAX], acc[KMAX][VEC];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-        m_run[k] = -INFINITY; d_run[k] = 0.f;
+        m_run[k] = 0.f; d_run[k] = 0.f;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) acc[k][q] = 0.f;
     }
-    const float* zsh = smem_l + plan.shared;
     if (p.layer0) {       // 145 of a head's 146 in-edges are this one row: one copy per CTA instead of one per in-edge
-        for (int c = tid; c < ldz / 4; c += kAggWarps * 32)
-            agg_cp_async16(agg_smem_u32(zsh + 4 * c), p.z + (size_t)p.n_heads_total * ldz + 4 * c);
+        for (int c = tid; c < ldz4; c += kAggWarps * 32)
+            agg_cp_async16(zsh_u32 + 16u * c, p.z + (size_t)p.n_heads_total * ldz + 4 * c);
         agg_cp_async_commit();
         agg_cp_async_wait<0>();
         __syncthreads();
     }
+    int n_rows = 0;
     if (v < Hb) {
         const int gv = n0 + v;
         const int beg = p.row_ptr[gv];
         const int deg = p.row_ptr[gv + 1] - beg;
-        const int seg = (deg + kWarpsPerHead - 1) / kWarpsPerHead;
+        const int seg = min((deg + kWarpsPerHead - 1) / kWarpsPerHead, hidx_cap);   // deg <= max_heads (build_graph)
         const int i_beg = part_w * seg, i_end = min(deg, i_beg + seg);
-        const int n_rows = max(0, i_end - i_beg);
+        n_rows = max(0, i_end - i_beg);
+        for (int i = lane; i < n_rows; i += 32) hidx[i] = __ldg(p.col + beg + i_beg + i) - n0;
         float a2v[KMAX];
         {
             const float* rowv = grow_of(v);
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) a2v[k] = rowv[HD + H + head_of[k]];
         }
-        // the sources of my in-edges, 96 at a time in three registers: no index load sits in front of a row copy
-        int c_idx[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) c_idx[c] = (32 * c + lane < n_rows) ? __ldg(p.col + beg + i_beg + 32 * c + lane) : 0;
+        __syncwarp();
         auto fetch = [&](int i) {                                            // in-edge i_beg + i -> ring slot i % kHeadRing
             if (i < n_rows) {
-                const int g = i < 32 ? __shfl_sync(0xffffffffu, c_idx[0], i) : i < 64 ? __shfl_sync(0xffffffffu, c_idx[1], i - 32)
-                            : i < 96 ? __shfl_sync(0xffffffffu, c_idx[2], i - 64) : __ldg(p.col + beg + i_beg + i);
-                const int l = g - n0;
-                if (!(p.layer0 && l >= Hb)) agg_row_async(ring + (size_t)(i % kHeadRing) * ldz, grow_of(l), ldz, lane);
+                const int l = hidx[i];
+                if (!(p.layer0 && l >= Hb)) agg_row_async(ring_u32 + 4u * ((i % kHeadRing) * ldz) + 16u * lane, grow_of(l) + 4 * lane, ldz4, lane);
             }
             agg_cp_async_commit();
         };
-        auto src_local = [&](int i) -> int {
-            const int g = i < 32 ? __shfl_sync(0xffffffffu, c_idx[0], i) : i < 64 ? __shfl_sync(0xffffffffu, c_idx[1], i - 32)
-                        : i < 96 ? __shfl_sync(0xffffffffu, c_idx[2], i - 64) : __ldg(p.col + beg + i_beg + i);
-            return g - n0;
-        };
 #pragma unroll
         for (int i = 0; i < kHeadRing; ++i) fetch(i);
+        const uint32_t col_b = 4u * VEC * lane;
+        uint32_t a1_b[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) a1_b[k] = 4u * (HD + head_of[k]);
         for (int i = 0; i < n_rows; ++i) {
             agg_cp_async_wait<kHeadRing - 1>();
             __syncwarp();
-            const float* r = (p.layer0 && src_local(i) >= Hb) ? zsh : ring + (size_t)(i % kHeadRing) * ldz;
+            const uint32_t r = (p.layer0 && hidx[i] >= Hb) ? zsh_u32 : ring_u32 + 4u * ((i % kHeadRing) * ldz);
+            // Softmax weights relative to a per-warp reference logit m_run (the first in-edge's, moved only when a
+            // logit exceeds it by kRescaleAt): softmax is shift invariant, the merge below rebases the warps on a
+            // common maximum, and exp(x) for x <= 30 is far from fp32 overflow - so the per-row work is one exp and
+            // VEC FMAs per vector instead of a rescale of the whole accumulator.
+            float e[KMAX];
+            bool move = false;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                const int cv = lane + 32 * k;
-                if (cv < n_vec) {
-                    const float e = leaky(r[HD + head_of[k]] + a2v[k], p.alpha);     // gat2.py:78-81
-                    const float m_new = fmaxf(m_run[k], e);
-                    const float sc = soft_exp(m_run[k] - m_new), w = soft_exp(e - m_new);
-                    float f[VEC];
-                    load_vec<VEC>(r + cv * VEC, f);
-                    d_run[k] = fmaf(d_run[k], sc, w);
+                e[k] = lrelu(lds_f32(r + a1_b[k]) + a2v[k]);                           // gat2.py:78-81
+                if (i == 0) m_run[k] = e[k];
+                move |= (e[k] - m_run[k] > kRescaleAt);
+            }
+            if (__any_sync(0xffffffffu, move)) {
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(acc[k][q], sc, w * f[q]);
+                for (int k = 0; k < KMAX; ++k) {
+                    const float m_new = fmaxf(m_run[k], e[k]);
+                    const float sc = soft_exp(m_run[k] - m_new);
+                    d_run[k] *= sc;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[k][q] *= sc;
                     m_run[k] = m_new;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < KMAX - 1 || last) {
+                    const float w = soft_exp(e[k] - m_run[k]);
+                    float f[VEC];
+                    lds_vec<VEC>(r + col_b + 128u * VEC * k, f);
+                    d_run[k] += w;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[k][q] = fmaf(w, f[q], acc[k][q]);
+                }
             __syncwarp();
             fetch(i + kHeadRing);
         }
@@ -956,15 +1039,15 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int cv = lane + 32 * k;
-        if (cv < n_vec) {
-            pm[warp * n_vec + cv] = m_run[k];
+        if (k < KMAX - 1 || last) {
+            pm[warp * n_vec + cv] = n_rows > 0 ? m_run[k] : -INFINITY;
             pd[warp * n_vec + cv] = d_run[k];
 #pragma unroll
             for (int q = 0; q < VEC; ++q) part[(size_t)warp * HD + cv * VEC + q] = acc[k][q];
         }
     }
     __syncthreads();
-    // merge the partial triples of a head's warps in warp order; outputs (gat2.py:66, :141-142)
+    // merge the partial (reference, denominator, sum) triples of a head's warps in warp order; outputs (gat2.py:66, :141-142)
     for (int t = tid; t < kLargeHeads * HD; t += kAggWarps * 32) {
         const int hq = t / HD, c = t - hq * HD, cv = c / VEC;
         const int vq = (u - p.edge_units) * kLargeHeads + hq;
@@ -1064,7 +1147,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
     // ---- large frames: fused edge-chunk + head units, every z row read from HBM once ----
-    if (impl == 0 && mh > 48 && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4) {
+    if (impl == 0 && mh > 48 && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
         p.stage_cap = kLargeStageCap;
         p.edge_units = ceil_div(max_enodes_per_frame, kLargeChunk);
         p.head_units = ceil_div(mh, kLargeHeads);
@@ -1078,10 +1161,14 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
                 B2_CHECK_LAUNCH();
                 return B200POSE_OK;
             };
-            const int n_vec_l = HD / vec;
-            if (vec == 4) return n_vec_l <= 64 ? launch_large(gat_aggregate_large_kernel<4, 2>) : launch_large(gat_aggregate_large_kernel<4, 4>);
-            if (vec == 2) return n_vec_l <= 64 ? launch_large(gat_aggregate_large_kernel<2, 2>) : launch_large(gat_aggregate_large_kernel<2, 4>);
-            return launch_large(gat_aggregate_large_kernel<1, 4>);
+            const int n_vec_l = HD / vec, kmax = ceil_div(n_vec_l, 32);       // kernels need 32 (KMAX - 1) < n_vec <= 32 KMAX
+            if (vec == 4 && kmax == 4) return launch_large(gat_aggregate_large_kernel<4, 4>);
+            if (vec == 4 && kmax == 3) return launch_large(gat_aggregate_large_kernel<4, 3>);
+            if (vec == 4 && kmax == 2) return launch_large(gat_aggregate_large_kernel<4, 2>);
+            if (vec == 2 && kmax == 4) return launch_large(gat_aggregate_large_kernel<2, 4>);
+            if (vec == 2 && kmax == 3) return launch_large(gat_aggregate_large_kernel<2, 3>);
+            if (vec == 2 && kmax == 2) return launch_large(gat_aggregate_large_kernel<2, 2>);
+            if (vec == 1 && kmax == 4) return launch_large(gat_aggregate_large_kernel<1, 4>);
         }
     }
     // shared memory: the frame's head rows (+1 shared edge-node row for layer 0), capped at 96 KB, plus

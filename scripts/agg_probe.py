@@ -52,3 +52,10 @@ for li, lay in enumerate(pipe.gat[:-1]):
         if i >= 2:
             ts.append(e0.elapsed_time(e1))
     print('layer %d (hd %d, ldz %d)  %.1f us' % (li, lay['hd'], lay['ldz'], 1e3 * sum(ts) / len(ts)))
+# clustering phases of frame 0 (device printf under debug bit 128)
+L.b200pose_set_debug(128)
+try:
+    out = pipe.infer(db)
+    torch.cuda.synchronize()
+finally:
+    L.b200pose_set_debug(0)
