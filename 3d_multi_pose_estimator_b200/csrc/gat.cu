@@ -1141,13 +1141,13 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
             return launch_frame(gat_aggregate_frame_kernel<1, 4>);
         }
     }
-    B2_CHECK_ARG(impl == 0 || impl == 1, "gat_aggregate: impl must be 0 (auto) or 1 (gather kernel)");
+    B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel) or 2 (large-frame kernel)");
     // ---- gather kernel: work unit = (frame, chunk of destination nodes). ---- In-degree of a head is 1 + H_b - n_g <= H_b and of an
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
     // ---- large frames: fused edge-chunk + head units, every z row read from HBM once ----
-    if (impl == 0 && mh > 48 && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
+    if (((impl == 0 && mh > 48) || impl == 2) && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
         p.stage_cap = kLargeStageCap;
         p.edge_units = ceil_div(max_enodes_per_frame, kLargeChunk);
         p.head_units = ceil_div(mh, kLargeHeads);

@@ -135,8 +135,10 @@ int b200pose_split_planes(const float* x, int32_t rows, int32_t cols, int32_t ld
  *     b200pose_linear with the attention vectors folded into the projection;
  *   layer0 != 0: z holds S+1 compact rows (heads + the shared edge-node row, see node_features);
  *   max_heads_per_frame / max_enodes_per_frame size the shared-memory plan of a frame (0 = unknown);
- *   impl: 0 = frame-resident column-parallel kernel when a frame's plan fits in shared memory, else the
- *         warp-per-destination gather kernel; 1 = always the gather kernel (kept for large frames and A/B runs);
+ *   impl: 0 = frame-resident column-parallel kernel when a frame's plan fits in shared memory (<= 32 heads per
+ *         frame), the large-frame kernel (edge-node chunks with staged head rows + head destinations over cp.async
+ *         row rings) above 48 heads per frame, else the warp-per-destination gather kernel; 1 = always the gather
+ *         kernel, 2 = always the large-frame kernel where its plan fits (A/B runs);
  *   out[v,h,:] = sum_u softmax_u(LeakyReLU_alpha(a1[u,h] + a2[v,h])) * ft2[u,h,:]
  * Outputs (any may be null): raw_f32 [N_tot, heads*dim] (the layer output, gat2.py:68),
  *   planes act_hi/lo [N_tot, ld_planes] = LeakyReLU_{act_slope}(out) (GAT2.forward :141-142),

@@ -15,6 +15,7 @@ cfg, frames = load_workload(config, n_frames, persons, 0)
 gat, mlp = load_weights(config, cfg)
 pb = pack.pack_frames(frames, cfg, keep_json=False)
 pipe = pm.PosePipeline(cfg, gat, mlp, device='cuda:0')
+pipe.agg_impl = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 db = pm.HostBatch(pb).to_device('cuda:0')
 g = pipe.build_graph(db, with_coo=False)
 lay = pipe.gat[1]
