@@ -440,6 +440,74 @@ def test_stress_frame_10_views_16_persons():
     assert np.isfinite(res['joints'].cpu().numpy()).all()
 
 
+@pytest.mark.parametrize('config,persons,impls', [('ring10', (16, 9, 6, 2, 12), (0, 1)), ('panoptic', None, (2, 0)), ('arp3', None, (2, 1))])
+def test_large_frame_aggregation_agrees_with_other_kernels(config, persons, impls):
+    """The large-frame aggregation kernel (staged head rows, cp.async row rings, fixed-reference softmax for heads with
+    many in-edges) against the gather / frame-resident kernels, layer by layer: ragged batches of 160-, 90-, 60-,
+    20- and 120-head frames where the dispatch picks it (impl 0), and the golden Panoptic / ARP frames with it forced
+    (impl 2). It reassociates the heads' sums, so the comparison is to fp32 rounding, not bitwise."""
+    pipe = get_pipe(config)
+    cfg = pipe.cfg
+    if persons is None:
+        tags, pb, db = golden_batch(config)
+    else:
+        frames = [helpers.synth.make_frame(cfg, 777 + i, n) for i, n in enumerate(persons)]
+        frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+        pb = pack_mod.pack_frames(frames, cfg)
+        assert pb.max_heads > 48
+        db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    g = pipe.build_graph(db, with_coo=False)
+    outs = []
+    for impl in impls:
+        pipe.agg_impl = impl
+        try:
+            scores, raws = pipe.gat_forward(db, g, keep_layers=True)
+        finally:
+            pipe.agg_impl = 0
+        outs.append([r.cpu().numpy() for r in raws] + [scores.cpu().numpy()])
+    for l, (a, b) in enumerate(zip(*outs)):
+        scale = np.abs(b).max()
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() <= 5e-5 * scale, (l, np.abs(a - b).max(), scale)      # 5 layers of fp32 reassociation noise
+    sa, sb = outs[0][-1], outs[1][-1]
+    assert (np.abs(sa - sb) / np.abs(sb)).max() <= 2e-5
+
+
+def test_cluster_fuzz_large_frames_vs_oracle():
+    """Clustering of 160- and 90-head frames (1024-thread plan: compaction, CTA-wide sort, 32-at-a-time rejection tests
+    with re-test after a group absorption, parallel link scan) on fuzzed score vectors - uniform, bimodal, all-pass,
+    heavy ties, sparse - bit-exact against the oracle's restatement of get_person_proposal_from_network_output."""
+    config = 'ring10'
+    pipe = get_pipe(config)
+    cfg = pipe.cfg
+    tabs = O.CameraTables(cfg)
+    frames = [helpers.synth.make_frame(cfg, 99, 16), helpers.synth.make_frame(cfg, 100, 9)]
+    frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+    pb = pack_mod.pack_frames(frames, cfg)
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    g = pipe.build_graph(db, with_coo=False)
+    ogs = [O.build_graph(f, tabs) for f in frames]
+    rng = np.random.default_rng(5)
+    N = int(pb.node_off[-1])
+    cases = {
+        'uniform': rng.random(N),
+        'bimodal': np.where(rng.random(N) < 0.1, 0.5 + 0.5 * rng.random(N), 0.4 * rng.random(N)),
+        'all_pass': 0.5 + 0.5 * rng.random(N),
+        'ties': np.round(rng.random(N) * 8) / 8,
+        'sparse': np.where(rng.random(N) < 0.01, 0.9, 0.1),
+        'none': np.full(N, 0.5),
+    }
+    for name, sc in cases.items():
+        sc = sc.astype(np.float32)
+        ph, npers = pipe.cluster(db, g, torch.from_numpy(sc).cuda())
+        ph, npers = ph.cpu().numpy(), npers.cpu().numpy()
+        for b, og in enumerate(ogs):
+            n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+            props = O.cluster(sc[n0:n1], og['pairs'], og['nodes_camera'][:og['n_heads']], cfg.V_sm, og['n_heads'])
+            got = ph[pb.head_off[b]:pb.head_off[b] + npers[b]]
+            assert np.array_equal(got, props), (name, b, len(got), len(props))
+
+
 def test_host_api_variants_agree():
     """The public host entry points - infer_host (one chunk and several), infer_host_stream, and the native JSON packer
     feeding them - return exactly what infer() computes on the same frames, in frame order with batch-global indices."""
