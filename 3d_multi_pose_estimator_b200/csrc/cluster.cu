@@ -85,6 +85,7 @@ struct ClusterParams {
     int* person_heads; int* n_persons;
     int max_heads, max_keys, table_cap;
     int dbg;        // b200pose_set_debug bit 128: frame 0 prints the clock of each phase
+    int general;    // 1: edge-node list without closed form (b200pose_build_graph_pairs): first-seen order from the pairs
 };
 
 // blockDim = 32 (frames of a few hundred edge-nodes: everything is warp-synchronous) or 256 / 1024 (large frames: the sort
@@ -177,7 +178,27 @@ __global__ void __launch_bounds__(MAXT) cluster_kernel(ClusterParams p)
     // a1, a2, ..., then the heads of g2, g3, ... in index order; heads are numbered group by group, so
     //     first_seen = [0, n0 .. n0+n1-1, 1 .. n0-1, n0+n1 .. H-1]          (n0, n1 = sizes of the first two groups)
     // and a frame whose heads all sit in one camera has no edge-node and sees nothing. ----
-    if (tid == 0) {
+    if (p.general) {
+        // explicit edge-node list: the walk (:32-47) meets, per edge-node in order, its head1 then its head2, so a head's
+        // first appearance is its smallest position in the flattened pair list, and the first-seen order is the heads
+        // sorted by that position (rank by counting: positions are distinct)
+        for (int h = tid; h < H; h += nt) flag[h] = 0x7fffffff;
+        bsync();
+        for (int t = tid; t < 2 * M; t += nt) atomicMin(&flag[p.pairs[2 * (size_t)m0 + t]], t);
+        bsync();
+        if (tid == 0) n_seen_s = 0;
+        bsync();
+        for (int h = tid; h < H; h += nt) {
+            const int mine = flag[h];
+            if (mine == 0x7fffffff) continue;
+            int r = 0;
+            for (int o = 0; o < H; ++o) r += flag[o] < mine ? 1 : 0;
+            first_seen[r] = h;
+            atomicAdd(&n_seen_s, 1);
+        }
+        bsync();
+        for (int h = tid; h < H; h += nt) flag[h] = 0;
+    } else if (tid == 0) {
         int n0g = 1;
         while (n0g < H && cam[n0g] == cam[0]) ++n0g;
         int n_seen = 0;
@@ -452,11 +473,11 @@ static int set_table_capacity(int max_heads) {
     return mask + 1;
 }
 
-extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
-                                const int32_t* pairs, const int32_t* node_cam, const float* scores,
-                                int32_t v_sm, double threshold, int32_t min_views,
-                                int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
-                                int32_t* person_heads, int32_t* n_persons, void* stream)
+static int cluster_launch(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
+                          const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                          int32_t v_sm, double threshold, int32_t min_views,
+                          int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
+                          int32_t* person_heads, int32_t* n_persons, int general, void* stream)
 {
     B2_CHECK_ARG(head_off && node_off && pairs && node_cam && scores && person_heads && n_persons, "cluster: null pointer");
     B2_CHECK_ARG(v_sm >= 1 && v_sm <= B200POSE_MAX_CAMERAS, "cluster: v_sm out of range");
@@ -465,6 +486,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
     p.head_off = head_off; p.node_off = node_off; p.pairs = pairs; p.node_cam = node_cam; p.scores = scores;
     p.v_sm = v_sm; p.threshold = threshold; p.min_views = min_views; p.person_heads = person_heads; p.n_persons = n_persons;
     p.dbg = g_debug_flags;
+    p.general = general;
     p.max_heads = max_heads_per_frame < 1 ? 1 : max_heads_per_frame;
     int keys = 1;
     while (keys < max_enodes_per_frame) keys <<= 1;
@@ -485,6 +507,26 @@ extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n
     }
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_cluster(int32_t n_frames, const int32_t* head_off, const int32_t* node_off,
+                                const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                                int32_t v_sm, double threshold, int32_t min_views,
+                                int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
+                                int32_t* person_heads, int32_t* n_persons, void* stream)
+{
+    return cluster_launch(n_frames, head_off, node_off, pairs, node_cam, scores, v_sm, threshold, min_views, max_heads_per_frame,
+                          max_enodes_per_frame, person_heads, n_persons, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_cluster_pairs(int32_t n_graphs, const int32_t* head_off, const int32_t* node_off,
+                                      const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                                      int32_t v_sm, double threshold, int32_t min_views,
+                                      int32_t max_heads_per_graph, int32_t max_enodes_per_graph,
+                                      int32_t* person_heads, int32_t* n_persons, void* stream)
+{
+    return cluster_launch(n_graphs, head_off, node_off, pairs, node_cam, scores, v_sm, threshold, min_views, max_heads_per_graph,
+                          max_enodes_per_graph, person_heads, n_persons, 1, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int b200pose_gather_persons(int32_t n_frames, const int32_t* head_off, const int32_t* person_heads,

@@ -1187,7 +1187,8 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
         set_error("gat_aggregate: frame too large for the shared-memory plan (%zu bytes, %d heads per frame)", smem, mh);
         return B200POSE_E_UNSUPPORTED;
     }
-    const int max_nodes = mh + (mh * mh) / 2;
+    int max_nodes = mh + (mh * mh) / 2;
+    if (max_enodes_per_frame > 0 && mh + max_enodes_per_frame < max_nodes) max_nodes = mh + max_enodes_per_frame;
     p.chunk = 6 * kAggWarps;                                   // 48 destinations per CTA
     const int n_chunks = ceil_div(max_nodes, p.chunk);
     p.n_chunks = n_chunks;

@@ -150,6 +150,64 @@ __global__ void __launch_bounds__(128) build_graph_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// Graph from an explicit edge-node list: the training-side topology of process_training
+// (graph_generator.py:672-810), where edge-nodes follow the people / other-people / spurious loops, both
+// (h1, h2) and (h2, h1) exist, and dgl.batch concatenates several such graphs - no closed form, but the same
+// wiring per edge-node (add_edge_node_to_graph, :627-656). One CTA per graph: in-degrees by shared-memory atomics
+// (a count, so order-free), exclusive scan, then one thread per head walks the edge-node list in order, so the
+// in-edges of every node are in ascending reference edge id like the closed-form builder's.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_graph_pairs_kernel(
+    int n_graphs, const int* __restrict__ head_off, const int* __restrict__ node_off,
+    const int* __restrict__ sk_cam, const int* __restrict__ sm_slot, const int* __restrict__ pairs,
+    int* __restrict__ src, int* __restrict__ dst, int* __restrict__ row_ptr, int* __restrict__ col, int* __restrict__ node_cam)
+{
+    extern __shared__ int off_s[];                  // [H + 1] in-degree, then CSR offset of every head
+    const int b = blockIdx.x;
+    const int h0 = head_off[b], H = head_off[b + 1] - h0;
+    const int n0 = node_off[b], Nb = node_off[b + 1] - n0;
+    const int M = Nb - H, m0 = n0 - h0, e0 = h0 + 5 * m0;
+    const int* pr = pairs + 2 * (size_t)m0;
+    for (int h = threadIdx.x; h <= H; h += blockDim.x) off_s[h] = h < H ? 1 : 0;      // the self loop
+    __syncthreads();
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        atomicAdd(&off_s[pr[2 * k]], 1);
+        atomicAdd(&off_s[pr[2 * k + 1]], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int h = 0; h <= H; ++h) { const int d = off_s[h]; off_s[h] = run; run += d; }
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        int pos = e0 + off_s[h];
+        if (row_ptr) row_ptr[n0 + h] = pos;
+        if (node_cam) node_cam[n0 + h] = sm_slot[sk_cam[h0 + h]];
+        if (src) { src[e0 + h] = h; dst[e0 + h] = h; }
+        if (col) {
+            col[pos++] = n0 + h;                                             // self loop (edge id h)
+            for (int k = 0; k < M; ++k)                                       // (e -> h1) is edge H + 5k + 1, (e -> h2) edge H + 5k + 3
+                if (pr[2 * k] == h || pr[2 * k + 1] == h) col[pos++] = n0 + H + k;
+        }
+    }
+    const int csr_enode0 = off_s[H];                                         // == H + 2M
+    for (int k = threadIdx.x; k < M; k += blockDim.x) {
+        const int h1 = pr[2 * k], h2 = pr[2 * k + 1], e = H + k;
+        if (src) {
+            int* s = src + e0 + H + 5 * k;
+            int* d = dst + e0 + H + 5 * k;
+            s[0] = h1; d[0] = e; s[1] = e; d[1] = h1; s[2] = h2; d[2] = e; s[3] = e; d[3] = h2; s[4] = e; d[4] = e;   // :632-651
+        }
+        if (node_cam) node_cam[n0 + e] = -1;
+        const int pos = e0 + csr_enode0 + 3 * k;
+        if (row_ptr) row_ptr[n0 + e] = pos;
+        if (col) { col[pos] = n0 + h1; col[pos + 1] = n0 + h2; col[pos + 2] = n0 + e; }
+    }
+    if (row_ptr && b == n_graphs - 1 && threadIdx.x == 0) row_ptr[n0 + Nb] = e0 + H + 5 * M;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Node features. feature_value() evaluates one column of a head row with exactly the reference's
 // arithmetic: i/j normalisation in float64 then rounded to fp32 (graph_generator.py:496-497), rays as
 // two tiny fp32 matmuls whose CPU summation order is a sequential FMA chain (:488-489).
@@ -298,6 +356,23 @@ extern "C" __attribute__((visibility("default"))) int b200pose_build_graph(int32
     if (n_frames == 0) return B200POSE_OK;
     build_graph_kernel<<<n_frames, 128, 0, (cudaStream_t)stream>>>(n_frames, head_off, node_off, sk_cam, cams->sm_slot,
                                                                     src, dst, row_ptr, col, pairs, node_cam);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_build_graph_pairs(int32_t n_graphs, const int32_t* head_off, const int32_t* node_off,
+                                          const int32_t* sk_cam, const b200pose_cameras* cams, const int32_t* pairs,
+                                          int32_t max_heads_per_graph,
+                                          int32_t* src, int32_t* dst, int32_t* row_ptr, int32_t* col, int32_t* node_cam, void* stream)
+{
+    B2_CHECK_ARG(n_graphs >= 0 && head_off && node_off && sk_cam && cams && pairs, "build_graph_pairs: null input");
+    B2_CHECK_ARG((src == nullptr) == (dst == nullptr), "build_graph_pairs: src and dst go together");
+    B2_CHECK_ARG(max_heads_per_graph >= 0 && max_heads_per_graph <= 40000, "build_graph_pairs: max_heads_per_graph out of range");
+    if (n_graphs == 0) return B200POSE_OK;
+    const size_t smem = (size_t)(max_heads_per_graph + 1) * sizeof(int);
+    B2_CHECK_CUDA(cudaFuncSetAttribute(build_graph_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_graph_pairs_kernel<<<n_graphs, 256, smem, (cudaStream_t)stream>>>(n_graphs, head_off, node_off, sk_cam, cams->sm_slot, pairs,
+                                                                            src, dst, row_ptr, col, node_cam);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

@@ -180,6 +180,9 @@ class GraphArrays:
         self.col = torch.empty(max(E, 1), **i32)
         self.pairs = torch.empty((max(db.n_enodes, 1), 2), **i32)
         self.node_cam = torch.empty(max(db.n_nodes, 1), **i32)
+        # True: built from an explicit edge-node list (b200pose_build_graph_pairs: training-side topology, dgl.batch
+        # members) - the kernels that rely on the closed form of the test-mode graph step aside
+        self.general = False
 
 
 class PosePipeline:
@@ -289,6 +292,24 @@ class PosePipeline:
                                           self._stream()), 'build_graph')
         return g
 
+    def build_graph_pairs(self, db: DeviceBatch, pairs, with_coo=True) -> GraphArrays:
+        """Graphs of a block-diagonal batch from explicit edge-node lists (process_training topology,
+        graph_generator.py:672-810; dgl.batch members): `pairs` [M_tot, 2] int32 graph-local (head1, head2) per
+        edge-node, graph after graph, node_off already counting them. db.max_heads must cover the largest in-degree
+        (1 + edge-nodes touching a head), which sizes the aggregation scratch."""
+        g = GraphArrays(db, self.device, with_coo)
+        g.general = True
+        pairs = torch.as_tensor(pairs, dtype=torch.int32).reshape(-1, 2)
+        if pairs.shape[0] != db.n_enodes:
+            raise ValueError('build_graph_pairs: %d pairs for %d edge-nodes' % (pairs.shape[0], db.n_enodes))
+        if db.n_enodes:
+            g.pairs[: db.n_enodes].copy_(pairs.to(self.device, non_blocking=True))
+        self.launches += 1
+        check(self.L.b200pose_build_graph_pairs(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(db.sk_cam), self.cams.ref,
+                                                ptr(g.pairs), db.max_heads, ptr(g.src), ptr(g.dst), ptr(g.row_ptr), ptr(g.col),
+                                                ptr(g.node_cam), self._stream()), 'build_graph_pairs')
+        return g
+
     def node_features_f32(self, db: DeviceBatch) -> torch.Tensor:
         F = self.cfg.n_features_sm
         out = torch.empty((max(db.n_nodes, 1), F), dtype=torch.float32, device=self.device)
@@ -314,7 +335,8 @@ class PosePipeline:
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
                                             1 if layer0 else 0, db.max_heads, db.max_enodes, alpha, act_slope, ptr(raw),
                                             ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
-                                            ptr(scores), self.agg_impl, self._stream()), 'gat_aggregate')
+                                            ptr(scores), 1 if getattr(g, 'general', False) else self.agg_impl, self._stream()),
+              'gat_aggregate')
 
     # ------------------------------------------------------------------ stages
     def gat_forward(self, db: DeviceBatch, g: GraphArrays, x0: Optional[Planes] = None, dense_rows: bool = False,
@@ -355,9 +377,10 @@ class PosePipeline:
         person_heads = torch.empty((max(db.n_heads, 1), V), dtype=torch.int32, device=self.device)
         n_persons = torch.empty(max(db.n_frames, 1), dtype=torch.int32, device=self.device)
         self.launches += 1
-        check(self.L.b200pose_cluster(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(g.pairs), ptr(g.node_cam), ptr(scores),
-                                      V, thr, self.cfg.min_number_of_views, db.max_heads, db.max_enodes,
-                                      ptr(person_heads), ptr(n_persons), self._stream()), 'cluster')
+        fn = self.L.b200pose_cluster_pairs if getattr(g, 'general', False) else self.L.b200pose_cluster
+        check(fn(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(g.pairs), ptr(g.node_cam), ptr(scores),
+                 V, thr, self.cfg.min_number_of_views, db.max_heads, db.max_enodes,
+                 ptr(person_heads), ptr(n_persons), self._stream()), 'cluster')
         return person_heads, n_persons[: db.n_frames]
 
     def gather_persons(self, db: DeviceBatch, person_heads, n_persons):

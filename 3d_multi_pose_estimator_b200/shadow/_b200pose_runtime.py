@@ -21,6 +21,7 @@ if _REPO not in sys.path:
 pkg = importlib.import_module('3d_multi_pose_estimator_b200')
 pipeline = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
 pack = importlib.import_module('3d_multi_pose_estimator_b200.pack')
+training_graphs = importlib.import_module('3d_multi_pose_estimator_b200.training_graphs')
 
 _cfg = None
 _ctx = None

@@ -1,17 +1,21 @@
-"""Drop-in for the reference's skeleton_matching/graph_generator.py, inference side.
+"""Drop-in for the reference's skeleton_matching/graph_generator.py.
 
 Same public names: `MergedMultipleHumansDataset` (:516-916), `HumanGraphFromView` (:214-508), `graphData` (:21).
 `MergedMultipleHumansDataset(frame_dict | [json paths], mode='test', alt='3')` builds, on the GPU and without
 DGL, exactly the graph `process_test` builds (:813-876): heads in frame-dict camera order, one edge-node per
-cross-camera skeleton pair wired with 5 directed edges, alternative-'3' node features bit-exact in fp32. The
-graph object it hands out offers the slice of the DGL API the reference's callers use (`.to`, `.ndata['h']`,
-`.edata`, `.edges()`, `.nodes()`, `.number_of_nodes()`), and carries the CSR the B200 GAT2 / clustering
-drop-ins consume.
+cross-camera skeleton pair wired with 5 directed edges, alternative-'3' node features bit-exact in fp32. Any other
+mode ('train', 'dev', 'test_generated', ...) over a list of single-person files runs `process_training` (:672-810):
+the same sample tuples for the same `random` seed, the same edge-node order and labels, graphs built on the GPU from
+the explicit edge-node list (forward only - the B200 GAT2 has no backward). The graph object it hands out offers the
+slice of the DGL API the reference's callers use (`.to`, `.ndata['h']`, `.edata`, `.edges()`, `.nodes()`,
+`.number_of_nodes()`), carries the CSR the B200 GAT2 / clustering drop-ins consume, and is what the `dgl.batch` of
+the sibling `dgl` drop-in module merges.
 
-Out of scope (raise NotImplementedError): training-set synthesis (`mode != 'test'`, :672-810), graph
-alternatives '1' and '2' (unused by the shipped configuration, parameters.py:76) and the DGL cache files.
+Out of scope (raise NotImplementedError): graph alternatives '1' and '2' (unused by the shipped configuration,
+parameters.py:76) and the DGL cache files (every construction processes its inputs).
 """
 import json
+import random
 import sys
 from collections import namedtuple
 
@@ -71,19 +75,42 @@ class B200Graph:
         self._b200 = (db, arrays)
         self._n = db.n_nodes
         self._e = db.n_edges
-        H = db.n_heads
-        rel = torch.ones(self._e, dtype=torch.int64, device=feats.device)
-        rel[:H] = 0                                             # RELATIONS['3'].index('h_h')
-        rel[H + 4::5] = 2                                       # every 5th edge of an edge-node: 'link_link'
+        self.batch_size = db.n_frames
+        dev = feats.device
+        # edge ids: per graph H self loops ('h_h'), then per edge-node four 'link' edges and one 'link_link' (:627-656)
+        if db.n_frames == 1:
+            H = db.n_heads
+            rel = torch.ones(self._e, dtype=torch.int64, device=dev)
+            rel[:H] = 0
+            rel[H + 4::5] = 2
+            self._node_shift = None
+        else:                                                   # dgl.batch: graphs one after the other
+            ho, no = db.head_off[: db.n_frames + 1].long(), db.node_off[: db.n_frames + 1].long()
+            Hs = ho[1:] - ho[:-1]
+            Es = Hs + 5 * (no[1:] - no[:-1] - Hs)
+            graph_of = torch.repeat_interleave(torch.arange(db.n_frames, device=dev), Es)
+            first = torch.cumsum(Es, 0) - Es
+            local = torch.arange(self._e, device=dev) - first[graph_of]
+            k = local - Hs[graph_of]
+            rel = torch.where(k < 0, 0, torch.where(k % 5 == 4, 2, 1))
+            self._node_shift = no[:-1][graph_of].to(torch.int32)
         self.ndata = {'h': feats}
-        self.edata = {'rel_type': rel, 'norm': torch.ones((self._e, 1), dtype=torch.float32, device=feats.device)}
+        self.edata = {'rel_type': rel, 'norm': torch.ones((self._e, 1), dtype=torch.float32, device=dev)}
 
     def to(self, device, **kw):
         return self                                             # tensors already live on the CUDA device
 
     def edges(self):
         _, arrays = self._b200
-        return arrays.src[: self._e], arrays.dst[: self._e]
+        src, dst = arrays.src[: self._e], arrays.dst[: self._e]
+        if self._node_shift is not None:                        # the kernels keep graph-local ids; DGL's are batch-global
+            src, dst = src + self._node_shift, dst + self._node_shift
+        return src, dst
+
+    def batch_num_nodes(self):
+        db, _ = self._b200
+        no = db.node_off[: db.n_frames + 1].long()
+        return no[1:] - no[:-1]
 
     def nodes(self):
         return torch.arange(self._n, dtype=torch.int32, device=self.ndata['h'].device)
@@ -166,21 +193,22 @@ class MergedMultipleHumansDataset:
         if alt is None:
             print('Alt is None')
             sys.exit(-1)
-        self.inputs = []
-        if type(paths) == list:
-            if mode != 'test':
-                raise NotImplementedError('the B200 graph generator is inference-only (mode="test")')
-            for path in paths:
-                print('PATH', path)
-                self.inputs.append(json.loads(open(path, "rb").read()))
-        elif type(paths) == dict:
-            self.inputs.append(paths)
-        else:
-            raise Exception('Unhandled type for MergedMultipleHumansDataset')
-        if mode != 'test':
-            raise NotImplementedError('the B200 graph generator is inference-only (mode="test")')
         if alt != '3':
             raise NotImplementedError('graph alternative %s is not part of the B200 path' % alt)
+        self.inputs = []
+        self.inputs_indices = []
+        if type(paths) == list:
+            files = []
+            for path in paths:
+                print('PATH', path)
+                files.append(json.loads(open(path, "rb").read()))
+            # augmentation (train modes) and the shuffled index lists, drawing from the global `random` like the reference
+            self.inputs, self.inputs_indices = rt.training_graphs.load_inputs(files, mode, rt.config().used_pe_names, random)
+        elif type(paths) == dict:
+            self.inputs.append(paths)
+            self.inputs_indices.append(list(range(len(paths))))
+        else:
+            raise Exception('Unhandled type for MergedMultipleHumansDataset')
         self.name = "MergedMultipleHumansDataset"
         self.probabilities = probabilities
         self.mode = mode
@@ -191,7 +219,7 @@ class MergedMultipleHumansDataset:
         self.data['edge_nodes_indices'] = []
         self.data['nodes_camera'] = []
         self.debug = debug
-        self.force_reload = True
+        self.force_reload = force_reload or mode == 'test'
         self.device = device
         self.limit = limit
         self.verbose = verbose
@@ -200,7 +228,36 @@ class MergedMultipleHumansDataset:
         self.process()
 
     def process(self):
-        self.process_test()
+        if self.mode != 'test':
+            self.process_training()
+        else:
+            self.process_test()
+
+    def process_training(self):
+        """graph_generator.py:672-810: one graph per tuple of single-person samples. The tuples, the person / spurious
+        split, the edge-node order and the labels come from the host-side list logic of training_graphs; edges, CSR
+        and features are built on the device."""
+        ctx = rt.context()
+        cfg = rt.config()
+        names = cfg.used_sm_names
+        idx = 0
+        for multi_person in rt.training_graphs.sample_sets(self.inputs, self.inputs_indices, self.probabilities,
+                                                           int(self.limit), random):
+            if idx % 1000 == 0:
+                print(idx)
+            idx += 1
+            built = rt.training_graphs.training_graph_inputs(multi_person, cfg)
+            if built is None:                                   # no cross-camera pair: no graph (:802)
+                continue
+            pb, pairs, labels = built
+            db = rt.pipeline.HostBatch(pb).to_device(ctx.device)
+            arrays = ctx.build_graph_pairs(db, pairs, with_coo=True)
+            feats = ctx.node_features_f32(db)
+            H, N = db.n_heads, db.n_nodes
+            self.graphs.append(B200Graph(db, arrays, feats))
+            self.labels.append(th.from_numpy(labels))
+            self.data['edge_nodes_indices'].append(th.arange(H, N, dtype=th.int64).unsqueeze(1))
+            self.data['nodes_camera'].append([names[cfg.used_sm.index(int(c))] for c in pb.sk_cam] + [''] * (N - H))
 
     def process_test(self):
         assert len(self.inputs) == 1, "For testing, please provide __ONE__ single JSON file"

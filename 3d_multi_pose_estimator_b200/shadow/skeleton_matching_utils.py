@@ -24,6 +24,8 @@ def get_person_proposal_from_network_output(outputs, subgraph, indices, nodes_ca
         scores = torch.tensor(outputs, dtype=torch.float32, device=ctx.device)
     else:
         scores = outputs.detach().to(ctx.device, torch.float32)
+    if db.n_frames != 1:
+        raise NotImplementedError('get_person_proposal_from_network_output works on one graph, not on a dgl.batch of %d' % db.n_frames)
     scores = scores.reshape(-1).contiguous()
     if scores.numel() != db.n_nodes:
         raise ValueError('expected one score per graph node (%d), got %d' % (db.n_nodes, scores.numel()))

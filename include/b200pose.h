@@ -84,6 +84,19 @@ int b200pose_build_graph(int32_t n_frames, const int32_t* head_off, const int32_
                          int32_t* src, int32_t* dst, int32_t* row_ptr, int32_t* col,
                          int32_t* pairs, int32_t* node_cam, void* stream);
 
+/* Stage 1a', training-side topology. The same five edges per edge-node (add_edge_node_to_graph,
+ * graph_generator.py:627-656) for an EXPLICIT edge-node list: process_training (:672-810) orders edge-nodes by its
+ * people / other-people / spurious loops and creates both (h1,h2) and (h2,h1), and dgl.batch
+ * (train_skeleton_matching.py:80, sm_metrics_without_gt.py:60) concatenates graphs - "frames" here are graphs of a
+ * block-diagonal batch, nodes of a graph = its heads then its edge-nodes.
+ *   pairs [M_tot,2] i32 graph-local (head1, head2) of every edge-node, in edge-node order (input)
+ *   max_heads_per_graph sizes the per-graph scan; outputs as b200pose_build_graph (CSR in ascending edge id). */
+int b200pose_build_graph_pairs(int32_t n_graphs, const int32_t* head_off, const int32_t* node_off,
+                               const int32_t* sk_cam, const b200pose_cameras* cams, const int32_t* pairs,
+                               int32_t max_heads_per_graph,
+                               int32_t* src, int32_t* dst, int32_t* row_ptr, int32_t* col,
+                               int32_t* node_cam, void* stream);
+
 /* Stage 1b. Node features of alternative '3' (HumanGraphFromView.initializeWithAlternative3,
  * graph_generator.py:444-508), bit-exact fp32.
  *   feats_f32 != null : dense [N_tot, ld_f32] rows for every node (edge-nodes: one-hot column 1) - what
@@ -167,6 +180,15 @@ int b200pose_cluster(int32_t n_frames, const int32_t* head_off, const int32_t* n
                      int32_t v_sm, double threshold, int32_t min_views,
                      int32_t max_heads_per_frame, int32_t max_enodes_per_frame,
                      int32_t* person_heads, int32_t* n_persons, void* stream);
+
+/* Stage 2b on graphs built by b200pose_build_graph_pairs (training-side topology, dgl.batch members): the same
+ * function, with the first-seen head order of the reference's edge walk (skeleton_matching_utils.py:32-47) taken from
+ * the explicit pair list instead of the closed form of the test-mode graph. */
+int b200pose_cluster_pairs(int32_t n_graphs, const int32_t* head_off, const int32_t* node_off,
+                           const int32_t* pairs, const int32_t* node_cam, const float* scores,
+                           int32_t v_sm, double threshold, int32_t min_views,
+                           int32_t max_heads_per_graph, int32_t max_enodes_per_graph,
+                           int32_t* person_heads, int32_t* n_persons, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3a. MLP-input encoder: PoseEstimatorDataset.__init__ dict branch + get_3D_from_triangulation

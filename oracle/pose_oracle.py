@@ -141,6 +141,149 @@ def build_graph(frame: Dict[str, list], tabs: CameraTables) -> Optional[dict]:
 
 
 # ----------------------------------------------------------------------------------------------
+# Stage 1, training side: sample synthesis + graph of process_training (graph_generator.py:516-560, 672-810;
+# utils/data_augmentation.py:14-89). Forward-only scope: the graphs, labels and index lists the training /
+# validation drivers batch with dgl.batch (train_skeleton_matching.py:67-84, sm_metrics_without_gt.py:46-64).
+# ----------------------------------------------------------------------------------------------
+def augment_views(json_data: List[dict], used_cameras: Sequence[str], min_views: int = 1) -> List[dict]:
+    """add_data_to_json (data_augmentation.py:50-89): every sample restricted to the used cameras that saw
+    something, followed by each proper camera subset of it with at least min_views cameras, subsets in
+    itertools.product(range(2)) order over the used-camera list (permutations_generator, :14-27)."""
+    import itertools
+    out = []
+    for data in json_data:
+        flags = [0] * len(used_cameras)
+        base = {}
+        for c in data:                                                        # dict order of the sample survives
+            if c in used_cameras and json.loads(data[c][0]):
+                flags[list(used_cameras).index(c)] = 1
+                base[c] = data[c]
+        if sum(flags) == 0:
+            continue
+        out.append(dict(base))
+        for comb in itertools.product(range(2), repeat=len(flags)):
+            if any(f - c < 0 for f, c in zip(flags, comb)) or sum(comb) < min_views or tuple(flags) == comb:
+                continue
+            out.append({c: base[c] for c in base if comb[list(used_cameras).index(c)]})
+    return out
+
+
+def load_training_inputs(files_json: List[List[dict]], mode: str, used_cameras: Sequence[str], rnd) -> Tuple[list, list]:
+    """MergedMultipleHumansDataset.__init__, list branch (:526-538): per file, optional augmentation
+    (mode not test / test_generated), index list, random.shuffle of it (mode != 'test'). `rnd` is the
+    `random` module (or a random.Random) - the reference draws from the global one."""
+    inputs, indices = [], []
+    for data in files_json:
+        if mode != 'test' and mode != 'test_generated':
+            data = augment_views(data, used_cameras, 2)
+        idx = list(range(len(data)))
+        if mode != 'test':
+            rnd.shuffle(idx)
+        inputs.append(data)
+        indices.append(idx)
+    return inputs, indices
+
+
+def training_samples(inputs, inputs_indices, probabilities, limit: int, rnd):
+    """sample_and_remove (:675-697): up to `limit` tuples of single-person samples; the num_people files with
+    the largest probabilities (np.argpartition order) each give up the sample at the end of their shuffled list."""
+    for _ in range(limit):
+        if all(len(l) == 0 for l in inputs):
+            break
+        num_people = rnd.randint(1, len(inputs))
+        max_indx = np.argpartition(np.array(probabilities), -num_people)[-num_people:]
+        views = []
+        for index in max_indx:
+            if not inputs_indices[index]:
+                return                                                        # IndexError in the reference (:691-692)
+            views.append(inputs[index][inputs_indices[index].pop()])
+        if views:
+            yield views
+
+
+def build_training_graph(multi_person: List[Dict[str, list]], tabs: CameraTables) -> Optional[dict]:
+    """One iteration of process_training (:699-810): heads of every single-person sample (the skeleton with
+    most joints per camera is the person, the others are spurious), then edge-nodes in the order
+    true links of person 0, its false links to the other people, its false links to spurious heads, person 1 ...,
+    finally spurious x spurious - ordered pairs, so (a, b) and (b, a) both exist."""
+    cfg = tabs.cfg
+    rows, nodes_camera = [], []
+    people, spurious = [], []
+    total = 0
+    for sample in multi_person:
+        view_heads, view_joints = {}, {}
+        head_id = 0
+        for camera in sample:                                                 # load_people_view_graph (:573-605)
+            if camera not in tabs.sm_names:
+                continue
+            view_heads[camera], view_joints[camera] = [], []
+            for skeleton in json.loads(sample[camera][0]):
+                row, nj = head_feature_row(skeleton, camera, tabs)
+                if nj == 0:
+                    continue
+                rows.append(row)
+                view_heads[camera].append(head_id)
+                view_joints[camera].append(nj)
+                nodes_camera.append(tabs.sm_names.index(camera))
+                head_id += 1
+        person = []
+        for camera in sample:                                                 # :722-730
+            if camera in tabs.sm_names and view_joints[camera]:
+                heads_cam, joints_cam = view_heads[camera], view_joints[camera]
+                good = max(enumerate(joints_cam), key=lambda x: x[1])[0]
+                spurious += [(x + total, camera) for x in heads_cam if x != heads_cam[good]]
+                person.append((heads_cam[good] + total, camera))
+        people.append(person)
+        total += head_id
+    H = total
+    pairs, labels = [], []
+    for ip, person in enumerate(people):
+        for h1, c1 in person:                                                 # :755-764
+            for h2, c2 in person:
+                if c1 != c2:
+                    pairs.append((h1, h2)); labels.append(1.)
+        for io, other in enumerate(people):                                   # :766-778
+            if io == ip:
+                continue
+            for h1, c1 in person:
+                for h2, c2 in other:
+                    if c1 != c2:
+                        pairs.append((h1, h2)); labels.append(0.)
+        for h1, c1 in person:                                                 # :780-789
+            for h2, c2 in spurious:
+                if c1 != c2:
+                    pairs.append((h1, h2)); labels.append(0.)
+    for h1, c1 in spurious:                                                   # :791-800
+        for h2, c2 in spurious:
+            if c1 != c2:
+                pairs.append((h1, h2)); labels.append(0.)
+    M = len(pairs)
+    if M == 0:
+        return None                                                           # :802
+    src, dst = list(range(H)), list(range(H))
+    for k, (h1, h2) in enumerate(pairs):
+        e = H + k
+        src += [h1, e, h2, e, e]
+        dst += [e, h1, e, h2, e]
+    feats = np.zeros((H + M, cfg.n_features_sm), dtype=f32)
+    feats[:H] = np.stack(rows)
+    feats[H:, 1] = 1.0
+    return dict(src=np.array(src, dtype=np.int32), dst=np.array(dst, dtype=np.int32), n_nodes=H + M, n_heads=H, feats=feats,
+                labels=np.array(labels, dtype=np.float64).reshape(-1, 1), indices=np.arange(H, H + M, dtype=np.int64),
+                nodes_camera=np.array(nodes_camera + [-1] * M, dtype=np.int32), pairs=np.array(pairs, dtype=np.int32).reshape(-1, 2),
+                rel_type=np.array([0] * H + [1, 1, 1, 1, 2] * M, dtype=np.int64))
+
+
+def batch_graphs(graphs: List[dict]) -> dict:
+    """dgl.batch (train_skeleton_matching.py:80): block-diagonal union, node and edge ids shifted graph by graph."""
+    src, dst, feats, off = [], [], [], 0
+    for g in graphs:
+        src.append(g['src'] + off); dst.append(g['dst'] + off); feats.append(g['feats'])
+        off += g['n_nodes']
+    return dict(src=np.concatenate(src), dst=np.concatenate(dst), feats=np.concatenate(feats), n_nodes=off)
+
+
+# ----------------------------------------------------------------------------------------------
 # Stage 2a: GAT forward  (skeleton_matching/gat2.py)
 # ----------------------------------------------------------------------------------------------
 def leaky(x, slope):

@@ -62,3 +62,18 @@ def save_graphs(path, graphs):
 
 def load_graphs(path):
     raise NotImplementedError("dgl shim: graph cache I/O is out of scope")
+
+
+def batch(graphs):
+    """dgl.batch: block-diagonal union; node/edge ids shifted graph by graph, ndata/edata concatenated."""
+    src, dst, off = [], [], 0
+    for g in graphs:
+        src.append(g._src + off)
+        dst.append(g._dst + off)
+        off += g._n
+    out = DGLGraph(torch.cat(src), torch.cat(dst), off, graphs[0]._idtype)
+    for k in graphs[0].ndata:
+        out.ndata[k] = torch.cat([g.ndata[k] for g in graphs], dim=0)
+    for k in graphs[0].edata:
+        out.edata[k] = torch.cat([g.edata[k] for g in graphs], dim=0)
+    return out

@@ -1,0 +1,115 @@
+"""GPU: the training-side graph path through the drop-in modules, against goldens produced by the
+unmodified reference (tests/golden/make_golden_training.py): MergedMultipleHumansDataset over single-person files in
+modes 'test_generated' and 'train' (process_training, graph_generator.py:672-810), the collate of
+test/sm_metrics_without_gt.py:46-64 with `dgl.batch`, GAT2 forward on single and batched graphs and
+get_person_proposal_from_network_output on every graph. Forward only."""
+import importlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import dropin_env
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def collate(batch, dgl, device):
+    """test/sm_metrics_without_gt.py:46-64, verbatim in behaviour."""
+    graphs = [batch[0][0]]
+    batched_labels = batch[0][1]
+    batched_indices = batch[0][2]
+    total_nodes = batch[0][0].number_of_nodes()
+    for graph, labels, indices, nodes_camera in batch[1:]:
+        graphs.append(graph)
+        batched_labels = torch.cat([batched_labels, labels], dim=0)
+        batched_indices = torch.cat([batched_indices, indices + total_nodes], dim=0)
+        total_nodes += graph.number_of_nodes()
+    return dgl.batch(graphs).to(torch.device(device)), batched_labels, batched_indices
+
+
+@pytest.mark.parametrize('mode', ['test_generated', 'train'])
+def test_training_dataset_batch_and_forward_against_reference(mode, tmp_path):
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    gz = np.load(os.path.join(GOLDEN, 'golden_training_panoptic.npz'))
+    gm = json.load(open(os.path.join(GOLDEN, 'golden_training_panoptic.json')))
+    mods = dropin_env.activate(cfg)
+    dgl = importlib.import_module('dgl')
+    assert dgl.__file__.startswith(dropin_env.SHADOW)
+    gg, smu = mods['graph_generator'], mods['skeleton_matching_utils']
+    gat_state, _ = helpers.golden_weights('panoptic')
+    device = torch.device('cuda')
+    model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
+                              torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
+    model.load_state_dict(gat_state)
+    model = model.to(device)
+    paths = []
+    for i, frames in enumerate(gm['files']):
+        p = tmp_path / ('single_%d.json' % i)
+        p.write_text(json.dumps(frames))
+        paths.append(str(p))
+    random.seed(gm['seed'])
+    ds = gg.MergedMultipleHumansDataset(paths, gm['probabilities'], limit=gm['limit'], mode=mode, alt='3', raw_dir='.',
+                                        verbose=False, debug=True)
+    recs = gm['modes'][mode]['graphs']
+    assert len(ds) == len(recs)
+    names = cfg.used_sm_names
+    n_props = 0
+    for i, rec in enumerate(recs):
+        g, labels, indices, nodes_camera = ds[i]
+        pre = '%s/%d/' % (mode, i)
+        src, dst = [x.cpu().numpy() for x in g.edges()]
+        assert np.array_equal(src, gz[pre + 'src']) and np.array_equal(dst, gz[pre + 'dst'])
+        assert g.number_of_nodes() == rec['n_nodes']
+        assert labels.dtype == torch.float64 and np.array_equal(labels.numpy(), gz[pre + 'labels'])
+        assert indices.dtype == torch.int64 and indices.reshape(-1).tolist() == list(range(rec['n_heads'], rec['n_nodes']))
+        assert nodes_camera == ['' if c < 0 else names[c] for c in gz[pre + 'nodes_camera']]
+        feats = g.ndata['h']
+        assert np.array_equal(feats.cpu().numpy().astype(np.float64).sum(axis=1), gz[pre + 'feat_sum'])
+        if i == 0:
+            assert np.array_equal(feats.cpu().numpy(), gz[pre + 'feats'])
+        H, M = rec['n_heads'], rec['n_nodes'] - rec['n_heads']
+        assert g.edata['rel_type'].tolist() == [0] * H + [1, 1, 1, 1, 2] * M
+        # forward + proposals, as the drivers call them (sm_metrics_without_gt.py:117-135)
+        model.g = g
+        for layer in model.layers:
+            layer.g = g
+        outputs = torch.squeeze(model(feats.float(), g))
+        ref = gz[pre + 'scores']
+        idx = np.arange(H, H + M)
+        got = outputs.cpu().numpy()
+        assert (np.abs(got[idx] - ref[idx]) / np.abs(ref[idx])).max() <= 1e-4, (mode, i)
+        props = smu.get_person_proposal_from_network_output(torch.from_numpy(ref), g, torch.squeeze(indices), nodes_camera, None, 0.5)
+        arr = np.array([[-1 if p[c] is None else p[c] for c in names] for p in props], dtype=np.int32).reshape(-1, len(names))
+        assert np.array_equal(arr, gz[pre + 'proposals']), (mode, i)
+        n_props += len(arr)
+    assert n_props > 0
+    # ---- dgl.batch through the drivers' collate ----
+    nb = gm['modes'][mode]['batch']
+    bg, blabels, bindices = collate([ds[i] for i in range(nb)], dgl, device)
+    src, dst = [x.cpu().numpy() for x in bg.edges()]
+    assert np.array_equal(src, gz['%s/batch/src' % mode]) and np.array_equal(dst, gz['%s/batch/dst' % mode])
+    assert bg.batch_size == nb and bg.number_of_nodes() == sum(r['n_nodes'] for r in recs[:nb])
+    assert bg.batch_num_nodes().tolist() == [r['n_nodes'] for r in recs[:nb]]
+    rel = []
+    for r in recs[:nb]:
+        rel += [0] * r['n_heads'] + [1, 1, 1, 1, 2] * (r['n_nodes'] - r['n_heads'])
+    assert bg.edata['rel_type'].tolist() == rel
+    model.g = bg
+    for layer in model.layers:
+        layer.g = bg
+    bfeats = bg.ndata['h']
+    bout = torch.squeeze(model(bfeats.float(), bg)).cpu().numpy()
+    ref = gz['%s/batch/scores' % mode]
+    bi = bindices.reshape(-1).numpy()
+    assert (np.abs(bout[bi] - ref[bi]) / np.abs(ref[bi])).max() <= 1e-4
+    with pytest.raises(NotImplementedError):
+        smu.get_person_proposal_from_network_output(torch.from_numpy(ref), bg, bindices, [], None, 0.5)
+    with pytest.raises(AttributeError):
+        dgl.graph
