@@ -90,6 +90,7 @@ class DeviceBatch:
     sk_cam: torch.Tensor
     head_off: torch.Tensor
     node_off: torch.Tensor
+    host_offsets: Optional[tuple] = None      # (head_off, node_off) numpy copies, when the batch came from a PackedBatch
 
     @property
     def n_enodes(self):
@@ -165,7 +166,8 @@ class HostBatch:
         pb = self.pb
         cp = lambda t: t.to(device, non_blocking=True)
         return DeviceBatch(pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes,
-                           cp(self.sk_xy), cp(self.sk_vp), cp(self.sk_mask), cp(self.sk_cam), cp(self.head_off), cp(self.node_off))
+                           cp(self.sk_xy), cp(self.sk_vp), cp(self.sk_mask), cp(self.sk_cam), cp(self.head_off), cp(self.node_off),
+                           host_offsets=(np.asarray(pb.head_off, dtype=np.int64), np.asarray(pb.node_off, dtype=np.int64)))
 
 
 class GraphArrays:
@@ -181,7 +183,9 @@ class GraphArrays:
         self.pairs = torch.empty((max(db.n_enodes, 1), 2), **i32)
         self.node_cam = torch.empty(max(db.n_nodes, 1), **i32)
         # True: built from an explicit edge-node list (b200pose_build_graph_pairs: training-side topology, dgl.batch
-        # members) - the kernels that rely on the closed form of the test-mode graph step aside
+        # members) - clustering then takes the first-seen head order from the list instead of the test-mode closed form.
+        # The aggregation kernels only need what both builders guarantee: heads first, three in-edges (h1, h2, self) per
+        # edge-node, in-edges of a node in ascending edge id.
         self.general = False
 
 
@@ -335,8 +339,7 @@ class PosePipeline:
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
                                             1 if layer0 else 0, db.max_heads, db.max_enodes, alpha, act_slope, ptr(raw),
                                             ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
-                                            ptr(scores), 1 if getattr(g, 'general', False) else self.agg_impl, self._stream()),
-              'gat_aggregate')
+                                            ptr(scores), self.agg_impl, self._stream()), 'gat_aggregate')
 
     # ------------------------------------------------------------------ stages
     def gat_forward(self, db: DeviceBatch, g: GraphArrays, x0: Optional[Planes] = None, dense_rows: bool = False,

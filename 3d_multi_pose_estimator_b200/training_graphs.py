@@ -144,13 +144,31 @@ def batch_device(members, device):
     cat = lambda name: torch.cat([getattr(db, name)[: db.n_heads] for db, _ in members])
     head_off, node_off, pairs = [0], [0], []
     for db, arrays in members:
-        ho = db.head_off[: db.n_frames + 1].cpu().numpy().astype(np.int64)
-        no = db.node_off[: db.n_frames + 1].cpu().numpy().astype(np.int64)
+        if db.host_offsets is not None:
+            ho, no = db.host_offsets
+        else:
+            ho = db.head_off[: db.n_frames + 1].cpu().numpy().astype(np.int64)
+            no = db.node_off[: db.n_frames + 1].cpu().numpy().astype(np.int64)
         head_off += list(head_off[-1] + ho[1:])
         node_off += list(node_off[-1] + no[1:])
         pairs.append(arrays.pairs[: db.n_enodes])
     i32 = lambda a: torch.tensor(a, dtype=torch.int32, device=device)
     merged = DeviceBatch(len(head_off) - 1, int(head_off[-1]), int(node_off[-1]),
                          max(db.max_heads for db, _ in members), max(db.max_enodes for db, _ in members),
-                         cat('sk_xy'), cat('sk_vp'), cat('sk_mask'), cat('sk_cam'), i32(head_off), i32(node_off))
+                         cat('sk_xy'), cat('sk_vp'), cat('sk_mask'), cat('sk_cam'), i32(head_off), i32(node_off),
+                         host_offsets=(np.array(head_off, dtype=np.int64), np.array(node_off, dtype=np.int64)))
     return merged, torch.cat(pairs) if pairs else torch.empty((0, 2), dtype=torch.int32, device=device)
+
+
+def batch_packed(graphs: List[Tuple[PackedBatch, np.ndarray]]) -> Tuple[PackedBatch, np.ndarray]:
+    """The same union on the host, over packed graphs that have not been uploaded yet: one PackedBatch whose "frames" are
+    the graphs, and the concatenated graph-local edge-node list - the ingest format of a validation batch."""
+    head_off, node_off = [0], [0]
+    for pb, _ in graphs:
+        head_off += list(head_off[-1] + np.asarray(pb.head_off[1:], dtype=np.int64))
+        node_off += list(node_off[-1] + np.asarray(pb.node_off[1:], dtype=np.int64))
+    cat = lambda name: np.concatenate([getattr(pb, name) for pb, _ in graphs])
+    merged = PackedBatch(n_frames=len(head_off) - 1, sk_xy=cat('sk_xy'), sk_vp=cat('sk_vp'), sk_mask=cat('sk_mask'), sk_cam=cat('sk_cam'),
+                         head_off=np.array(head_off, dtype=np.int32), node_off=np.array(node_off, dtype=np.int32),
+                         max_heads=max(pb.max_heads for pb, _ in graphs), max_enodes=max(pb.max_enodes for pb, _ in graphs))
+    return merged, np.concatenate([p for _, p in graphs]).astype(np.int32).reshape(-1, 2)

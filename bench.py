@@ -178,7 +178,7 @@ def main():
     ap.add_argument('--config', default='panoptic')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
-    ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation'],
+    ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
     ap.add_argument('--latency-frames', type=int, default=200, help='single-frame calls timed for p50_frame_latency_ms')
@@ -194,6 +194,8 @@ def main():
 
     if args.workload == 'triangulation':
         return triangulation_workload(args, rank, world, local_rank)
+    if args.workload == 'train_batch':
+        return train_batch_workload(args, rank, world, local_rank)
     # ------------------------------------------------------------------ reference arm (CPU port)
     if args.impl == 'reference':
         if rank != 0:
@@ -454,6 +456,138 @@ def triangulation_workload(args, rank, world, local_rank):
                          'frac': (in_bytes + out_bytes) / ms / 1e6 / 6471.1, 'traffic': None,
                          'note': 'ALU-bound kernel (pairwise 4x4 solves), HBM fraction reported for completeness'},
             'cpu_baseline': {'value': cpu, 'unit': 'persons/s', 'cores': 1, 'kind': 'port', 'sample': '%d persons, one process' % n}}
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def train_batch_workload(args, rank, world, local_rank):
+    """SURVEY.md 8f-3, forward only: the validation pass of skeleton_matching/train_skeleton_matching.py:88-110 - graphs of
+    process_training (graph_generator.py:672-810) merged with dgl.batch (:80) and pushed through GAT2. One step = one
+    block-diagonal batch of --frames graphs (the reference batches 15; a batch here is as large as the caller likes):
+    edge/CSR build from the explicit edge-node lists, head features, 5 GAT layers. Dataset synthesis (sampling, packing)
+    is outside the timed region, as the reference builds its datasets before the loop (:134-141)."""
+    import random
+    import torch
+    pkg = importlib.import_module('3d_multi_pose_estimator_b200')
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    pm = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+    tg = importlib.import_module('3d_multi_pose_estimator_b200.training_graphs')
+    cfg = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
+    gat, mlp = load_weights(args.config, cfg)
+    G = args.frames
+    n_files, per_file = 4, 24
+    files = [[synth.make_frame(cfg, 7000 + 100 * f + t, 1, drop_joint_p=0.1, drop_view_p=0.1) for t in range(per_file)] for f in range(n_files)]
+    random.seed(rank)
+    inputs, indices = tg.load_inputs(files, 'dev', cfg.used_pe_names, random)          # 'dev': with the view augmentation
+    built = []
+    for mp in tg.sample_sets(inputs, indices, [0.8, 0.6, 0.7, 0.5], 10 ** 9, random):
+        b = tg.training_graph_inputs(mp, cfg)
+        if b is not None:
+            built.append(b)
+        if len(built) >= min(G, 256):
+            break
+    graphs = [(built[i % len(built)][0], built[i % len(built)][1]) for i in range(G)]   # cycled up to the batch size
+    pb, pairs = tg.batch_packed(graphs)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    pipe = pm.PosePipeline(cfg, gat, mlp, device=dev)
+    hb = pm.HostBatch(pb)
+    h_pairs = torch.from_numpy(pairs).pin_memory()
+    db = hb.to_device(dev)
+    d_pairs = h_pairs.to(dev)
+
+    def step(db, d_pairs):
+        g = pipe.build_graph_pairs(db, d_pairs, with_coo=False)
+        return pipe.gat_forward(db, g)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        step(db, d_pairs)
+    torch.cuda.synchronize()
+    l0 = pipe.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for a, b in ev:
+        flush.fill_(1); a.record(); scores = step(db, d_pairs); b.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = (pipe.launches - l0) // args.steps
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # per-class time (CUDA events around the launches of one extra step)
+    acc = {}
+    orig_linear, orig_agg = pipe.linear, pipe.aggregate
+
+    def timed(name, fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(*a, **k); e1.record()
+            acc.setdefault(name, []).append((e0, e1))
+            return r
+        return w
+    pipe.linear, pipe.aggregate = timed('gat_projection_gemm', orig_linear), timed('edge_softmax_aggregate', orig_agg)
+    flush.fill_(1)
+    step(db, d_pairs)
+    torch.cuda.synchronize()
+    pipe.linear, pipe.aggregate = orig_linear, orig_agg
+    kern = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in acc.items()}
+    # end to end: packed host batch -> device -> scores back on the host
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2 = hb.to_device(dev)
+        s2 = step(d2, h_pairs.to(dev, non_blocking=True))
+        host_scores = s2.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    # CPU port of the same step on a bounded sample: batches of 15 graphs as the reference's loader makes them
+    from oracle import pose_oracle as O
+    tabs = O.CameraTables(cfg)
+    gat_np = {k: v.numpy() for k, v in gat.items()}
+    random.seed(rank)
+    inputs, indices = O.load_training_inputs(files, 'dev', cfg.used_pe_names, random)
+    sets = []
+    for mp in O.training_samples(inputs, indices, [0.8, 0.6, 0.7, 0.5], 10 ** 9, random):
+        sets.append(mp)
+        if len(sets) >= 60:
+            break
+    ogs = [g for g in (O.build_training_graph(mp, tabs) for mp in sets) if g is not None]
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < min(args.cpu_budget, 15.0):
+        members = [ogs[(n + i) % len(ogs)] for i in range(15)]
+        bg = O.batch_graphs(members)
+        O.gat_forward(gat_np, bg['feats'], bg['src'], bg['dst'])
+        n += 15
+    cpu = n / (time.perf_counter() - t0)
+    W = importlib.import_module('3d_multi_pose_estimator_b200.weights')
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    agg_bytes, gat_flops, _ = algorithmic_work(pb, W.gat_layer_dims(cfg.n_features_sm), [], 0)
+    tc_peak, hbm_peak = peaks.get('bf16_tflops_sustained', 1400.0), peaks.get('hbm_gbs', 6650.0)
+    kernels = [{'kernel': 'gat_projection_gemm', 'ms_per_step': kern.get('gat_projection_gemm'), 'bound': 'tensor',
+                'achieved': 3 * gat_flops / kern['gat_projection_gemm'] / 1e9, 'peak': tc_peak, 'unit': 'TFLOP/s'},
+               {'kernel': 'edge_softmax_aggregate', 'ms_per_step': kern.get('edge_softmax_aggregate'), 'bound': 'hbm',
+                'achieved': agg_bytes / kern['edge_softmax_aggregate'] / 1e6, 'peak': hbm_peak, 'unit': 'GB/s'}]
+    for k in kernels:
+        k['frac'] = k['achieved'] / k['peak']
+    dom = max(kernels, key=lambda k: k['ms_per_step'])
+    line = {'metric': 'graphs/sec (process_training graphs, dgl.batch + GAT2 forward, %d-graph batch)' % G, 'value': G / ms * 1e3, 'unit': 'graphs/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate', 'data': 'synthetic',
+            'config': {'workload': 'training-side validation batch: %d process_training graphs (%d nodes, %d edges) merged block-diagonally, '
+                                   'edge/CSR build + features + 5 GAT layers, forward only' % (G, pb.n_nodes, pb.n_edges),
+                       'camera_config': args.config, 'graphs_per_step': G, 'l2': 'L2 flushed (256 MiB write) between timed iterations'},
+            'e2e': {'value': G / e2e_ms * 1e3, 'unit': 'graphs/s', 'h2d_bytes_per_step': int(hb.nbytes() + h_pairs.numel() * 4),
+                    'd2h_bytes_per_step': int(host_scores.numel() * 4), 'ms_per_step': e2e_ms},
+            'gpu_launches': launches, 'clocks': sampler.summary(),
+            'roofline': {'kernel': dom['kernel'], 'bound': dom['bound'], 'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': dom['unit'],
+                         'frac': dom['frac'], 'traffic': None, 'peak_source': 'measured' if peaks else 'fallback'},
+            'kernels': kernels,
+            'cpu_baseline': {'value': cpu, 'unit': 'graphs/s', 'cores': 1, 'kind': 'port',
+                             'sample': '%d graphs in batches of 15 (the reference loader\'s batch size), one process' % n}}
     if rank == 0:
         print(json.dumps(line))
 

@@ -69,9 +69,9 @@ def test_small_helpers(mods):
 def test_out_of_scope_modes_fail_loudly(mods):
     gg = mods['graph_generator']
     with pytest.raises(NotImplementedError):
-        gg.MergedMultipleHumansDataset({}, mode='train', alt='3')
-    with pytest.raises(NotImplementedError):
         gg.MergedMultipleHumansDataset({}, mode='test', alt='1')
+    with pytest.raises(NotImplementedError):
+        gg.MergedMultipleHumansDataset({}, mode='train', alt='2')
     with pytest.raises(SystemExit):
         gg.MergedMultipleHumansDataset({}, mode='test', alt=None)
     with pytest.raises(NotImplementedError):
@@ -79,3 +79,21 @@ def test_out_of_scope_modes_fail_loudly(mods):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):                       # no CPU fallback
             gg.MergedMultipleHumansDataset({'trackera': ['[{"1": [1, 5.0, 5.0, 1, 1]}]', 0.0]}, mode='test', alt='3')
+
+
+def test_dgl_drop_in_offers_batch_only(mods):
+    """`import dgl` resolves to the drop-in's module (train_skeleton_matching.py:11,80; sm_metrics_without_gt.py:6,60):
+    `batch` for the B200 graphs, a clear error for everything else."""
+    import importlib
+    import sys
+    sys.modules.pop('dgl', None)
+    dgl = importlib.import_module('dgl')
+    assert dgl.__file__.startswith(dropin_env.SHADOW)
+    assert list(inspect.signature(dgl.batch).parameters)[0] == 'graphs'
+    with pytest.raises(ValueError):
+        dgl.batch([])
+    with pytest.raises(TypeError):
+        dgl.batch([object()])
+    with pytest.raises(AttributeError):
+        dgl.graph
+    sys.modules.pop('dgl', None)
