@@ -113,3 +113,73 @@ def test_training_dataset_batch_and_forward_against_reference(mode, tmp_path):
         smu.get_person_proposal_from_network_output(torch.from_numpy(ref), bg, bindices, [], None, 0.5)
     with pytest.raises(AttributeError):
         dgl.graph
+
+
+def test_many_person_training_graph_and_mixed_batch_vs_oracle():
+    """A 12-sample tuple (about 60 heads, ordered pairs: ~2900 edge-nodes, in-degree ~100 - the large-frame aggregation
+    kernel and the 256-thread clustering plan on an explicit-list graph) against the oracle restatement; then that graph,
+    a test-mode graph and a small training graph in one dgl.batch: member scores unchanged by the batching."""
+    from oracle import pose_oracle as O
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    mods = dropin_env.activate(cfg)
+    dgl = importlib.import_module('dgl')
+    gg, smu, rt = mods['graph_generator'], mods['skeleton_matching_utils'], mods['rt']
+    tg = rt.training_graphs
+    ctx = rt.context()
+    gat_state, _ = helpers.golden_weights('panoptic')
+    model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
+                              torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
+    model.load_state_dict(gat_state)
+    model = model.to('cuda')
+    synth = helpers.synth
+    samples = [synth.make_frame(cfg, 31000 + i, 1 + (i % 3 == 0), drop_joint_p=0.2) for i in range(12)]
+    pb, pairs, labels = tg.training_graph_inputs(samples, cfg)
+    assert pb.n_heads > 48 and pb.max_heads > pb.n_heads               # in-degree above the head count: ordered pairs
+    db = rt.pipeline.HostBatch(pb).to_device(ctx.device)
+    arrays = ctx.build_graph_pairs(db, pairs, with_coo=True)
+    big = gg.B200Graph(db, arrays, ctx.node_features_f32(db))
+    og = O.build_training_graph(samples, O.CameraTables(cfg))
+    src, dst = [x.cpu().numpy() for x in big.edges()]
+    assert np.array_equal(src, og['src']) and np.array_equal(dst, og['dst'])
+    assert np.array_equal(big.ndata['h'].cpu().numpy(), og['feats']) and np.array_equal(labels, og['labels'])
+    row_ptr, col = arrays.row_ptr.cpu().numpy(), arrays.col.cpu().numpy()
+    order = np.argsort(og['dst'], kind='stable')                        # CSR by destination, in-edges in ascending edge id
+    assert np.array_equal(col[: len(order)], og['src'][order])
+    assert np.array_equal(np.diff(row_ptr), np.bincount(og['dst'], minlength=og['n_nodes']))
+
+    def forward(g):
+        model.set_g(g)
+        return torch.squeeze(model(g.ndata['h'].float(), g)).cpu().numpy()
+    s_big = forward(big)
+    ref = O.gat_forward(helpers.np_state(gat_state), og['feats'], og['src'], og['dst'])
+    idx = og['indices']
+    assert (np.abs(s_big[idx] - ref[idx]) / np.abs(ref[idx])).max() <= 1e-4
+    rng = np.random.default_rng(3)
+    H = og['n_heads']
+    for sc in (ref, rng.random(len(ref)).astype(np.float32), (0.5 + 0.5 * rng.random(len(ref))).astype(np.float32),
+               (np.round(rng.random(len(ref)) * 4) / 4).astype(np.float32)):
+        props = smu.get_person_proposal_from_network_output(torch.from_numpy(sc), big, None, None, None, 0.5)
+        arr = np.array([[-1 if p[c] is None else p[c] for c in cfg.used_sm_names] for p in props], dtype=np.int32).reshape(-1, cfg.V_sm)
+        assert np.array_equal(arr, O.cluster(sc, og['pairs'], og['nodes_camera'][:H], cfg.V_sm, H))
+    # ---- mixed batch: explicit-list graphs and a closed-form test-mode graph ----
+    frame = meta['frames'][helpers.graph_cases('panoptic')[0]]
+    pi = {c: [frame[c][0], 0.0] for c in frame if json.loads(frame[c][0])}
+    test_g = gg.MergedMultipleHumansDataset(pi, mode='test', limit=10000, debug=True, alt='3', verbose=False).graphs[0]
+    small = tg.training_graph_inputs(samples[:2], cfg)
+    sdb = rt.pipeline.HostBatch(small[0]).to_device(ctx.device)
+    small_g = gg.B200Graph(sdb, ctx.build_graph_pairs(sdb, small[1]), ctx.node_features_f32(sdb))
+    members = [small_g, test_g, big]
+    singles = [forward(g) for g in members]
+    bg = dgl.batch(members)
+    sb = forward(bg)
+    assert bg.number_of_nodes() == sum(g.number_of_nodes() for g in members)
+    off = 0
+    bsrc, bdst = [x.cpu().numpy() for x in bg.edges()]
+    e_off = 0
+    for g, s in zip(members, singles):
+        n, e = g.number_of_nodes(), g.number_of_edges()
+        gs, gd = [x.cpu().numpy() for x in g.edges()]
+        assert np.array_equal(bsrc[e_off:e_off + e], gs + off) and np.array_equal(bdst[e_off:e_off + e], gd + off)
+        assert (np.abs(sb[off:off + n] - s) / np.abs(s)).max() <= 2e-5
+        off += n
+        e_off += e
