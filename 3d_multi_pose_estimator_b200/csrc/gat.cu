@@ -1123,9 +1123,13 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.dbg = g_debug_flags;
     p.stage_cap = 0; p.edge_units = 0; p.head_units = 0;
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
+    // A live frame or two (fewer frames than an eighth of the SMs): one CTA per frame would leave the GPU idle and pay one
+    // CTA's serial latency (25 us per layer for a Panoptic frame); the large-frame kernel spreads a frame over its edge and
+    // head units (8 CTAs for 20 heads / 160 edge-nodes: 10-16 us), so tiny batches take it.
+    const bool tiny_batch = impl == 0 && n_frames * 8 <= 148 && 3 * heads <= 32;
     // ---- frame-resident kernel: one CTA per frame, whenever the frame plan fits in shared memory ----
-    if (impl == 0 && max_heads_per_frame > 0 && max_enodes_per_frame > 0 && max_heads_per_frame <= kFrameOwn * kFrameWarps &&
-        HD / vec <= 32 * 4) {
+    if (((impl == 0 && !tiny_batch) || impl == 3) && max_heads_per_frame > 0 && max_enodes_per_frame > 0 &&
+        max_heads_per_frame <= kFrameOwn * kFrameWarps && HD / vec <= 32 * 4) {
         const FramePlan f = frame_plan(max_heads_per_frame, max_enodes_per_frame, HD, heads, ldz);
         const size_t smem_frame = (size_t)f.total_floats * sizeof(float);
         if (smem_frame <= 220 * 1024) {
@@ -1141,13 +1145,19 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
             return launch_frame(gat_aggregate_frame_kernel<1, 4>);
         }
     }
-    B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel) or 2 (large-frame kernel)");
+    if (impl == 3) {
+        set_error("gat_aggregate: impl 3 (frame-resident kernel) needs frames of at most %d heads whose plan fits in shared memory "
+                  "(%d heads, %d edge-nodes per frame here)", kFrameOwn * kFrameWarps, max_heads_per_frame, max_enodes_per_frame);
+        return B200POSE_E_UNSUPPORTED;
+    }
+    B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel), 2 (large-frame kernel) or 3 (frame-resident kernel, "
+                 "frames of at most 32 heads whose plan fits in shared memory)");
     // ---- gather kernel: work unit = (frame, chunk of destination nodes). ---- In-degree of a head is 1 + H_b - n_g <= H_b and of an
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
     // ---- large frames: fused edge-chunk + head units, every z row read from HBM once ----
-    if (((impl == 0 && mh > 48) || impl == 2) && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
+    if (((impl == 0 && (mh > 48 || tiny_batch)) || impl == 2) && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
         p.stage_cap = kLargeStageCap;
         p.edge_units = ceil_div(max_enodes_per_frame, kLargeChunk);
         p.head_units = ceil_div(mh, kLargeHeads);

@@ -1024,9 +1024,14 @@ __global__ void __launch_bounds__(256) gemm_split_simt_kernel(const GemmParams p
 // in shared memory, and reduces across lanes. Evaluates (a_hi + a_lo) . (w_hi + w_lo) in fp32, i.e. the same
 // product as the 3-term tensor-core path plus the (negligible) lo*lo term.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSmallM = 8;
-constexpr int kSmallWarps = 8;
+constexpr int kSmallM = 16;            // rows the weight-streaming kernel takes (8 accumulators per lane below 9 rows, 16 above)
+constexpr int kSmallWarps = 16;
 
+// Few rows (a live frame has a handful of persons): the layer is a stream of its weights - 116 MB of hi/lo planes for the
+// pose MLP - against which a tensor-core tile would be 98 % padding. A is staged once per CTA as fp32 (hi + lo, exact:
+// the planes are the split of an fp32 value) with 16-byte loads; every warp then streams whole weight rows (one output
+// column each) with 16-byte loads, 8 in flight per lane, and the 32 lanes' partial dot products meet in a shuffle tree.
+template <int MMAX>
 __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
     const __nv_bfloat16* __restrict__ a_hi, const __nv_bfloat16* __restrict__ a_lo, int lda,
     const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo, int ldw,
@@ -1034,17 +1039,31 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
     float* __restrict__ out_f32, int ld_out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ld_planes)
 {
     extern __shared__ __align__(16) float As[];              // [M][kpad]
-    for (int i = threadIdx.x; i < M * kpad; i += blockDim.x) {
-        const int m = i / kpad, k = i - m * kpad;
-        As[i] = __bfloat162float(a_hi[(size_t)m * lda + k]) + __bfloat162float(a_lo[(size_t)m * lda + k]);
+    {
+        const int vec_per_row = kpad >> 3;                    // kpad is a multiple of 64, lda of 8
+        for (int i = threadIdx.x; i < M * vec_per_row; i += blockDim.x) {
+            const int m = i / vec_per_row, k8 = i - m * vec_per_row;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(a_hi + (size_t)m * lda) + k8);
+            const uint4 l = __ldg(reinterpret_cast<const uint4*>(a_lo + (size_t)m * lda) + k8);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                v[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                v[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+            }
+            float4* d = reinterpret_cast<float4*>(As + (size_t)m * kpad + 8 * k8);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_cols = out_hi ? ld_planes : N;               // plane padding columns are written as zeros
     for (int n = blockIdx.x * kSmallWarps + warp; n < n_cols; n += gridDim.x * kSmallWarps) {
-        float acc[kSmallM];
+        float acc[MMAX];
 #pragma unroll
-        for (int m = 0; m < kSmallM; ++m) acc[m] = 0.f;
+        for (int m = 0; m < MMAX; ++m) acc[m] = 0.f;
         if (n < N) {
             const uint4* wh = reinterpret_cast<const uint4*>(w_hi + (size_t)n * ldw);
             const uint4* wl = reinterpret_cast<const uint4*>(w_lo + (size_t)n * ldw);
@@ -1059,7 +1078,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
                     wv[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
                 }
 #pragma unroll
-                for (int m = 0; m < kSmallM; ++m) {
+                for (int m = 0; m < MMAX; ++m) {
                     if (m < M) {
                         const float4 x0 = *reinterpret_cast<const float4*>(As + (size_t)m * kpad + k0);
                         const float4 x1 = *reinterpret_cast<const float4*>(As + (size_t)m * kpad + k0 + 4);
@@ -1072,13 +1091,13 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
             }
         }
 #pragma unroll
-        for (int m = 0; m < kSmallM; ++m)
+        for (int m = 0; m < MMAX; ++m)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
         if (lane < M) {
             float v = 0.f;
 #pragma unroll
-            for (int m = 0; m < kSmallM; ++m) if (m == lane) v = acc[m];
+            for (int m = 0; m < MMAX; ++m) if (m == lane) v = acc[m];
             if (n < N) v = leaky(v + (bias ? __ldg(bias + n) : 0.f), slope) * out_scale; else v = 0.f;
             if (out_f32 && n < N) out_f32[(size_t)lane * ld_out + n] = v;
             if (out_hi) {
@@ -1210,20 +1229,24 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
-    if ((impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 160 * 1024) {   // weight-streaming small-M kernel
+    if ((impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
+        // weight-streaming small-M kernel: as many CTAs as fit at once (the A staging is per CTA), every warp takes columns
         const size_t smem = (size_t)m * kpad * sizeof(float);
         const int cols = out_hi ? ld_planes : n;
         int ctas = ceil_div(cols, kSmallWarps);
-        const int cap = num_sms() * 4;
+        const int cap = num_sms() * (smem <= 100 * 1024 ? 2 : 1);
         if (ctas > cap) ctas = cap;
-        B2_CHECK_CUDA(cudaFuncSetAttribute(gemm_small_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_small_m_kernel<<<ctas, kSmallWarps * 32, smem, st>>>(p.a_hi, p.a_lo, lda, p.w_hi, p.w_lo, ldw, bias, m, n, kpad, slope, out_scale,
-                                                                  out_f32, ld_out, p.out_hi, p.out_lo, ld_planes);
-        B2_CHECK_LAUNCH();
-        return B200POSE_OK;
+        auto launch_small = [&](auto kern) -> int {
+            B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<ctas, kSmallWarps * 32, smem, st>>>(p.a_hi, p.a_lo, lda, p.w_hi, p.w_lo, ldw, bias, m, n, kpad, slope, out_scale,
+                                                       out_f32, ld_out, p.out_hi, p.out_lo, ld_planes);
+            B2_CHECK_LAUNCH();
+            return B200POSE_OK;
+        };
+        return m <= 8 ? launch_small(gemm_small_m_kernel<8>) : launch_small(gemm_small_m_kernel<16>);
     }
     B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5 || impl == 6 || impl == 7, "linear: impl must be 0 (auto), 1 (simt self-test), 2 (manual-fill "
-                 "self-test), 3 (v1), 4 (persistent, single CTA), 5 (CTA pairs), 6 (wide CTA pairs) or 7 (small-m kernel when m <= 8)");
+                 "self-test), 3 (v1), 4 (persistent, single CTA), 5 (CTA pairs), 6 (wide CTA pairs) or 7 (small-m kernel when m <= 16)");
     // ---- persistent kernel ----
     if (out_f32) B2_CHECK_ARG(ld_out % 4 == 0 && ((uintptr_t)out_f32 % 16 == 0), "linear: out_f32 needs ld_out %% 4 == 0 and 16-byte alignment (TMA store)");
     if (out_hi) B2_CHECK_ARG(((uintptr_t)out_hi % 16 == 0) && ((uintptr_t)out_lo % 16 == 0), "linear: output planes must be 16-byte aligned");

@@ -8,6 +8,7 @@ through the C ABI (include/b200pose.h). There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import collections
 import dataclasses
 from typing import Dict, List, Optional
 
@@ -598,6 +599,82 @@ class PosePipeline:
             out['joints'] = out_bufs['joints'][:P_tot]
             out['valid'] = out_bufs['valid'][:P_tot]
         return out
+
+    # ------------------------------------------------------------------ low-latency path: one CUDA graph per batch shape
+    def _stage_b_static(self, db: DeviceBatch, res: dict, p_max: int):
+        """Stage 3 without the person-count readback: every launch is sized for p_max persons (a person needs two views,
+        so p_max = heads // 2 bounds the count); rows past the real count keep person_sk = -1, encode to zero rows with
+        valid = 0 and are dropped on the host. This is what lets the whole step live in one CUDA graph."""
+        Cn = self.cfg.n_cameras
+        person_sk = torch.full((p_max, Cn), -1, dtype=torch.int32, device=self.device)
+        person_frame = torch.zeros(p_max, dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
+                                             ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
+                                             ptr(person_sk), ptr(person_frame), self._stream()), 'gather_persons')
+        x, valid, _ = self.encode_persons(db, p_max, person_sk)
+        joints = self.mlp_forward(x, p_max)
+        return person_sk, valid, joints
+
+    def infer_host_graph(self, hb: HostBatch, max_cached: int = 64):
+        """The end-to-end call for live frames (one frame, or a few, per call): same inputs and outputs as infer_host, but
+        the ~30 launches, the input copies and the result copies of a batch SHAPE (frames, heads, nodes) are captured once
+        into a CUDA graph and replayed, and nothing in the step waits for the host - the person count is read with the
+        results. A rig that sees the same number of skeletons per camera from frame to frame replays one graph; a new
+        shape costs one eager run plus one capture. Needs the MLP weights (the full path)."""
+        if self.mlp is None or self.gat is None:
+            raise RuntimeError('infer_host_graph needs both models')
+        pb = hb.pb
+        if pb.n_heads == 0 or pb.n_nodes == pb.n_heads:          # nothing to match: the eager path handles the degenerate shapes
+            return self.infer_host(hb)
+        key = (pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes)
+        cache = self.__dict__.setdefault('_graphs', collections.OrderedDict())
+        ent = cache.get(key)
+        cur = torch.cuda.current_stream(self.device)
+        names = ('sk_xy', 'sk_vp', 'sk_mask', 'sk_cam', 'head_off', 'node_off')
+        if ent is None:
+            self.infer_host(hb)                                 # eager warm-up of this shape: workspaces, function attributes
+            pin = lambda t: torch.empty_like(t).pin_memory()
+            h_in = {n: pin(getattr(hb, n)) for n in names}
+            d_in = {n: torch.empty_like(getattr(hb, n), device=self.device) for n in names}
+            db = DeviceBatch(pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes, d_in['sk_xy'], d_in['sk_vp'],
+                             d_in['sk_mask'], d_in['sk_cam'], d_in['head_off'], d_in['node_off'])
+            p_max = max(pb.n_heads // 2, 1)
+            n_out = self.mlp[-1]['n']
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            h_out = dict(n_persons=mk((pb.n_frames,), torch.int32), person_off=mk((pb.n_frames + 1,), torch.int32),
+                         person_sk=mk((p_max, self.cfg.n_cameras), torch.int32), joints=mk((p_max, n_out), torch.float32),
+                         valid=mk((p_max,), torch.uint8))
+            for n in names:
+                h_in[n].copy_(getattr(hb, n))
+            graph = torch.cuda.CUDAGraph()
+            cur.synchronize()
+            with torch.cuda.graph(graph):
+                for n in names:
+                    d_in[n].copy_(h_in[n], non_blocking=True)
+                res = self.stage_a(db)
+                person_sk, valid, joints = self._stage_b_static(db, res, p_max)
+                h_out['n_persons'].copy_(res['n_persons'], non_blocking=True)
+                h_out['person_off'].copy_(res['person_off'], non_blocking=True)
+                h_out['person_sk'].copy_(person_sk, non_blocking=True)
+                h_out['joints'].copy_(joints, non_blocking=True)
+                h_out['valid'].copy_(valid, non_blocking=True)
+            # the graph bakes in device addresses: keep everything it touches alive (workspaces are replaced when a
+            # larger batch makes them grow)
+            ent = dict(graph=graph, h_in=h_in, h_out=h_out, keep=(d_in, db, res, person_sk, valid, joints, list(self._ws.values())))
+            cache[key] = ent
+            while len(cache) > max_cached:
+                cache.popitem(last=False)
+        else:
+            cache.move_to_end(key)
+            for n in names:
+                ent['h_in'][n].copy_(getattr(hb, n))
+        ent['graph'].replay()
+        cur.synchronize()
+        h_out = ent['h_out']
+        P = int(h_out['person_off'][pb.n_frames])
+        return dict(n_persons=h_out['n_persons'], person_off=h_out['person_off'], person_sk=h_out['person_sk'][:P],
+                    n_persons_total=P, joints=h_out['joints'][:P], valid=h_out['valid'][:P])
 
     def infer_host_stream(self, batches):
         """Generator over host batches: yields the host results of each batch, in order. The host->device copy of

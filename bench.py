@@ -312,7 +312,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---- single-frame latency: one frame per call through the same public host API (rank 0 only)
-    p50_ms = None
+    p50_ms = p50_eager_ms = p99_ms = None
     if rank == 0 and args.latency_frames > 0:
         singles = [pm.HostBatch(pb.slice(i, i + 1)) for i in range(min(32, pb.n_frames))]
         lat = []
@@ -323,7 +323,17 @@ def main():
             pipe.infer_host(h1, n_chunks=1)
             if i >= 20:
                 lat.append(time.perf_counter() - t0)
+        p50_eager_ms = 1e3 * float(np.median(lat))
+        lat = []
+        for i in range(args.latency_frames + 40):           # the same frames through the CUDA-graph path (one graph per shape)
+            h1 = singles[i % len(singles)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.infer_host_graph(h1)
+            if i >= 40:
+                lat.append(time.perf_counter() - t0)
         p50_ms = 1e3 * float(np.median(lat))
+        p99_ms = 1e3 * float(np.percentile(lat, 99))
     e2e_ms = 1e3 * float(np.mean(e2e_t))
     d2h = sum(v.numel() * v.element_size() for v in out.values() if hasattr(v, 'numel'))
     # ---- per-kernel-class timing for the roofline (separate pass, CUDA events around each class)
@@ -386,7 +396,9 @@ def main():
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
                 'cpu_baseline': cpu_line,
                 'persons_found_per_frame': P / args.frames,
-                'p50_frame_latency_ms': p50_ms}
+                'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
+                'latency_note': 'one frame per call, host buffers in / host results out: infer_host_graph (CUDA graph per batch '
+                                'shape) and, for comparison, the eager infer_host'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

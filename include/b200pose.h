@@ -120,7 +120,7 @@ int b200pose_node_features(int32_t n_frames, int32_t n_heads_total, int32_t n_no
  * out_scale multiplies the result after the activation (x10 of metrics_from_model.py:282).
  * impl: 0 = persistent tcgen05 + TMA tensor-core kernel (the product path; CTA pairs with cta_group::2 MMAs and
  * 256-row tiles, single CTAs for tiny m; full-width single-tile pairs for tall projections with 256 < n <= 512);
- * m <= 8 rows (the pose MLP of a single frame) go to a weight-streaming kernel instead: one warp per output column, every
+ * m <= 16 rows (the pose MLP of a single frame) go to a weight-streaming kernel instead: one warp per output column, every
  * hi/lo weight read once by all SMs; 4 / 5 / 6 / 7 force single CTAs / CTA pairs / wide CTA pairs / the small-m kernel (A/B runs);
  * 1 = fp32 SIMT kernel, 2 = tcgen05 kernel with tiles filled by ordinary stores, 3 = first one-tile-per-CTA
  * kernel - these three exist only for the kernel self-test.
@@ -150,8 +150,9 @@ int b200pose_split_planes(const float* x, int32_t rows, int32_t cols, int32_t ld
  *   max_heads_per_frame / max_enodes_per_frame size the shared-memory plan of a frame (0 = unknown);
  *   impl: 0 = frame-resident column-parallel kernel when a frame's plan fits in shared memory (<= 32 heads per
  *         frame), the large-frame kernel (edge-node chunks with staged head rows + head destinations over cp.async
- *         row rings) above 48 heads per frame, else the warp-per-destination gather kernel; 1 = always the gather
- *         kernel, 2 = always the large-frame kernel where its plan fits (A/B runs);
+ *         row rings) above 48 heads per frame and for batches of a few frames (fewer than SMs / 8: one CTA per frame
+ *         would pay a single CTA's latency), else the warp-per-destination gather kernel; 1 = always the gather kernel,
+ *         2 = the large-frame kernel where its plan fits, 3 = the frame-resident kernel (error if the plan does not fit);
  *   out[v,h,:] = sum_u softmax_u(LeakyReLU_alpha(a1[u,h] + a2[v,h])) * ft2[u,h,:]
  * Outputs (any may be null): raw_f32 [N_tot, heads*dim] (the layer output, gat2.py:68),
  *   planes act_hi/lo [N_tot, ld_planes] = LeakyReLU_{act_slope}(out) (GAT2.forward :141-142),
