@@ -203,6 +203,7 @@ class PosePipeline:
         if not torch.cuda.is_available():
             raise RuntimeError('PosePipeline needs a CUDA device (sm_100a); there is no CPU fallback')
         self.device = torch.device(device if device is not None else 'cuda')
+        self._dev_index = None
         self.cfg = cfg
         self.L = _lib.lib()
         self.gemm_impl = gemm_impl
@@ -240,7 +241,11 @@ class PosePipeline:
 
     # ------------------------------------------------------------------ weights
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # the raw cudaStream_t of torch's current stream on this device; the public torch.cuda.current_stream() costs
+        # ~17 us per call (device-index resolution), which at 30 launches is most of a live frame's host time
+        if self._dev_index is None:
+            self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
 
     def prepare_gat(self, st):
         """Split every projection into planes; fold the attention vectors into fc2 as 2*heads extra output

@@ -78,7 +78,11 @@ class GAT2(nn.Module):
             raise NotImplementedError('B200 GAT2: num_classes must be 1')
 
     def _weights(self, ctx):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        plist = self.__dict__.get('_plist')
+        if plist is None:                       # the module-tree walk of parameters() is most of a call: done once
+            plist = list(self.parameters())     # (.to() and load_state_dict keep the Parameter objects)
+            self.__dict__['_plist'] = plist
+        key = tuple((p.data_ptr(), p._version) for p in plist)
         if self._prepared is None or key != self._prepared_key:
             self._prepared = ctx.prepare_gat({k: v for k, v in self.state_dict().items()})
             self._prepared_key = key

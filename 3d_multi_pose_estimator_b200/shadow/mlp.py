@@ -24,7 +24,11 @@ class PoseEstimatorMLP(nn.Module):
 
     def forward(self, x):
         ctx = rt.context()
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        plist = self.__dict__.get('_plist')
+        if plist is None:                       # the module-tree walk of parameters() is done once
+            plist = list(self.parameters())
+            self.__dict__['_plist'] = plist
+        key = tuple((p.data_ptr(), p._version) for p in plist)
         if self._prepared is None or key != self._prepared_key:
             self._prepared = ctx.prepare_mlp({k: v for k, v in self.state_dict().items()})
             self._prepared_key = key

@@ -43,13 +43,16 @@ class PoseEstimatorDataset(torch.utils.data.Dataset):
             raise Exception(f'Invalid dataset input {type(input_data)} for json_files. Only list and dict are allowed.')
         ctx = rt.context()
         cfg = ctx.cfg
-        indices = get_skeleton_indices(input_data)
         person = {}
-        for c in input_data:                                     # one skeleton per camera (:249-254)
-            if c in cfg.used_pe_names:
+        for c in input_data:                                     # one skeleton per camera (:249-254): the one
+            if c in cfg.used_pe_names:                           # get_skeleton_indices picks, each JSON string parsed once
                 skeletons = json.loads(input_data[c][0])
                 if skeletons:
-                    person[c] = skeletons[indices[c]]
+                    best, best_n = 0, -1
+                    for i, s in enumerate(skeletons):
+                        if len(s) > best_n:
+                            best, best_n = i, len(s)
+                    person[c] = skeletons[best]
         x, valid = ctx.encode_person_dicts([person])
         if valid[0]:
             self.data.append(x[0])

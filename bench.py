@@ -334,6 +334,14 @@ def main():
                 lat.append(time.perf_counter() - t0)
         p50_ms = 1e3 * float(np.median(lat))
         p99_ms = 1e3 * float(np.percentile(lat, 99))
+    # ---- the reference driver's own per-frame loop on the drop-in modules (JSON strings in, python dicts out):
+    # what an unmodified test/metrics_from_model.py gets with the shadow directory first on sys.path (rank 0 only)
+    dropin_fps = None
+    if rank == 0 and args.latency_frames > 0:
+        try:
+            dropin_fps = dropin_driver_loop(cfg, frames[:48], gat, mlp)
+        except Exception as e:                                  # an extra line of the report, never the reason a bench fails
+            dropin_fps = 'failed: %s' % e
     e2e_ms = 1e3 * float(np.mean(e2e_t))
     d2h = sum(v.numel() * v.element_size() for v in out.values() if hasattr(v, 'numel'))
     # ---- per-kernel-class timing for the roofline (separate pass, CUDA events around each class)
@@ -396,6 +404,7 @@ def main():
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
                 'cpu_baseline': cpu_line,
                 'persons_found_per_frame': P / args.frames,
+                'dropin_driver_loop_frames_per_s': dropin_fps,
                 'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
                 'latency_note': 'one frame per call, host buffers in / host results out: infer_host_graph (CUDA graph per batch '
                                 'shape) and, for comparison, the eager infer_host'}
@@ -602,6 +611,34 @@ def train_batch_workload(args, rank, world, local_rank):
                              'sample': '%d graphs in batches of 15 (the reference loader\'s batch size), one process' % n}}
     if rank == 0:
         print(json.dumps(line))
+
+
+def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
+    """frames/s of the loop body of the reference's test/metrics_from_model.py:178-300, one frame at a time, written against
+    the drop-in modules under their reference names (tests/test_dropin_gpu.run_frame is that loop body)."""
+    import torch
+    sys.path.insert(0, os.path.join(REPO, 'tests'))
+    import dropin_env
+    from test_dropin_gpu import run_frame
+    mods = dropin_env.activate(cfg)
+    dev = torch.device('cuda')
+    model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
+                              torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
+    model.load_state_dict(gat_state)
+    model = model.to(dev)
+    mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)
+    mlp.load_state_dict(mlp_state)
+    mlp = mlp.to(dev)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):             # the reference's modules print while they work
+        for f in frames[:8]:
+            run_frame(mods, cfg, model, mlp, f)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for f in frames:
+            run_frame(mods, cfg, model, mlp, f)
+        torch.cuda.synchronize()
+    return len(frames) / (time.perf_counter() - t0)
 
 
 def profile_classes(pipe, db, pm, torch):

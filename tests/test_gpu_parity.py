@@ -574,3 +574,49 @@ def test_cuda_graph_host_path_matches_eager():
                 assert torch.equal(got['valid'].bool(), want['valid'].bool())
                 assert (got['joints'] - want['joints']).abs().max().item() <= 1e-5
     assert len(getattr(pipe, '_graphs')) >= 2 and len(getattr(pipe, '_graphs')) <= len(keys)
+
+
+def test_cabi_argument_errors_on_device():
+    """Error behaviour of the C ABI with real device buffers: a bad argument is a negative status with a message that
+    names the call, nothing is launched, and the next valid call works (no sticky state)."""
+    import ctypes as C
+    pipe = get_pipe('panoptic')
+    L, ptr = pipe.L, pipeline_mod.ptr
+    tags, pb, db = golden_batch('panoptic')
+    g = pipe.build_graph(db, with_coo=False)
+    lay = pipe.gat[1]
+    z = torch.zeros(db.n_nodes, lay['ldz'], device='cuda')
+    act = pipe.planes_ws('err_act', db.n_nodes, lay['hd'])
+    st = pipe._stream()
+
+    def agg(ldz=None, impl=0, ld_planes=None, z_t=z):
+        return L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off), ptr(g.row_ptr), ptr(g.col),
+                                        ptr(z_t), lay['ldz'] if ldz is None else ldz, lay['heads'], lay['dim'], 0, db.max_heads, db.max_enodes,
+                                        0.15, 0.01, None, ptr(act.hi), ptr(act.lo), act.ld if ld_planes is None else ld_planes, None, impl, st)
+    msg = lambda: (L.b200pose_last_error() or b'').decode()
+    assert agg(ldz=lay['ldz'] + 1) == -1 and 'gat_aggregate' in msg()                 # row pitch not a multiple of 4
+    assert agg(ld_planes=act.ld + 8) == -1 and 'ld_planes' in msg()
+    assert agg(impl=9) == -1 and 'impl' in msg()
+    assert agg(z_t=None) == -1
+    assert agg() == 0
+    scores = torch.rand(db.n_nodes, device='cuda')
+    ph = torch.empty((db.n_heads, pipe.cfg.V_sm), dtype=torch.int32, device='cuda')
+    npers = torch.empty(db.n_frames, dtype=torch.int32, device='cuda')
+    cl = lambda v_sm, pairs: L.b200pose_cluster(db.n_frames, ptr(db.head_off), ptr(db.node_off), pairs, ptr(g.node_cam), ptr(scores), v_sm,
+                                                 0.5, 2, db.max_heads, db.max_enodes, ptr(ph), ptr(npers), st)
+    assert cl(33, ptr(g.pairs)) == -1 and 'v_sm' in msg()
+    assert cl(pipe.cfg.V_sm, None) == -1 and 'null' in msg()
+    assert cl(pipe.cfg.V_sm, ptr(g.pairs)) == 0
+    # a frame plan beyond the compiled limits is "unsupported", not a crash: 40000 heads in one frame
+    big = L.b200pose_cluster(1, ptr(db.head_off), ptr(db.node_off), ptr(g.pairs), ptr(g.node_cam), ptr(scores), pipe.cfg.V_sm, 0.5, 2,
+                             40000, 1 << 24, ptr(ph), ptr(npers), st)
+    assert big == -3 and 'too large' in msg()
+    assert L.b200pose_build_graph_pairs(1, ptr(db.head_off), ptr(db.node_off), ptr(db.sk_cam), pipe.cams.ref, None, db.max_heads,
+                                        None, None, ptr(g.row_ptr), ptr(g.col), ptr(g.node_cam), st) == -1
+    A = pipeline_mod.Planes.from_f32(torch.randn(4, 64, device='cuda'), st)
+    out = torch.empty(4, 8, device='cuda')
+    lin = lambda ldo: L.b200pose_linear(ptr(A.hi), ptr(A.lo), A.ld, ptr(A.hi), ptr(A.lo), A.ld, None, 200, 8, 64, 1.0, 1.0, ptr(out), ldo,
+                                        None, None, 0, 4, st)
+    assert lin(7) == -1 and 'linear' in msg()                                            # TMA store needs a 16-byte row pitch
+    torch.cuda.synchronize()
+    assert pipe.infer(db)['n_persons_total'] >= 0
