@@ -299,6 +299,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 struct GemmParams2 {
     int M, N, num_kb;
+    int k_last;                              // 16-wide k steps of the last k-block that hold data (the rest is K padding: zeros)
     int tiles_m, tiles_n, panels_total;      // 64-column output panels; tiles_m counts (128 * NCTA)-row tiles
     int group_n;                             // consecutive n-tiles of one m-tile a CTA (pair) processes per visit
     int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
@@ -495,8 +496,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                     tcgen05_fence_after();
                     const uint32_t base = tiles_base + (uint32_t)s * stage_bytes;
                     const uint32_t sa_hi = base, sa_lo = base + a_bytes, sb_hi = base + 2 * a_bytes, sb_lo = base + 2 * a_bytes + b_bytes;
+                    // k steps that are entirely K padding (zero planes) are not issued: 3 of the 28 steps of a K = 400
+                    // projection - the operands an MMA reads from shared memory are the resource this kernel is bound by
+                    const int nk4 = kb == p.num_kb - 1 ? p.k_last : kBK / kUmmaK;
 #pragma unroll
                     for (int k4 = 0; k4 < kBK / kUmmaK; ++k4) {              // hi*hi, lo*hi, hi*lo per 16-wide k step
+                        if (k4 >= nk4) break;
                         const uint32_t off = k4 * kUmmaK * 2;
                         const uint64_t dah = make_sw128_desc(sa_hi + off), dal = make_sw128_desc(sa_lo + off);
                         const uint64_t dbh = make_sw128_desc(sb_hi + off), dbl = make_sw128_desc(sb_lo + off);
@@ -1255,7 +1260,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     // re-reads the whole weight matrix from L2)
     const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 4 * kBM ? 2 : 1);
     GemmParams2 q;
-    q.M = m; q.N = n; q.num_kb = kpad / kBK; q.bias = bias; q.slope = slope; q.out_scale = out_scale;
+    q.M = m; q.N = n; q.num_kb = kpad / kBK; q.k_last = ceil_div(k - (kpad / kBK - 1) * kBK, kUmmaK); q.bias = bias; q.slope = slope; q.out_scale = out_scale;
     q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags;
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));

@@ -616,21 +616,22 @@ def train_batch_workload(args, rank, world, local_rank):
 def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
     """frames/s of the loop body of the reference's test/metrics_from_model.py:178-300, one frame at a time, written against
     the drop-in modules under their reference names (tests/test_dropin_gpu.run_frame is that loop body)."""
+    import contextlib
+    import io
     import torch
     sys.path.insert(0, os.path.join(REPO, 'tests'))
-    import dropin_env
-    from test_dropin_gpu import run_frame
-    mods = dropin_env.activate(cfg)
-    dev = torch.device('cuda')
-    model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
-                              torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
-    model.load_state_dict(gat_state)
-    model = model.to(dev)
-    mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)
-    mlp.load_state_dict(mlp_state)
-    mlp = mlp.to(dev)
-    import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()):             # the reference's modules print while they work
+    with contextlib.redirect_stdout(io.StringIO()):             # the reference's modules print while they work; stdout is the JSON line's
+        import dropin_env
+        from test_dropin_gpu import run_frame
+        mods = dropin_env.activate(cfg)
+        dev = torch.device('cuda')
+        model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
+                                  torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
+        model.load_state_dict(gat_state)
+        model = model.to(dev)
+        mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)
+        mlp.load_state_dict(mlp_state)
+        mlp = mlp.to(dev)
         for f in frames[:8]:
             run_frame(mods, cfg, model, mlp, f)
         torch.cuda.synchronize()
@@ -638,7 +639,8 @@ def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
         for f in frames:
             run_frame(mods, cfg, model, mlp, f)
         torch.cuda.synchronize()
-    return len(frames) / (time.perf_counter() - t0)
+        dt = time.perf_counter() - t0
+    return len(frames) / dt
 
 
 def profile_classes(pipe, db, pm, torch):
