@@ -1115,6 +1115,102 @@ __global__ void __launch_bounds__(kSmallWarps * 32) gemm_small_m_kernel(
     }
 }
 
+// The same layer when it is a pure weight stream (at most 8 rows, K <= 4096): the k range is split over the lanes of the
+// whole CTA - lane (warp, lane) owns the 8 consecutive k values at (32 warp + lane) * 8 and keeps A[0..M) x those 8 in
+// registers for the life of the CTA - and the CTA walks blocks of C = 32 / MMAX output columns. Per block a lane issues the
+// 2 C 16-byte weight loads of its k slice back to back (nothing depends on shared memory, so they are all in flight
+// together: 96 KB per CTA for K = 3072), forms its C x MMAX partial dot products, and the warp reduces all 32 of them at
+// once with a 31-shuffle transposing butterfly (lane l ends up with the warp total of partial l) instead of 5 shuffles per
+// value; one shared-memory hop adds the warps. A is never staged, and the weights are touched exactly once.
+template <int MMAX>
+__global__ void __launch_bounds__(512, 1) gemm_stream_kernel(
+    const __nv_bfloat16* __restrict__ a_hi, const __nv_bfloat16* __restrict__ a_lo, int lda,
+    const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo, int ldw,
+    const float* __restrict__ bias, int M, int N, int kpad, float slope, float out_scale,
+    float* __restrict__ out_f32, int ld_out, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ld_planes)
+{
+    constexpr int C = 32 / MMAX;
+    __shared__ float part[2][16][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int k0 = (warp * 32 + lane) * 8;
+    const bool active = k0 < kpad;
+    auto unpack = [](const uint4& h, const uint4& l, float (&v)[8]) {
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            v[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+        }
+    };
+    float a[MMAX][8];
+#pragma unroll
+    for (int m = 0; m < MMAX; ++m) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[m][j] = 0.f;
+        if (m < M && active)
+            unpack(__ldg(reinterpret_cast<const uint4*>(a_hi + (size_t)m * lda + k0)),
+                   __ldg(reinterpret_cast<const uint4*>(a_lo + (size_t)m * lda + k0)), a[m]);
+    }
+    const int n_cols = out_hi ? ld_planes : N;               // plane padding columns are written as zeros
+    const int n_blocks = (n_cols + C - 1) / C;
+    int it = 0;
+    for (int cb = blockIdx.x; cb < n_blocks; cb += gridDim.x, ++it) {
+        const int n0 = cb * C;
+        uint4 wh[C], wl[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            wh[c] = make_uint4(0u, 0u, 0u, 0u); wl[c] = wh[c];
+            if (active && n0 + c < N) {
+                wh[c] = __ldg(reinterpret_cast<const uint4*>(w_hi + (size_t)(n0 + c) * ldw + k0));
+                wl[c] = __ldg(reinterpret_cast<const uint4*>(w_lo + (size_t)(n0 + c) * ldw + k0));
+            }
+        }
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float w[8];
+            unpack(wh[c], wl[c], w);
+#pragma unroll
+            for (int m = 0; m < MMAX; ++m) {
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fmaf(a[m][j], w[j], s);
+                v[c * MMAX + m] = s;
+            }
+        }
+        // transposing butterfly: after the step with offset o a lane keeps the half of its values whose index has bit o
+        // equal to its own lane bit, summed with its partner's copy; lane l ends with the warp total of value l
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+                const float keep = upper ? v[i + o] : v[i];
+                const float send = upper ? v[i] : v[i + o];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+        }
+        part[it & 1][warp][lane] = v[0];
+        __syncthreads();
+        if (warp == 0) {
+            float t = 0.f;
+            for (int w = 0; w < n_warps; ++w) t += part[it & 1][w][lane];
+            const int n = n0 + lane / MMAX, m = lane % MMAX;
+            if (m < M && n < n_cols) {
+                float y = 0.f;
+                if (n < N) y = leaky(t + (bias ? __ldg(bias + n) : 0.f), slope) * out_scale;
+                if (out_f32 && n < N) out_f32[(size_t)m * ld_out + n] = y;
+                if (out_hi) {
+                    __nv_bfloat16 hh, ll;
+                    split_bf16(y, hh, ll);
+                    out_hi[(size_t)m * ld_planes + n] = hh;
+                    out_lo[(size_t)m * ld_planes + n] = ll;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1233,6 +1329,21 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         gemm_split_tc_kernel<<<grid, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
+    }
+    if ((impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
+        // weight stream with A in registers: k split over the CTA's lanes, blocks of 32 / MMAX columns
+        const int warps = ceil_div(kpad, 256);
+        const int cols = out_hi ? ld_planes : n;
+        const int per_sm = warps >= 12 ? 1 : warps >= 6 ? 2 : 4;              // ~96 KB of weight loads in flight per SM
+        auto launch_stream = [&](auto kern, int c_per_block) -> int {
+            int ctas = ceil_div(cols, c_per_block);
+            if (ctas > num_sms() * per_sm) ctas = num_sms() * per_sm;
+            kern<<<ctas, warps * 32, 0, st>>>(p.a_hi, p.a_lo, lda, p.w_hi, p.w_lo, ldw, bias, m, n, kpad, slope, out_scale,
+                                              out_f32, ld_out, p.out_hi, p.out_lo, ld_planes);
+            B2_CHECK_LAUNCH();
+            return B200POSE_OK;
+        };
+        return m <= 4 ? launch_stream(gemm_stream_kernel<4>, 8) : launch_stream(gemm_stream_kernel<8>, 4);
     }
     if ((impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight-streaming small-M kernel: as many CTAs as fit at once (the A staging is per CTA), every warp takes columns

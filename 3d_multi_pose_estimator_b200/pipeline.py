@@ -477,14 +477,26 @@ class PosePipeline:
         layers = layers if layers is not None else self.mlp
         n_out = layers[-1]['n']
         out = self.f32_ws('mlp_out', P, round_up(n_out, 4))          # TMA store needs a 16-byte row pitch
+        # A live frame's handful of persons: the layers are weight streams (116 MB for 9 layers), served by the kernel that
+        # keeps up to 8 rows of A in registers; 9..32 rows go through it 8 at a time - the second pass over a layer's
+        # weights (at most 38 MB) comes out of L2
+        chunks = [(0, P)] if P <= 8 or P > 32 else [(r, min(r + 8, P)) for r in range(0, P, 8)]
+
+        def rows(pl: Planes, r0, r1):
+            v = Planes.__new__(Planes)
+            v.rows, v.cols, v.ld, v.hi, v.lo = r1 - r0, pl.cols, pl.ld, pl.hi[r0:r1], pl.lo[r0:r1]
+            return v
         for i, lay in enumerate(layers):
             last = i == len(layers) - 1
-            if last:
-                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out)
-            else:
-                y = self.planes_ws('mlp_y%d' % (i & 1), P, lay['n'])
-                self.linear(x, P, lay['w'], lay['b'], lay['n'], lay['k'], slope, out_planes=y)
-                x = y
+            y = None if last else self.planes_ws('mlp_y%d' % (i & 1), P, lay['n'])
+            for r0, r1 in chunks:
+                xi = x if len(chunks) == 1 else rows(x, r0, r1)
+                if last:
+                    self.linear(xi, r1 - r0, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out[r0:r1])
+                else:
+                    self.linear(xi, r1 - r0, lay['w'], lay['b'], lay['n'], lay['k'], slope,
+                                out_planes=y if len(chunks) == 1 else rows(y, r0, r1))
+            x = y
         return out[:P, :n_out]
 
     # ------------------------------------------------------------------ whole path
