@@ -119,10 +119,11 @@ int b200pose_node_features(int32_t n_frames, int32_t n_heads_total, int32_t n_no
  * so the padding can be consumed as K padding by the next GEMM.
  * out_scale multiplies the result after the activation (x10 of metrics_from_model.py:282).
  * impl: 0 = persistent tcgen05 + TMA tensor-core kernel (the product path; CTA pairs with cta_group::2 MMAs and
- * 256-row tiles, single CTAs for tiny m; full-width single-tile pairs for tall projections with 256 < n <= 512);
- * m <= 8 rows (the pose MLP of a single frame) go to a weight-streaming kernel with A in registers, 9..16 rows to one that
- * stages A in shared memory: one warp per output column, every
- * hi/lo weight read once by all SMs; 4 / 5 / 6 / 7 force single CTAs / CTA pairs / wide CTA pairs / the small-m kernel (A/B runs);
+ * 256-row tiles above 512 rows, single CTAs below); m <= 8 rows (the pose MLP of a live frame) go to a weight-streaming
+ * kernel that keeps A in registers and splits k over the lanes of a CTA, 9..16 rows to one that stages A in shared memory
+ * and gives every warp an output column - either way every hi/lo weight is read once;
+ * 4 / 5 / 6 / 7 force single CTAs / CTA pairs / full-width single-tile CTA pairs (256 < n <= 512; measured slower, kept
+ * for A/B runs) / the few-row kernels;
  * 1 = fp32 SIMT kernel, 2 = tcgen05 kernel with tiles filled by ordinary stores, 3 = first one-tile-per-CTA
  * kernel - these three exist only for the kernel self-test.
  * ------------------------------------------------------------------------------------------- */
