@@ -439,15 +439,32 @@ class PosePipeline:
                 a, b, m = pack_skeleton(sk)
                 person_sk[p, names.index(cam)] = len(xy)
                 xy.append(a); vp.append(b); mask.append(m)
-        S = len(xy)
-        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device)
-        sk_xy = up(np.stack(xy) if S else np.zeros((1, N_JOINTS, 2)), torch.float64)
-        sk_vp = up(np.stack(vp) if S else np.zeros((1, N_JOINTS, 2), np.float32), torch.float32)
-        sk_mask = up(np.array(mask if S else [0], dtype=np.uint32).view(np.int32), torch.int32)
+        S = max(len(xy), 1)
         P = len(persons)
-        psk = up(person_sk, torch.int32)
-        valid = torch.empty(max(P, 1), dtype=torch.uint8, device=self.device)
-        xf = torch.zeros((max(P, 1), self.cfg.mlp_in), dtype=torch.float32, device=self.device)
+        Pn = max(P, 1)
+        # one pinned staging buffer and one host->device copy for the four small inputs (a call per person is how the
+        # reference's drivers use this: test/metrics_from_model.py:243-266)
+        n_xy, n_vp, n_mask, n_psk = S * N_JOINTS * 2 * 8, S * N_JOINTS * 2 * 4, S * 4, Pn * self.cfg.n_cameras * 4
+        offs = [0]
+        for nb in (n_xy, n_vp, n_mask, n_psk):                  # every region starts 8-byte aligned
+            offs.append((offs[-1] + nb + 7) // 8 * 8)
+        total = offs[-1]
+        stage = self.__dict__.setdefault('_person_stage', {})
+        if total not in stage:
+            stage[total] = (torch.empty(total, dtype=torch.uint8).pin_memory(), torch.empty(total, dtype=torch.uint8, device=self.device))
+        h_buf, d_buf = stage[total]
+        hv = h_buf.numpy()
+        hv[offs[0]:offs[0] + n_xy].view(np.float64)[:] = (np.stack(xy) if xy else np.zeros((1, N_JOINTS, 2))).ravel()
+        hv[offs[1]:offs[1] + n_vp].view(np.float32)[:] = (np.stack(vp) if vp else np.zeros((1, N_JOINTS, 2), np.float32)).ravel()
+        hv[offs[2]:offs[2] + n_mask].view(np.uint32)[:] = np.array(mask if mask else [0], dtype=np.uint32)
+        hv[offs[3]:offs[3] + n_psk].view(np.int32)[:] = person_sk.ravel()
+        d_buf.copy_(h_buf, non_blocking=True)
+        sk_xy = d_buf[offs[0]:offs[0] + n_xy].view(torch.float64)
+        sk_vp = d_buf[offs[1]:offs[1] + n_vp].view(torch.float32)
+        sk_mask = d_buf[offs[2]:offs[2] + n_mask].view(torch.int32)
+        psk = d_buf[offs[3]:offs[3] + n_psk].view(torch.int32)
+        valid = torch.empty(Pn, dtype=torch.uint8, device=self.device)
+        xf = torch.zeros((Pn, self.cfg.mlp_in), dtype=torch.float32, device=self.device)
         self.launches += 1
         check(self.L.b200pose_encode_persons(P, ptr(psk), ptr(sk_xy), ptr(sk_vp), ptr(sk_mask), self.cams.ref,
                                              ptr(xf), self.cfg.mlp_in, None, None, 0, ptr(valid), self._stream()), 'encode_persons')
