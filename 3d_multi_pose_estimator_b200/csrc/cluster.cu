@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(MAXT) cluster_kernel(ClusterParams p)
         // sorted by that position (rank by counting: positions are distinct)
         for (int h = tid; h < H; h += nt) flag[h] = 0x7fffffff;
         bsync();
-        for (int t = tid; t < 2 * M; t += nt) atomicMin(&flag[p.pairs[2 * (size_t)m0 + t]], t);
+        for (int t = tid; t < 2 * M; t += nt) {
+            const unsigned h = (unsigned)p.pairs[2 * (size_t)m0 + t];
+            if (h < (unsigned)H) atomicMin(&flag[h], t);
+        }
         bsync();
         if (tid == 0) n_seen_s = 0;
         bsync();

@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
     const bool slope_le1 = p.act_slope >= 0.f && p.act_slope <= 1.f;
     const bool alpha_le1 = p.alpha >= 0.f && p.alpha <= 1.f;
     auto lrelu = [&](float x) { return alpha_le1 ? leaky_le1(x, p.alpha) : leaky(x, p.alpha); };
+    if (Hb > max_heads) return;                                // outside the sized plan (caller contract: max_heads covers every frame)
     const LargePlan plan = large_plan(max_heads, HD, ldz, VEC);
     const uint32_t smem_base = agg_smem_u32(smem_l);
     int head_of[KMAX];

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) build_graph_kernel(
 // in-edges of every node are in ascending reference edge id like the closed-form builder's.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_graph_pairs_kernel(
-    int n_graphs, const int* __restrict__ head_off, const int* __restrict__ node_off,
+    int n_graphs, int max_heads, const int* __restrict__ head_off, const int* __restrict__ node_off,
     const int* __restrict__ sk_cam, const int* __restrict__ sm_slot, const int* __restrict__ pairs,
     int* __restrict__ src, int* __restrict__ dst, int* __restrict__ row_ptr, int* __restrict__ col, int* __restrict__ node_cam)
 {
@@ -168,11 +168,13 @@ __global__ void __launch_bounds__(256) build_graph_pairs_kernel(
     const int n0 = node_off[b], Nb = node_off[b + 1] - n0;
     const int M = Nb - H, m0 = n0 - h0, e0 = h0 + 5 * m0;
     const int* pr = pairs + 2 * (size_t)m0;
+    if (H > max_heads || M < 0) return;             // outside the sized plan (the host checked the batch-wide maximum)
     for (int h = threadIdx.x; h <= H; h += blockDim.x) off_s[h] = h < H ? 1 : 0;      // the self loop
     __syncthreads();
     for (int k = threadIdx.x; k < M; k += blockDim.x) {
-        atomicAdd(&off_s[pr[2 * k]], 1);
-        atomicAdd(&off_s[pr[2 * k + 1]], 1);
+        const unsigned h1 = (unsigned)pr[2 * k], h2 = (unsigned)pr[2 * k + 1];
+        if (h1 < (unsigned)H) atomicAdd(&off_s[h1], 1);    // a pair that names a head outside the graph gets no in-edge
+        if (h2 < (unsigned)H) atomicAdd(&off_s[h2], 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -371,7 +373,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_build_graph_pairs
     if (n_graphs == 0) return B200POSE_OK;
     const size_t smem = (size_t)(max_heads_per_graph + 1) * sizeof(int);
     B2_CHECK_CUDA(cudaFuncSetAttribute(build_graph_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    build_graph_pairs_kernel<<<n_graphs, 256, smem, (cudaStream_t)stream>>>(n_graphs, head_off, node_off, sk_cam, cams->sm_slot, pairs,
+    build_graph_pairs_kernel<<<n_graphs, 256, smem, (cudaStream_t)stream>>>(n_graphs, max_heads_per_graph, head_off, node_off, sk_cam, cams->sm_slot, pairs,
                                                                             src, dst, row_ptr, col, node_cam);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
