@@ -86,3 +86,42 @@ def test_augment_views_subsets():
     assert [list(o) for o in tg.augment_views([sample], used, 2)] == [['a', 'c']]
     assert tg.augment_views([{'b': ['[]']}], used, 1) == []
     assert [list(o) for o in O.augment_views([sample], used, 1)] == [['a', 'c'], ['c'], ['a']]
+
+
+def test_edge_node_list_matches_oracle_on_random_tuples():
+    """The product's host-side edge-node / label logic against the oracle restatement of process_training on 120 random
+    tuples of 1..5 single-person samples with spurious skeletons, empty cameras, skeletons without joints and
+    single-camera samples (graph_generator.py:699-800)."""
+    import json as _json
+    cfg, _, _ = helpers.load_golden('panoptic')
+    tabs = O.CameraTables(cfg)
+    rng = np.random.default_rng(11)
+    n_graphs = 0
+    for case in range(120):
+        samples = []
+        for s in range(int(rng.integers(1, 6))):
+            fr = helpers.synth.make_frame(cfg, 40000 + 10 * case + s, 1, drop_joint_p=float(rng.uniform(0, 0.6)),
+                                          drop_view_p=float(rng.uniform(0, 0.7)), rand_conf=True, keep_empty=bool(rng.integers(0, 2)))
+            for cam in list(fr):
+                r = rng.random()
+                if r < 0.2:                                     # spurious partial skeleton(s) in this camera
+                    extra = _json.loads(helpers.synth.make_frame(cfg, 50000 + 10 * case + s, 1, drop_joint_p=0.6)[cam][0])
+                    sk = _json.loads(fr[cam][0])
+                    fr[cam][0] = _json.dumps(extra + sk if rng.random() < 0.5 else sk + extra)
+                elif r < 0.3:
+                    fr[cam][0] = '[]'                           # camera present but empty
+                elif r < 0.4:
+                    del fr[cam]
+            samples.append(fr)
+        og = O.build_training_graph(samples, tabs)
+        built = tg.training_graph_inputs(samples, cfg)
+        assert (og is None) == (built is None), case
+        if og is None:
+            continue
+        pb, pairs, labels = built
+        assert pb.n_heads == og['n_heads']
+        assert np.array_equal(pairs, og['pairs']) and np.array_equal(labels, og['labels']), case
+        assert np.array_equal(pb.sk_cam, np.array([cfg.used_sm[c] for c in og['nodes_camera'][:og['n_heads']]], dtype=np.int32))
+        assert pb.max_heads >= 1 + np.bincount(pairs.ravel()).max() and pb.max_enodes == len(pairs)
+        n_graphs += 1
+    assert n_graphs > 60
