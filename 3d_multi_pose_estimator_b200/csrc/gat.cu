@@ -6,11 +6,22 @@
 //   :66           out[v] = sum_{u->v} s[e] * ft2[u]                           (update_all u_mul_e / sum)
 //   :141-142      next input = LeakyReLU_0.01(out.flatten(1));  :144-145 sigmoid on the last layer
 //
-// One CTA per frame, one warp per destination node walking its CSR row. The z rows of the frame's
-// heads (and, for layer 0, the single shared edge-node row) are staged in shared memory: every
-// edge-node destination reads two head rows and every head reads its own, so 2/3 of the row gathers
-// of a frame are served on chip; edge-node rows come through the read-only path. Lanes own 4 (or 2)
-// consecutive feature columns, so every row read is a coalesced, vectorised sweep.
+// Four kernels, one arithmetic (softmax through the SFU, sums in ascending reference edge id unless noted):
+//   gat_aggregate_frame_kernel  frames of at most 32 heads whose plan fits in shared memory (the Panoptic-sized case):
+//                               one CTA per frame, head rows resident, edge-node rows streamed once through a bulk-copy
+//                               ring, warp per destination, head accumulators in registers. The product path at 1024 frames.
+//   gat_aggregate_large_kernel  frames of more than 48 heads (10 views x 16 persons) and batches of a few frames: edge
+//                               units with staged head rows and per-warp cp.async rings, head units with a one-pass
+//                               fixed-reference softmax (reassociated sums: equal to fp32 rounding, not bitwise).
+//   gat_aggregate_kernel        the general gather kernel: warp per destination over the CSR, any graph.
+//   gat_aggregate_scalar_kernel the last layer (one output per node) with the sigmoid fused.
+// The host function at the bottom picks one (impl 0) or takes the caller's choice (A/B runs, tests).
+//
+// gat_aggregate_kernel: one CTA per (frame, chunk of destinations), one warp per destination node walking its CSR row.
+// When a frame's heads fit (at most 48 rows) their z rows (and, for layer 0, the single shared edge-node row) are staged
+// in shared memory: every edge-node destination reads two head rows and every head reads its own, so 2/3 of the row
+// gathers are served on chip; edge-node rows come through the read-only path. Lanes own 4 (or 2) consecutive feature
+// columns, so every row read is a coalesced, vectorised sweep.
 #include "common.cuh"
 
 namespace b200pose {
