@@ -202,7 +202,7 @@ __device__ void triangulate_pair(const double* __restrict__ P1, const double* __
 //            upper median + 5 cm filter + mean for the baseline): same order as the reference's
 //            itertools.combinations loop, so the result does not depend on the thread mapping
 //   phase W: the whole CTA writes the person's row with 16-byte stores (fp32 and/or bf16 planes)
-constexpr int kLiftThreads = 96;           // 170-180 pair solves per joint batch: two rounds of 96 waste fewer lanes than 128 + 52 (measured -4 %)
+constexpr int kLiftThreads = 96;  // 170-180 pair solves per joint batch: two rounds of 96 waste fewer lanes than 128 + 52 (measured -4 %)
 constexpr int kPairBudgetBytes = 48 * 1024;
 
 struct LiftSmem {           // byte offsets into dynamic shared memory
