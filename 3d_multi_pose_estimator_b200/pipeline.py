@@ -635,13 +635,14 @@ class PosePipeline:
         return out
 
     # ------------------------------------------------------------------ low-latency path: one CUDA graph per batch shape
-    def _stage_b_static(self, db: DeviceBatch, res: dict, p_max: int):
-        """Stage 3 without the person-count readback: every launch is sized for p_max persons (a person needs two views,
-        so p_max = heads // 2 bounds the count); rows past the real count keep person_sk = -1, encode to zero rows with
-        valid = 0 and are dropped on the host. This is what lets the whole step live in one CUDA graph."""
+    def _stage_b_static(self, db: DeviceBatch, res: dict, p_bound: int, p_max: int):
+        """Stage 3 without the person-count readback: the person list is sized for p_bound = heads // 2 persons (a person
+        needs two views), the encoder and the MLP for p_max <= p_bound rows; rows past the real count keep person_sk = -1,
+        encode to zero rows with valid = 0 and are dropped on the host. This is what lets the whole step live in one CUDA
+        graph."""
         Cn = self.cfg.n_cameras
-        person_sk = torch.full((p_max, Cn), -1, dtype=torch.int32, device=self.device)
-        person_frame = torch.zeros(p_max, dtype=torch.int32, device=self.device)
+        person_sk = torch.full((p_bound, Cn), -1, dtype=torch.int32, device=self.device)
+        person_frame = torch.zeros(p_bound, dtype=torch.int32, device=self.device)
         self.launches += 1
         check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
                                              ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
@@ -667,13 +668,19 @@ class PosePipeline:
         cur = torch.cuda.current_stream(self.device)
         names = ('sk_xy', 'sk_vp', 'sk_mask', 'sk_cam', 'head_off', 'node_off')
         if ent is None:
-            self.infer_host(hb)                                 # eager warm-up of this shape: workspaces, function attributes
+            warm = self.infer_host(hb)                          # eager warm-up of this shape: workspaces, function attributes
+            hint = self.__dict__.setdefault('_graph_person_hint', {})
+            seen = max(int(warm['n_persons_total']), hint.get(key, 0))
             pin = lambda t: torch.empty_like(t).pin_memory()
             h_in = {n: pin(getattr(hb, n)) for n in names}
             d_in = {n: torch.empty_like(getattr(hb, n), device=self.device) for n in names}
             db = DeviceBatch(pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes, d_in['sk_xy'], d_in['sk_vp'],
                              d_in['sk_mask'], d_in['sk_cam'], d_in['head_off'], d_in['node_off'])
-            p_max = max(pb.n_heads // 2, 1)
+            # heads // 2 bounds the person count (a person needs two views) and sizes the person list; the encoder and the MLP
+            # are captured for a tighter capacity - the count this shape showed, with head-room, in multiples of 8 rows (the
+            # weight-stream kernel's step) - and a replay that finds more persons than that is redone eagerly and re-captured
+            p_bound = max(pb.n_heads // 2, 1)
+            p_max = min(p_bound, max(8, (int(seen * 1.25) + 7) // 8 * 8))
             n_out = self.mlp[-1]['n']
             mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
             h_out = dict(n_persons=mk((pb.n_frames,), torch.int32), person_off=mk((pb.n_frames + 1,), torch.int32),
@@ -687,15 +694,15 @@ class PosePipeline:
                 for n in names:
                     d_in[n].copy_(h_in[n], non_blocking=True)
                 res = self.stage_a(db)
-                person_sk, valid, joints = self._stage_b_static(db, res, p_max)
+                person_sk, valid, joints = self._stage_b_static(db, res, p_bound, p_max)
                 h_out['n_persons'].copy_(res['n_persons'], non_blocking=True)
                 h_out['person_off'].copy_(res['person_off'], non_blocking=True)
-                h_out['person_sk'].copy_(person_sk, non_blocking=True)
+                h_out['person_sk'].copy_(person_sk[:p_max], non_blocking=True)
                 h_out['joints'].copy_(joints, non_blocking=True)
                 h_out['valid'].copy_(valid, non_blocking=True)
             # the graph bakes in device addresses: keep everything it touches alive (workspaces are replaced when a
             # larger batch makes them grow)
-            ent = dict(graph=graph, h_in=h_in, h_out=h_out, keep=(d_in, db, res, person_sk, valid, joints, list(self._ws.values())))
+            ent = dict(graph=graph, h_in=h_in, h_out=h_out, p_cap=p_max, keep=(d_in, db, res, person_sk, valid, joints, list(self._ws.values())))
             cache[key] = ent
             while len(cache) > max_cached:
                 cache.popitem(last=False)
@@ -707,6 +714,10 @@ class PosePipeline:
         cur.synchronize()
         h_out = ent['h_out']
         P = int(h_out['person_off'][pb.n_frames])
+        if P > ent['p_cap']:                                    # more persons than the captured capacity: eager, and a new capture next time
+            self.__dict__.setdefault('_graph_person_hint', {})[key] = P
+            del cache[key]
+            return self.infer_host(hb)
         return dict(n_persons=h_out['n_persons'], person_off=h_out['person_off'], person_sk=h_out['person_sk'][:P],
                     n_persons_total=P, joints=h_out['joints'][:P], valid=h_out['valid'][:P])
 

@@ -574,6 +574,18 @@ def test_cuda_graph_host_path_matches_eager():
                 assert torch.equal(got['valid'].bool(), want['valid'].bool())
                 assert (got['joints'] - want['joints']).abs().max().item() <= 1e-5
     assert len(getattr(pipe, '_graphs')) >= 2 and len(getattr(pipe, '_graphs')) <= len(keys)
+    # a replay that finds more persons than the captured capacity falls back to the eager path and re-captures next time
+    hb = pipeline_mod.HostBatch(batches[0])
+    want = {k: (v.clone() if hasattr(v, 'clone') else v) for k, v in pipe.infer_host(hb).items()}
+    key = next(k for k in pipe._graphs if k[0] == 1 and k[1] == batches[0].n_heads and k[2] == batches[0].n_nodes)
+    assert want['n_persons_total'] > 0
+    pipe._graphs[key]['p_cap'] = 0
+    got = pipe.infer_host_graph(hb)
+    assert key not in pipe._graphs and got['n_persons_total'] == want['n_persons_total']
+    assert torch.equal(got['person_sk'], want['person_sk']) and torch.equal(got['joints'], want['joints'])
+    got = pipe.infer_host_graph(hb)                                     # captured again, capacity from the remembered count
+    assert key in pipe._graphs and pipe._graphs[key]['p_cap'] >= want['n_persons_total']
+    assert torch.equal(got['person_sk'], want['person_sk']) and (got['joints'] - want['joints']).abs().max().item() <= 1e-5
 
 
 def test_cabi_argument_errors_on_device():
