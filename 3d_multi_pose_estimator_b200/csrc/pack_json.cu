@@ -17,6 +17,9 @@
 #include <string.h>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <vector>
 
 namespace b200pose {
@@ -355,10 +358,42 @@ extern "C" __attribute__((visibility("default"))) int b200pose_pack_json(const c
     B2_CHECK_ARG(json && len >= 0 && out_handle && (n_cams == 0 || (cam_names && cam_index)), "pack_json: null argument");
     PackCfg cfg;
     for (int i = 0; i < n_cams; ++i) { cfg.names.emplace_back(cam_names[i]); cfg.cam_index.push_back(cam_index[i]); }
-    // pass 1: frame boundaries
+    // The boundary scan (one thread: a frame ends where the top-level value ends) and the frame parsing (worker threads) run
+    // as a pipeline: the scanner hands every frame span to a queue as soon as it has it, so the serial pass - a third of the
+    // wall time at 8 threads when it ran first - hides behind the parsing. The caller's thread scans, then parses too.
     std::string err;
     Cur c{json, json + len, &err};
-    std::vector<std::pair<const char*, const char*>> spans;
+    struct Item { size_t f; const char* b; const char* e; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Item> queue;
+    bool scan_done = false;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    std::vector<std::vector<std::pair<size_t, FrameOut>>> parsed((size_t)nt);
+    auto worker = [&](int t) {
+        while (true) {
+            Item it;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !queue.empty() || scan_done; });
+                if (queue.empty()) return;
+                it = queue.front();
+                queue.pop_front();
+            }
+            parsed[(size_t)t].emplace_back(it.f, FrameOut());
+            parse_frame(it.b, it.e, cfg, parsed[(size_t)t].back().second);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker, t);
+    size_t B = 0;
+    std::string scan_error;
+    auto push = [&](const char* b, const char* e) {
+        { std::lock_guard<std::mutex> lk(mu); queue.push_back(Item{B, b, e}); }
+        cv.notify_one();
+        ++B;
+    };
     c.ws();
     if (c.p < c.end && *c.p == '[') {
         ++c.p;
@@ -366,38 +401,30 @@ extern "C" __attribute__((visibility("default"))) int b200pose_pack_json(const c
             while (true) {
                 c.ws();
                 const char* b = c.p;
-                if (!skip_value(c)) { set_error("pack_json: %s (frame %zu)", err.c_str(), spans.size()); return B200POSE_E_INVALID; }
-                spans.emplace_back(b, c.p);
+                if (!skip_value(c)) { scan_error = err + " (frame " + std::to_string(B) + ")"; break; }
+                push(b, c.p);
                 if (c.eat(',')) continue;
                 if (c.eat(']')) break;
-                set_error("pack_json: expected ',' or ']' after frame %zu", spans.size() - 1);
-                return B200POSE_E_INVALID;
+                scan_error = "expected ',' or ']' after frame " + std::to_string(B - 1);
+                break;
             }
         }
     } else if (c.p < c.end && *c.p == '{') {
         const char* b = c.p;
-        if (!skip_value(c)) { set_error("pack_json: %s", err.c_str()); return B200POSE_E_INVALID; }
-        spans.emplace_back(b, c.p);
+        if (!skip_value(c)) scan_error = err;
+        else push(b, c.p);
     } else {
-        set_error("pack_json: input must be a list of frames or one frame object");
-        return B200POSE_E_INVALID;
+        scan_error = "input must be a list of frames or one frame object";
     }
-    // pass 2: frames in parallel
+    { std::lock_guard<std::mutex> lk(mu); scan_done = true; }
+    cv.notify_all();
+    worker(0);
+    for (auto& x : th) x.join();
+    if (!scan_error.empty()) { set_error("pack_json: %s", scan_error.c_str()); return B200POSE_E_INVALID; }
     Packed* P = new Packed();
-    const size_t B = spans.size();
     P->frames.resize(B);
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    if (nt < 1) nt = 1;
-    if ((size_t)nt > B) nt = B ? (int)B : 1;
-    auto work = [&](int t) {
-        for (size_t f = (size_t)t; f < B; f += (size_t)nt) parse_frame(spans[f].first, spans[f].second, cfg, P->frames[f]);
-    };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-        for (auto& x : th) x.join();
-    }
+    for (auto& list : parsed)
+        for (auto& fo : list) P->frames[fo.first] = std::move(fo.second);
     P->head_off.assign(B + 1, 0);
     P->node_off.assign(B + 1, 0);
     for (size_t f = 0; f < B; ++f) {
