@@ -342,6 +342,15 @@ def main():
             dropin_fps = dropin_driver_loop(cfg, frames[:48], gat, mlp)
         except Exception as e:                                  # an extra line of the report, never the reason a bench fails
             dropin_fps = 'failed: %s' % e
+    # ---- host-side ingest: the native JSON packer on the text of 512 of these frames (all host threads; rank 0 only)
+    json_fps = None
+    if rank == 0:
+        try:
+            text = json.dumps(frames[:512]).encode()
+            best = min(_timed(lambda: pack.pack_json(text, cfg)) for _ in range(3))
+            json_fps = len(frames[:512]) / best
+        except Exception as e:
+            json_fps = 'failed: %s' % e
     e2e_ms = 1e3 * float(np.mean(e2e_t))
     d2h = sum(v.numel() * v.element_size() for v in out.values() if hasattr(v, 'numel'))
     # ---- per-kernel-class timing for the roofline (separate pass, CUDA events around each class)
@@ -404,7 +413,7 @@ def main():
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
                 'cpu_baseline': cpu_line,
                 'persons_found_per_frame': P / args.frames,
-                'dropin_driver_loop_frames_per_s': dropin_fps,
+                'dropin_driver_loop_frames_per_s': dropin_fps, 'json_pack_frames_per_s': json_fps,
                 'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
                 'latency_note': 'one frame per call, host buffers in / host results out: infer_host_graph (CUDA graph per batch '
                                 'shape) and, for comparison, the eager infer_host'}
@@ -611,6 +620,12 @@ def train_batch_workload(args, rank, world, local_rank):
                              'sample': '%d graphs in batches of 15 (the reference loader\'s batch size), one process' % n}}
     if rank == 0:
         print(json.dumps(line))
+
+
+def _timed(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
 
 
 def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
