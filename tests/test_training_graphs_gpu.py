@@ -90,6 +90,22 @@ def test_training_dataset_batch_and_forward_against_reference(mode, tmp_path):
         assert np.array_equal(arr, gz[pre + 'proposals']), (mode, i)
         n_props += len(arr)
     assert n_props > 0
+    # ---- the loop body of test/sm_metrics_without_gt.py:107-135: DataLoader batch of ONE graph through collate, forward,
+    # proposals on the (one-member) batched graph ----
+    for i in range(min(3, len(recs))):
+        sg, _, sidx = collate([ds[i]], dgl, device)
+        pre = '%s/%d/' % (mode, i)
+        model.g = sg
+        for layer in model.layers:
+            layer.g = sg
+        out1 = torch.squeeze(model(sg.ndata['h'].to(device).float(), sg))
+        assert sg.nodes().tolist() == list(range(recs[i]['n_nodes']))
+        props = smu.get_person_proposal_from_network_output(torch.from_numpy(gz[pre + 'scores']), sg, torch.squeeze(sidx), ds[i][3], None, 0.5)
+        arr = np.array([[-1 if p[c] is None else p[c] for c in names] for p in props], dtype=np.int32).reshape(-1, len(names))
+        assert np.array_equal(arr, gz[pre + 'proposals']), (mode, i)
+        idx = np.arange(recs[i]['n_heads'], recs[i]['n_nodes'])
+        ref = gz[pre + 'scores']
+        assert (np.abs(out1.cpu().numpy()[idx] - ref[idx]) / np.abs(ref[idx])).max() <= 1e-4
     # ---- dgl.batch through the drivers' collate ----
     nb = gm['modes'][mode]['batch']
     bg, blabels, bindices = collate([ds[i] for i in range(nb)], dgl, device)
