@@ -114,3 +114,24 @@ def test_binary_ingest_roundtrip(tmp_path):
     pb = pack.pack_frames([meta['frames'][t] for t in meta['cases']], cfg, keep_json=False)
     pb.save(str(tmp_path / 'batch.npz'))
     same(pack.PackedBatch.load(str(tmp_path / 'batch.npz')), pb)
+
+
+@pytest.mark.parametrize('config', helpers.CONFIGS)
+def test_pack_frames_fast_is_identical(config):
+    """pack_frames_fast (camera payload strings handed to the native packer) against the Python packer: same arrays bit for
+    bit, same skeleton dicts and per-camera indices - golden frames plus ragged ones (missing joints, unseen persons,
+    joint-less skeletons), one frame at a time and as a batch; inline-list payloads fall back to pack_frames."""
+    cfg, npz, meta = helpers.load_golden(config)
+    frames = [meta['frames'][t] for t in meta['cases']]
+    frames += [helpers.synth.make_frame(cfg, 900 + i, 3, drop_joint_p=0.4, drop_view_p=0.3, rand_conf=True, keep_empty=True) for i in range(12)]
+    keys = ('sk_xy', 'sk_vp', 'sk_mask', 'sk_cam', 'head_off', 'node_off')
+    for batch in [[f] for f in frames] + [frames]:
+        a, b = pack.pack_frames(batch, cfg), pack.pack_frames_fast(batch, cfg)
+        assert all(np.array_equal(getattr(a, k), getattr(b, k)) for k in keys)
+        assert (a.max_heads, a.max_enodes, a.n_frames) == (b.max_heads, b.max_enodes, b.n_frames)
+        assert a.skeletons == b.skeletons and a.skeleton_index == b.skeleton_index
+    c = pack.pack_frames_fast(frames, cfg, keep_json=False)
+    assert c.skeletons is None and np.array_equal(c.sk_xy, a.sk_xy)
+    inline = [{cam: [json.loads(p[0])] + list(p[1:]) for cam, p in f.items()} for f in frames[:3]]
+    d, e = pack.pack_frames_fast(inline, cfg), pack.pack_frames(inline, cfg)
+    assert all(np.array_equal(getattr(d, k), getattr(e, k)) for k in keys)
