@@ -105,8 +105,10 @@ class DeviceBatch:
 class HostBatch:
     """Pinned host copy of a PackedBatch, so host->device copies are asynchronous DMA."""
 
-    def __init__(self, pb: PackedBatch):
-        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory() if torch.cuda.is_available() \
+    def __init__(self, pb: PackedBatch, pinned: bool = True):
+        # pinned=False: plain host tensors (page-locking six small arrays costs more than a live frame's copy saves;
+        # infer_host_graph stages through its own pinned buffers anyway)
+        pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory() if pinned and torch.cuda.is_available() \
             else torch.from_numpy(np.ascontiguousarray(a)).to(dt)
         self.pb = pb
         self.sk_xy = pin(pb.sk_xy, torch.float64)
@@ -720,6 +722,15 @@ class PosePipeline:
             return self.infer_host(hb)
         return dict(n_persons=h_out['n_persons'], person_off=h_out['person_off'], person_sk=h_out['person_sk'][:P],
                     n_persons_total=P, joints=h_out['joints'][:P], valid=h_out['valid'][:P])
+
+    def infer_frames(self, frames):
+        """Live frames as the reference hands them around - a list of `{camera: [json_string, timestamp, ...]}` dicts (or one
+        such dict) - to person proposals and joints on the host: native packing of the payload strings, one CUDA-graph
+        replay per batch shape (infer_host_graph). Returns what infer_host returns."""
+        from .pack import pack_frames_fast
+        if isinstance(frames, dict):
+            frames = [frames]
+        return self.infer_host_graph(HostBatch(pack_frames_fast(frames, self.cfg, keep_json=False), pinned=False))
 
     def infer_host_stream(self, batches):
         """Generator over host batches: yields the host results of each batch, in order. The host->device copy of

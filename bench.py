@@ -312,7 +312,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---- single-frame latency: one frame per call through the same public host API (rank 0 only)
-    p50_ms = p50_eager_ms = p99_ms = None
+    p50_ms = p50_eager_ms = p99_ms = p50_dict_ms = None
     if rank == 0 and args.latency_frames > 0:
         singles = [pm.HostBatch(pb.slice(i, i + 1)) for i in range(min(32, pb.n_frames))]
         lat = []
@@ -334,6 +334,15 @@ def main():
                 lat.append(time.perf_counter() - t0)
         p50_ms = 1e3 * float(np.median(lat))
         p99_ms = 1e3 * float(np.percentile(lat, 99))
+        lat = []
+        for i in range(args.latency_frames + 40):           # from the reference's frame dict (JSON strings per camera) to host results
+            fr = frames[i % min(32, len(frames))]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pipe.infer_frames(fr)
+            if i >= 40:
+                lat.append(time.perf_counter() - t0)
+        p50_dict_ms = 1e3 * float(np.median(lat))
     # ---- the reference driver's own per-frame loop on the drop-in modules (JSON strings in, python dicts out):
     # what an unmodified test/metrics_from_model.py gets with the shadow directory first on sys.path (rank 0 only)
     dropin_fps = None
@@ -415,8 +424,10 @@ def main():
                 'persons_found_per_frame': P / args.frames,
                 'dropin_driver_loop_frames_per_s': dropin_fps, 'json_pack_frames_per_s': json_fps,
                 'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
+                'p50_frame_latency_from_dict_ms': p50_dict_ms,
                 'latency_note': 'one frame per call, host buffers in / host results out: infer_host_graph (CUDA graph per batch '
-                                'shape) and, for comparison, the eager infer_host'}
+                                'shape) and, for comparison, the eager infer_host; from_dict = infer_frames, packing of the '
+                                'reference frame dict (JSON strings) included'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

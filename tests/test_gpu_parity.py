@@ -632,3 +632,20 @@ def test_cabi_argument_errors_on_device():
     assert lin(7) == -1 and 'linear' in msg()                                            # TMA store needs a 16-byte row pitch
     torch.cuda.synchronize()
     assert pipe.infer(db)['n_persons_total'] >= 0
+
+
+def test_infer_frames_from_reference_dicts():
+    """infer_frames (reference frame dicts -> native packing -> CUDA-graph replay) returns what infer_host returns for the
+    same frames packed by the Python packer."""
+    pipe = get_pipe('panoptic')
+    cfg = pipe.cfg
+    frames = [helpers.synth.make_frame(cfg, 820 + i, 4, drop_joint_p=0.1) for i in range(4)]
+    for batch in ([frames[0]], [frames[1]], frames, frames[2]):
+        want_frames = batch if isinstance(batch, list) else [batch]
+        want = pipe.infer_host(pipeline_mod.HostBatch(pack_mod.pack_frames([{c: f[c] for c in f} for f in want_frames], cfg)))
+        want = {k: (v.clone() if hasattr(v, 'clone') else v) for k, v in want.items()}
+        got = pipe.infer_frames(batch)
+        assert got['n_persons_total'] == want['n_persons_total']
+        assert torch.equal(got['person_sk'], want['person_sk']) and torch.equal(got['person_off'], want['person_off'])
+        if want['n_persons_total']:
+            assert (got['joints'] - want['joints']).abs().max().item() <= 1e-5
