@@ -19,7 +19,8 @@ class Cameras(C.Structure):
     _fields_ = [('n_cameras', C.c_int32), ('v_sm', C.c_int32), ('v_pe', C.c_int32),
                 ('image_width', C.c_float), ('image_height', C.c_float),
                 ('sm_slot', C.c_void_p), ('pe_slot', C.c_void_p), ('kinv32', C.c_void_p),
-                ('t_cam2root32', C.c_void_p), ('k64', C.c_void_p), ('dist64', C.c_void_p), ('p64', C.c_void_p)]
+                ('t_cam2root32', C.c_void_p), ('k64', C.c_void_p), ('dist64', C.c_void_p), ('p64', C.c_void_p),
+                ('t_cam2root32_sm', C.c_void_p)]
 
 
 class B200PoseError(RuntimeError):

@@ -78,6 +78,15 @@ class CameraConfig:
     def used_pe_names(self) -> List[str]:
         return [self.camera_names[i] for i in self.used_pe]
 
+    def sm_table_camera(self, c: int) -> int:
+        """Camera whose fp32 tables (K^-1, camera->root, centre) the head features of camera c are built from.
+        graph_generator.py:38-52 appends the tables walking camera_names and keeping the cameras that are in
+        used_cameras_skeleton_matching; HumanGraphFromView indexes them with used_cameras_skeleton_matching.index(camera)
+        (:232-233): slot s holds the s-th used camera in rig order. c itself whenever the used list is in rig order."""
+        if c not in self.used_sm:
+            return c
+        return sorted(self.used_sm)[self.used_sm.index(c)]
+
     def K32(self, c: int) -> np.ndarray:
         """3x3 float32 intrinsics, as torch.tensor([[fx,0,cx],...]) (pose_estimator_utils.py:17-30)."""
         return np.array([[self.fx[c], 0.0, self.cx[c]],

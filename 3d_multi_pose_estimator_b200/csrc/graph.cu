@@ -387,7 +387,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_node_features(int
 {
     B2_CHECK_ARG(cams && head_off && node_off && sk_xy && sk_vp && sk_mask && sk_cam, "node_features: null input");
     FeatureTables t;
-    t.sm_slot = cams->sm_slot; t.kinv32 = cams->kinv32; t.t_cam2root32 = cams->t_cam2root32;
+    t.sm_slot = cams->sm_slot; t.kinv32 = cams->kinv32; t.t_cam2root32 = cams->t_cam2root32_sm;
     t.W = cams->image_width; t.Hh = cams->image_height; t.F = 2 + 180 * cams->v_sm;
     cudaStream_t st = (cudaStream_t)stream;
     if (feats_f32 && n_frames > 0) {

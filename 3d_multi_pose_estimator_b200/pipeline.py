@@ -59,18 +59,20 @@ class DeviceCameras:
             sm_slot[c] = s
         for s, c in enumerate(cfg.used_pe):
             pe_slot[c] = s
-        kinv = np.stack([cfg.Kinv32(c) for c in range(Cn)]).astype(np.float32)
+        kinv = np.stack([cfg.Kinv32(cfg.sm_table_camera(c)) for c in range(Cn)]).astype(np.float32)
         tinv = np.stack([cfg.T_cam2root32(c) for c in range(Cn)]).astype(np.float32)
+        tinv_sm = np.stack([cfg.T_cam2root32(cfg.sm_table_camera(c)) for c in range(Cn)]).astype(np.float32)
         k64 = np.stack([[cfg.K64_from32(c)[0, 0], cfg.K64_from32(c)[1, 1], cfg.K64_from32(c)[0, 2], cfg.K64_from32(c)[1, 2]]
                         for c in range(Cn)]).astype(np.float64)
         dist = np.stack([cfg.dist64(c) for c in range(Cn)]).astype(np.float64)
         p64 = np.stack([cfg.P64(c) for c in range(Cn)]).astype(np.float64)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-        self.t = dict(sm_slot=up(sm_slot), pe_slot=up(pe_slot), kinv=up(kinv), tinv=up(tinv), k64=up(k64), dist=up(dist), p64=up(p64))
+        self.t = dict(sm_slot=up(sm_slot), pe_slot=up(pe_slot), kinv=up(kinv), tinv=up(tinv), k64=up(k64), dist=up(dist), p64=up(p64),
+                      tinv_sm=up(tinv_sm))
         self.struct = Cameras(Cn, cfg.V_sm, cfg.V_pe, float(cfg.image_width), float(cfg.image_height),
                               self.t['sm_slot'].data_ptr(), self.t['pe_slot'].data_ptr(), self.t['kinv'].data_ptr(),
                               self.t['tinv'].data_ptr(), self.t['k64'].data_ptr(), self.t['dist'].data_ptr(),
-                              self.t['p64'].data_ptr())
+                              self.t['p64'].data_ptr(), self.t['tinv_sm'].data_ptr())
 
     @property
     def ref(self):

@@ -53,16 +53,22 @@ def random_people(cfg: CameraConfig, rng: np.random.Generator, n_persons: int) -
 
 def make_frame(cfg: CameraConfig, seed: int, n_persons: int, *, drop_joint_p: float = 0.0,
                drop_view_p: float = 0.0, rand_conf: bool = False, keep_empty: bool = False,
-               with_gt: bool = False, camera_order: Optional[List[int]] = None) -> Dict[str, list]:
+               with_gt: bool = False, camera_order: Optional[List[int]] = None, all_cameras: bool = False,
+               pixel_noise: float = 0.0) -> Dict[str, list]:
     """One synthetic frame. Joints are kept iff in front of the camera and inside the image.
 
     drop_joint_p / drop_view_p / rand_conf add detector-like raggedness (missing joint keys,
     persons unseen in a view, valid=0 joints and non-unit confidences; keep_empty keeps skeletons
-    with no joints, which the reference skips as heads) for the parity tests.
+    with no joints, which the reference skips as heads) for the parity tests. all_cameras: the frame carries every
+    camera of the rig (parameters.camera_names), used or not. pixel_noise: sigma [px] of Gaussian detector noise on the
+    kept joints (its own random stream, so the noiseless frames of a seed do not change).
     """
     rng = np.random.default_rng(seed)
+    rng_noise = np.random.default_rng([seed, 0x5eed])
     people = random_people(cfg, rng, n_persons)
     cams = list(cfg.used_sm) if camera_order is None else list(camera_order)
+    if all_cameras and camera_order is None:
+        cams = list(range(cfg.n_cameras))
     frame: Dict[str, list] = {}
     for c in cams:
         skeletons = []
@@ -80,7 +86,11 @@ def make_frame(cfg: CameraConfig, seed: int, n_persons: int, *, drop_joint_p: fl
                 if rand_conf:
                     prob = float(np.round(rng.uniform(0.05, 1.0), 6))
                     valid = 1 if prob > 0.2 else 0
-                sk[str(j)] = [j, float(uv[j, 0]), float(uv[j, 1]), valid, prob]
+                u, v = float(uv[j, 0]), float(uv[j, 1])
+                if pixel_noise > 0:
+                    du, dv = rng_noise.normal(0.0, pixel_noise, size=2)
+                    u, v = u + float(du), v + float(dv)
+                sk[str(j)] = [j, u, v, valid, prob]
             if sk or keep_empty:
                 skeletons.append(sk)
         gt = []

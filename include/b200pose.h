@@ -51,11 +51,16 @@ typedef struct {
     float   image_width, image_height;
     const int32_t* sm_slot;            /* [C] camera -> index in used_cameras_skeleton_matching or -1 */
     const int32_t* pe_slot;            /* [C] camera -> index in used_cameras or -1 */
-    const float*   kinv32;             /* [C,3,3] torch.inverse(K_fp32)          (graph_generator.py:50) */
-    const float*   t_cam2root32;       /* [C,4,4] fp32(inv(T_root->cam))         (graph_generator.py:45) */
+    const float*   kinv32;             /* [C,3,3] torch.inverse(K_fp32) the head features of camera c read (graph_generator.py:50, see below) */
+    const float*   t_cam2root32;       /* [C,4,4] fp32(inv(T_root->cam)) of camera c    (dataset.py:38-41, indexed by camera_names.index) */
     const double*  k64;                /* [C,4]   fx,fy,cx,cy of fp64(K_fp32)    (dataset.py:43) */
     const double*  dist64;             /* [C,5]   k1,k2,p1,p2,k3                 (dataset.py:45) */
     const double*  p64;                /* [C,3,4] T_root->cam[0:3,:]             (dataset.py:47) */
+    /* [C,4,4] the camera->root table HumanGraphFromView reads for camera c. graph_generator.py:38-52 appends its tables
+     * walking camera_names (keeping the cameras in used_cameras_skeleton_matching) but :232-233 indexes them with
+     * used_cameras_skeleton_matching.index(camera): slot s holds the s-th used camera IN RIG ORDER. Equal to
+     * t_cam2root32 whenever the used list is in rig order (every shipped configuration); kinv32 follows the same rule. */
+    const float*   t_cam2root32_sm;
 } b200pose_cameras;
 
 /* ---------------------------------------------------------------------------------------------

@@ -53,9 +53,16 @@ class CameraTables:
         self.cfg = cfg
         self.sm_names = cfg.used_sm_names
         self.pe_names = cfg.used_pe_names
-        self.kinv32 = {n: cfg.Kinv32(cfg.camera_names.index(n)) for n in self.sm_names}
-        self.ti32 = {n: cfg.T_cam2root32(i) for i, n in enumerate(cfg.camera_names)}
-        self.centre32 = {n: cfg.centre32(i) for i, n in enumerate(cfg.camera_names)}
+        self.ti32 = {n: cfg.T_cam2root32(i) for i, n in enumerate(cfg.camera_names)}      # dataset.py:38-41, by camera name
+        # graph_generator.py:38-52 appends its tables walking parameters.camera_names and keeping the cameras that are in
+        # used_cameras_skeleton_matching, but HumanGraphFromView reads them at used_cameras_skeleton_matching.index(camera)
+        # (:232-233, :488-489): slot s of the used list gets the tables of the s-th used camera in camera_names order.
+        # The same camera whenever the two orders agree (every shipped configuration); pinned by the 'pansub' goldens.
+        in_rig_order = [n for n in cfg.camera_names if n in self.sm_names]
+        table_cam = {n: cfg.camera_names.index(in_rig_order[s]) for s, n in enumerate(self.sm_names)}
+        self.kinv32 = {n: cfg.Kinv32(table_cam[n]) for n in self.sm_names}
+        self.sm_ti32 = {n: cfg.T_cam2root32(table_cam[n]) for n in self.sm_names}
+        self.centre32 = {n: cfg.centre32(table_cam[n]) for n in self.sm_names}
         self.K64 = {n: cfg.K64_from32(i) for i, n in enumerate(cfg.camera_names)}
         self.dist64 = {n: cfg.dist64(i) for i, n in enumerate(cfg.camera_names)}
         self.P64 = {n: cfg.P64(i) for i, n in enumerate(cfg.camera_names)}
@@ -76,7 +83,7 @@ def head_feature_row(skeleton: dict, camera: str, tabs: CameraTables) -> Tuple[n
             continue
         x, y = values[1], values[2]
         ray_cam = _matvec_fma32(tabs.kinv32[camera], [f32(x), f32(y), f32(1.0)])       # :488
-        ray = _matvec_fma32(tabs.ti32[camera], [ray_cam[0], ray_cam[1], ray_cam[2], f32(0.0)])  # :489
+        ray = _matvec_fma32(tabs.sm_ti32[camera], [ray_cam[0], ray_cam[1], ray_cam[2], f32(0.0)])  # :489
         base = 2 + 180 * c + 10 * int(j)                             # FEATURES['3'] order :128-140
         row[base + 0] = (x - W / 2) / (W / 2)                        # :496 python float64 -> fp32 store
         row[base + 1] = (H / 2 - y) / (H / 2)                        # :497
@@ -567,7 +574,7 @@ def encode_person(person: Dict[str, dict], tabs: CameraTables) -> Optional[np.nd
             continue
         off = tabs.pe_names.index(cam) * (N_JOINTS * 14)
         Ti = tabs.ti32[cam]
-        centre = (tabs.centre32[cam] / f32(10.)).astype(f32)          # :247
+        centre = (Ti[:, 3] / f32(10.)).astype(f32)                    # :247 (T . [0,0,0,1] = last column)
         for j, values in sk.items():
             if j == "ID":
                 continue

@@ -42,6 +42,25 @@ def _cases(config):
                 ('rag', 6, 2, dict(drop_joint_p=0.3, drop_view_p=0.3, rand_conf=True, keep_empty=True))]
     if config == 'ring10':
         return [('p3', 3, 0, {}), ('rag', 4, 1, dict(drop_joint_p=0.3, drop_view_p=0.3, rand_conf=True))]
+    if config == 'arp6':
+        # the reference's shipped ARPLAB configuration (parameters.py:79-123): four room cameras + the narrow-baseline
+        # orinbot_l / orinbot_r stereo pair (0.12 m). 'stereo*': persons seen by the pair only, exact and with pixel noise
+        # (the ill-conditioned DLT of SURVEY.md 7-7); 'mixed': one room camera + the pair.
+        return [('p4', 4, 0, {}), ('p3n', 3, 1, dict(pixel_noise=1.5)),
+                ('rag', 5, 2, dict(drop_joint_p=0.3, drop_view_p=0.3, rand_conf=True, keep_empty=True, pixel_noise=0.7)),
+                ('stereo', 3, 3, dict(camera_order=[4, 5])), ('stereo_n', 4, 4, dict(camera_order=[5, 4], pixel_noise=1.0)),
+                ('mixed', 3, 5, dict(camera_order=[4, 1, 5], pixel_noise=0.5, drop_joint_p=0.2))]
+    if config == 'arp_robot2':
+        # parameters.py:110-112: models using only the robot cameras. Frames still carry every camera of the rig.
+        return [('p3', 3, 0, dict(all_cameras=True)), ('p4n', 4, 1, dict(all_cameras=True, pixel_noise=1.0)),
+                ('rag', 5, 2, dict(all_cameras=True, drop_joint_p=0.3, drop_view_p=0.2, rand_conf=True, keep_empty=True)),
+                ('only', 2, 3, dict(camera_order=[5, 4])), ('unused_only', 3, 4, dict(camera_order=[0, 2, 4]))]
+    if config == 'pansub':
+        # Panoptic with used_cameras_skeleton_matching = 4 of the 5 cameras in a permuted order and used_cameras = 3 of
+        # those; frames carry all five cameras (graph_generator.py:583-584 skips the unused one).
+        return [('p3', 3, 0, dict(all_cameras=True)), ('p4', 4, 1, dict(all_cameras=True)),
+                ('rag', 5, 2, dict(all_cameras=True, drop_joint_p=0.3, drop_view_p=0.3, rand_conf=True, keep_empty=True)),
+                ('order', 3, 3, dict(camera_order=[4, 0, 1, 3])), ('pe_absent', 3, 4, dict(camera_order=[2, 0, 3]))]
     raise ValueError(config)
 
 
@@ -55,6 +74,19 @@ def _activate(config):
         return ref_env.activate('ARPLAB', lambda p: p._replace(
             cameras=[0, 1, 2], camera_names=p.camera_names[:3], used_cameras=p.camera_names[:3],
             used_cameras_skeleton_matching=p.camera_names[:3], transformations_path=tm_path))
+    if config == 'arp6':
+        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_arp.pickle')
+        return ref_env.activate('ARPLAB', lambda p: p._replace(transformations_path=tm_path))
+    if config == 'arp_robot2':
+        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_arp.pickle')
+        return ref_env.activate('ARPLAB', lambda p: p._replace(
+            used_cameras=['orinbot_l', 'orinbot_r'], used_cameras_skeleton_matching=['orinbot_l', 'orinbot_r'],
+            transformations_path=tm_path))
+    if config == 'pansub':
+        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_panoptic.pickle')
+        return ref_env.activate('PANOPTIC', lambda p: p._replace(
+            used_cameras_skeleton_matching=['trackerd', 'trackerb', 'trackere', 'trackerc'],
+            used_cameras=['trackerb', 'trackere', 'trackerd'], transformations_path=tm_path))
     if config == 'ring10':
         # synthetic 10-camera rig: pickle a shim TransformManager for the reference to load
         sys.path.insert(0, os.path.join(REPO, 'oracle', 'shims'))
@@ -84,7 +116,10 @@ def build_reference_models(parameters, n_feats):
     gat = GAT2(None, 5, n_feats, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(), torch.nn.Sigmoid(),
                0., 0., 0.15, False, bias=True)
     torch.manual_seed(MLP_SEED)
-    mlp = PoseEstimatorMLP(input_dimensions=len(parameters.cameras) * len(parameters.joint_list) * parameters.numbers_per_joint,
+    # metrics_from_model.py:91 sizes the MLP with len(parameters.cameras), show_results_from_model.py:123 with
+    # len(parameters.used_cameras); the encoder emits len(used_cameras) blocks (dataset.py:129), so only the latter
+    # runs when used_cameras is a proper subset.
+    mlp = PoseEstimatorMLP(input_dimensions=len(parameters.used_cameras) * len(parameters.joint_list) * parameters.numbers_per_joint,
                            output_dimensions=54)
     return gat.eval(), mlp.eval()
 
@@ -136,7 +171,26 @@ def reference_frame(frame, parameters, gat, mlp, mods):
         rec['gat_l%d' % l] = o.numpy()
     rec['proposals'] = proposals_to_array(final_output, cam_names)
     # ---- stage 3 (metrics_from_model.py:243-280) + triangulation baseline (metrics_from_triangulation.py:234-249)
-    mlp_in, tri, tri_mask = [], [], []
+    stage3(rec, '', final_output, scenario, parameters, mlp, mods)
+    # the same stage on a FORCED assignment (k-th head of every camera = person k), so the encoder / DLT tiers are
+    # covered on every golden frame whatever the random-init scores make of the clustering
+    per_cam = {}
+    for h, c in enumerate(nodes_camera):
+        if c != '':
+            per_cam.setdefault(c, []).append(h)
+    forced = []
+    for k in range(max(len(v) for v in per_cam.values())):
+        person = {c: (per_cam[c][k] if c in per_cam and k < len(per_cam[c]) else None) for c in cam_names}
+        forced.append(person)
+    rec['forced_proposals'] = proposals_to_array(forced, cam_names)
+    stage3(rec, 'forced_', forced, scenario, parameters, mlp, mods)
+    return rec
+
+
+def stage3(rec, prefix, final_output, scenario, parameters, mlp, mods):
+    import torch
+    PoseEstimatorDataset = mods['dataset'].PoseEstimatorDataset
+    mlp_in, tri, tri_mask, enc_ok = [], [], [], []
     dsm = mods['dataset']
     for person in final_output:
         raw_input = {}
@@ -147,8 +201,11 @@ def reference_frame(frame, parameters, gat, mlp, mods):
                 raw_input[camera] = [json.dumps([sk])]
                 for j, values in sk.items():
                     points_2D.setdefault(j, {})[camera] = [values[1], values[2]]
-        ds = PoseEstimatorDataset(raw_input, parameters.cameras, parameters.joint_list, save=False)
-        mlp_in.append(ds[0][0].numpy())
+        try:
+            ds = PoseEstimatorDataset(raw_input, parameters.cameras, parameters.joint_list, save=False)
+            mlp_in.append(ds[0][0].numpy()); enc_ok.append(1)
+        except RuntimeError:          # torch.stack([]) when the row is (almost) empty, dataset.py:287-298
+            mlp_in.append(np.zeros(len(parameters.used_cameras) * 252, np.float32)); enc_ok.append(0)
         r = mods['utils'].triangulate(points_2D, dsm.camera_matrices, dsm.distortion_coefficients,
                                       dsm.projection_matrices, parameters.axes_3D['Y'][0])
         t = np.zeros((18, 3)); m = np.zeros(18, dtype=np.uint8)
@@ -157,10 +214,10 @@ def reference_frame(frame, parameters, gat, mlp, mods):
         tri.append(t); tri_mask.append(m)
     if mlp_in:
         x = torch.from_numpy(np.stack(mlp_in))
-        rec['mlp_in'] = x.numpy()
-        rec['mlp_out'] = mlp(x).numpy()
-        rec['tri'] = np.stack(tri); rec['tri_mask'] = np.stack(tri_mask)
-    return rec
+        rec[prefix + 'mlp_in'] = x.numpy()
+        rec[prefix + 'mlp_out'] = mlp(x).numpy()
+        rec[prefix + 'enc_ok'] = np.array(enc_ok, np.uint8)
+        rec[prefix + 'tri'] = np.stack(tri); rec[prefix + 'tri_mask'] = np.stack(tri_mask)
 
 
 def proposals_to_array(final_output, cam_names):
@@ -255,10 +312,11 @@ def run_config(config):
     out['centre32'] = np.stack([m.numpy() for m in graph_generator.all_cameras_from_root])
     cases = _cases(config)
     frames = {tag: synth.make_frame(cfg, seed, P, **kw) for tag, P, seed, kw in cases}
-    calib_frames = [synth.make_frame(cfg, 1000 + i, 4 if config != 'arp3' else 8) for i in range(2)]
+    calib_frames = [synth.make_frame(cfg, 1000 + i, 4 if config != 'arp3' else 8, all_cameras=config in ('arp_robot2', 'pansub')) for i in range(2)]
     gain, shift, z = calibrate(gat, calib_frames, parameters, mods)
     print(config, 'calibration gain %.4f shift %.6f -> logits std %.3f median %.4f' % (gain, shift, z.std(), np.median(z)))
     meta = dict(config=config, cases=[c[0] for c in cases], gat_seed=GAT_SEED, mlp_seed=MLP_SEED,
+                mlp_in_dim=int(mlp.layers[1].in_features),
                 calib_gain=gain, calib_shift=shift,
                 gat_last_fc2_bias=float(gat.layers[-1].fc2.bias[0]),
                 gat_checksum=checksum(gat.state_dict()), mlp_checksum=checksum(mlp.state_dict()),
@@ -282,7 +340,7 @@ def run_config(config):
         graphs.append((tag, sc.graphs[0], torch.squeeze(sc.data['edge_nodes_indices'][0]), sc.data['nodes_camera'][0]))
         print(config, tag, 'N=%d E=%d persons=%d' % (rec['n_nodes'], len(rec['src']), len(rec['proposals'])),
               'score range %.3f..%.3f' % (rec['scores'][rec['indices']].min(), rec['scores'][rec['indices']].max()))
-    fuzz = cluster_fuzz(graphs, parameters, mods, np.random.default_rng(7), 240 if config != 'ring10' else 60)
+    fuzz = cluster_fuzz(graphs, parameters, mods, np.random.default_rng(7), 240 if config in ('panoptic', 'arp3') else 60)
     meta['fuzz_tags'] = [f[0] for f in fuzz]
     for i, (tag, s, arr) in enumerate(fuzz):
         out['fuzz/%d/scores' % i] = s

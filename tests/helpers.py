@@ -12,7 +12,10 @@ pkg = importlib.import_module('3d_multi_pose_estimator_b200')
 weights_mod = importlib.import_module('3d_multi_pose_estimator_b200.weights')
 synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
 
-CONFIGS = ['panoptic', 'arp3', 'ring10']
+# panoptic / arp3 / ring10: BASELINE configs 1-2 / 3 / 5; arp6: the reference's shipped ARPLAB rig (narrow-baseline stereo
+# pair included); arp_robot2: its robot-cameras-only variant (parameters.py:110-112: used cameras a subset of the rig);
+# pansub: Panoptic with a permuted 4-of-5 skeleton-matching set and a 3-camera pose-estimator set
+CONFIGS = ['panoptic', 'arp3', 'ring10', 'arp6', 'arp_robot2', 'pansub']
 
 
 @functools.lru_cache(maxsize=None)
@@ -32,7 +35,7 @@ def golden_weights(config):
     gat = weights_mod.make_gat_state(cfg.n_features_sm, meta['gat_seed'])
     gat['layers.4.fc2.weight'] = torch.from_numpy(npz['gat_last_fc2_weight'].copy())
     gat['layers.4.fc2.bias'] = torch.from_numpy(npz['gat_last_fc2_bias'].copy())
-    mlp = weights_mod.make_mlp_state(cfg.n_cameras * 18 * 14, 54, meta['mlp_seed'])
+    mlp = weights_mod.make_mlp_state(meta.get('mlp_in_dim', cfg.n_cameras * 18 * 14), 54, meta['mlp_seed'])
     return gat, mlp
 
 

@@ -9,6 +9,8 @@ import torch
 
 import dropin_env
 import helpers
+from oracle import check as OC
+from oracle import pose_oracle as O
 
 pytestmark = pytest.mark.gpu
 
@@ -57,7 +59,7 @@ def run_frame(mods, cfg, model, mlp, frame):
                 results=results, raw_inputs=raw_inputs)
 
 
-@pytest.mark.parametrize('config', ['panoptic', 'arp3'])
+@pytest.mark.parametrize('config', ['panoptic', 'arp3', 'arp6', 'arp_robot2', 'pansub'])
 def test_driver_loop_against_reference_goldens(config):
     cfg, npz, meta = helpers.load_golden(config)
     mods = dropin_env.activate(cfg)
@@ -68,12 +70,14 @@ def test_driver_loop_against_reference_goldens(config):
                               torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
     model.load_state_dict(gat_state)
     model = model.to(device)
-    mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)
+    mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=meta['mlp_in_dim'], output_dimensions=54)   # show_results_from_model.py:123
     mlp.load_state_dict(mlp_state)
     mlp = mlp.to(device)
     pu = mods['pose_estimator_utils']
     names = cfg.used_sm_names
     n_checked = 0
+    explained = []
+    tabs = O.CameraTables(cfg)
     for tag in meta['cases']:
         out = run_frame(mods, cfg, model, mlp, meta['frames'][tag])
         if tag in meta['no_graph']:
@@ -99,12 +103,17 @@ def test_driver_loop_against_reference_goldens(config):
         want = npz[tag + '/proposals']
         got = np.array([[-1 if p[c] is None else p[c] for c in names] for p in out['final_output']], dtype=np.int32).reshape(-1, len(names))
         if not np.array_equal(got, want):
-            continue                                    # a sub-tolerance score gap decided the greedy order
+            # accepted only with a full attribution to a score gap below the tolerance; raises otherwise
+            f = meta['frames'][tag]
+            og = O.build_graph({c: f[c] for c in f if json.loads(f[c][0])}, tabs)
+            explained.append((tag, OC.explain_assignment_mismatch(ref, out['outputs'], og, cfg, got)))
+            continue
         n_checked += 1
         for p in range(len(want)):
             assert np.abs(out['mlp_in'][p] - npz[tag + '/mlp_in'][p]).max() <= 1e-6, (tag, p)
-        ref_j = npz[tag + '/mlp_out'] * np.float32(10.)
-        assert np.abs(out['results'] - ref_j).max() <= 0.5e-3, tag
+        if len(want):
+            ref_j = npz[tag + '/mlp_out'] * np.float32(10.)
+            assert np.abs(out['results'] - ref_j).max() <= 0.5e-3, tag
         # triangulation baseline, fed like test/metrics_from_triangulation.py:237-249
         cam_matrix = {c: cfg.K32(i) for i, c in enumerate(cfg.camera_names)}
         dist = {c: cfg.dist64(i) for i, c in enumerate(cfg.camera_names)}
@@ -121,7 +130,8 @@ def test_driver_loop_against_reference_goldens(config):
             for j, X in res.items():
                 assert X.shape == (3, 1)
                 assert np.abs(X[:, 0] - npz[tag + '/tri'][p][int(j)]).max() <= 1e-7
-    assert n_checked >= len(meta['cases']) // 2
+    print('drop-in driver loop %s: %d frames equal the reference, explained near-ties: %s' % (config, n_checked, explained))
+    assert n_checked > 0
 
 
 def test_proposals_accept_python_lists_and_custom_threshold():

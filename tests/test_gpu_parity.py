@@ -12,6 +12,7 @@ import torch
 
 import helpers
 from oracle import pose_oracle as O
+from oracle import check as OC
 
 pytestmark = pytest.mark.gpu
 
@@ -219,16 +220,21 @@ def test_cluster_fuzz_bit_exact(config):
     assert len(fuzz_tags) >= 60
 
 
+@pytest.mark.parametrize('prefix', ['', 'forced_'])
 @pytest.mark.parametrize('config', helpers.CONFIGS)
-def test_encoder_mlp_triangulation_vs_reference(config):
+def test_encoder_mlp_triangulation_vs_reference(config, prefix):
+    """Stage 3 on the reference's own proposals ('') and on the forced assignment of the goldens (k-th head of every camera
+    = person k: covers every frame, e.g. the narrow-baseline stereo frames of arp6 / arp_robot2 whatever the clustering
+    made of them, single-view persons, and cameras that are matched but not used by the pose estimator)."""
     cfg, npz, meta = helpers.load_golden(config)
     pipe = get_pipe(config)
     tags, pb, db = golden_batch(config)
     g = pipe.build_graph(db, with_coo=False)
-    # person assignment from the reference's proposals
     rows, owner = [], []
     for b, tag in enumerate(tags):
-        for p, person in enumerate(npz[tag + '/proposals']):
+        if tag + '/' + prefix + 'mlp_in' not in npz:
+            continue
+        for p, person in enumerate(npz[tag + '/' + prefix + 'proposals']):
             r = np.full(cfg.n_cameras, -1, np.int32)
             for s, h in enumerate(person):
                 if h >= 0:
@@ -239,26 +245,42 @@ def test_encoder_mlp_triangulation_vs_reference(config):
     x, valid, xf = pipe.encode_persons(db, P, person_sk, want_f32=True)
     xf = xf.cpu().numpy()
     joints = pipe.mlp_forward(x, P).cpu().numpy()
-    xyz, mask = pipe.triangulate(db, P, person_sk)
+    # triangulate() works on the views its caller hands it (metrics_from_triangulation.py:237-247); the goldens fed it the
+    # pose-estimator cameras of each person
+    tri_sk = person_sk.clone()
+    tri_sk[:, [c for c in range(cfg.n_cameras) if c not in cfg.used_pe]] = -1
+    xyz, mask = pipe.triangulate(db, P, tri_sk)
     xyz, mask = xyz.cpu().numpy(), mask.cpu().numpy()
-    assert valid.cpu().numpy().all()
-    worst_j = 0.0
+    valid = valid.cpu().numpy()
+    x32 = x.to_f32().cpu().numpy()
+    worst_j = worst_t = worst_x = 0.0
     for i, (tag, p) in enumerate(owner):
-        ref_in = npz[tag + '/mlp_in'][p]
-        assert np.abs(xf[i] - ref_in).max() <= 1e-6, (tag, p, np.abs(xf[i] - ref_in).max())
-        assert np.abs(x.to_f32()[i].cpu().numpy() - ref_in).max() <= 1e-5
-        ref_j = npz[tag + '/mlp_out'][p] * np.float32(10.)
-        worst_j = max(worst_j, np.abs(joints[i] - ref_j).max())
-        assert np.abs(joints[i] - ref_j).max() <= JOINT_TOL_M, (tag, p)
-        assert np.array_equal(mask[i], npz[tag + '/tri_mask'][p])
-        assert np.abs(xyz[i] - npz[tag + '/tri'][p]).max() <= 1e-7, (tag, p, np.abs(xyz[i] - npz[tag + '/tri'][p]).max())
-    print('worst joint deviation [mm]', config, worst_j * 1e3)
+        key = tag + '/' + prefix
+        # the reference raises for a row with sum|v| <= 1 (dataset.py:287-298); the batched path flags it instead
+        assert bool(valid[i]) == bool(npz[key + 'enc_ok'][p]), (tag, p)
+        if valid[i]:
+            ref_in = npz[key + 'mlp_in'][p]
+            worst_x = max(worst_x, np.abs(xf[i] - ref_in).max())
+            assert np.abs(xf[i] - ref_in).max() <= 1e-6, (tag, p, np.abs(xf[i] - ref_in).max())
+            assert (np.abs(x32[i] - ref_in) <= 1e-6 + 2.0 ** -16 * np.abs(ref_in)).all()      # hi + lo bf16 planes: 16 mantissa bits
+            ref_j = npz[key + 'mlp_out'][p] * np.float32(10.)
+            worst_j = max(worst_j, np.abs(joints[i] - ref_j).max())
+            assert np.abs(joints[i] - ref_j).max() <= JOINT_TOL_M, (tag, p)
+        assert np.array_equal(mask[i], npz[key + 'tri_mask'][p]), (tag, p)
+        d = np.abs(xyz[i] - npz[key + 'tri'][p]).max()
+        worst_t = max(worst_t, d)
+        assert d <= 1e-7, (tag, p, d)
+    assert len(owner) > 0
+    print('stage 3 %s%s: %d persons, worst MLP-input deviation %.2e, worst joint deviation %.4f mm, worst triangulation deviation %.2e m'
+          % (config, ' (forced)' if prefix else '', len(owner), worst_x, worst_j * 1e3, worst_t))
 
 
 @pytest.mark.parametrize('config', helpers.CONFIGS)
 def test_end_to_end_vs_reference(config):
-    """Whole path on a ragged batch of the golden frames. Person assignment must equal the reference's
-    unless a score gap below the score tolerance decides the greedy order (counted)."""
+    """Whole path on a ragged batch of the golden frames. Person assignment must equal the reference's; a frame where it
+    does not is accepted only with a full attribution (oracle.check.explain_assignment_mismatch): scores within tolerance,
+    the oracle clustering of the GPU's scores IS the GPU's assignment, and the reference's sorted matchings hold a gap the
+    score tolerance cannot resolve. Everything else fails."""
     cfg, npz, meta = helpers.load_golden(config)
     pipe = get_pipe(config)
     tags, pb, db = golden_batch(config)
@@ -266,17 +288,23 @@ def test_end_to_end_vs_reference(config):
     ph, npers = res['person_heads'].cpu().numpy(), res['n_persons'].cpu().numpy()
     poff = res['person_off'].cpu().numpy()
     joints = res['joints'].cpu().numpy()
-    mismatched = 0
+    scores = res['scores'].cpu().numpy()
+    tabs = O.CameraTables(cfg)
+    explained = []
     for b, tag in enumerate(tags):
         want = npz[tag + '/proposals']
         got = ph[pb.head_off[b]:pb.head_off[b] + npers[b]]
         if not np.array_equal(got, want):
-            mismatched += 1
+            f = meta['frames'][tag]
+            og = O.build_graph({c: f[c] for c in f if json.loads(f[c][0])}, tabs)
+            why = OC.explain_assignment_mismatch(npz[tag + '/scores'], scores[pb.node_off[b]:pb.node_off[b + 1]], og, cfg, got)
+            explained.append((tag, why))
             continue
-        ref_j = npz[tag + '/mlp_out'] * np.float32(10.)
-        assert np.abs(joints[poff[b]:poff[b + 1]] - ref_j).max() <= JOINT_TOL_M, tag
-    print('end-to-end frames with different assignment:', mismatched, 'of', len(tags))
-    assert mismatched <= max(1, len(tags) // 4)
+        if len(want):
+            ref_j = npz[tag + '/mlp_out'] * np.float32(10.)
+            assert np.abs(joints[poff[b]:poff[b + 1]] - ref_j).max() <= JOINT_TOL_M, tag
+    print('end-to-end %s: %d of %d frames equal the reference assignment; explained near-ties: %s' % (config, len(tags) - len(explained), len(tags), explained))
+    assert len(explained) < len(tags)
 
 
 def test_against_oracle_on_fresh_frames():
@@ -341,6 +369,18 @@ def test_full_size_properties():
     assert np.array_equal(half['scores'].cpu().numpy(), scores[pb.node_off[512]:])
     assert np.array_equal(half['n_persons'].cpu().numpy(), npers[512:])
     assert np.isfinite(joints).all() and npers.sum() > 0
+    # the composed full-size run against the oracle: 16 frames spread over the batch (scores, assignment on the GPU's
+    # scores, joints) - the kernels the 1024-frame step dispatches, not the small-batch ones
+    gat_w, mlp_w = helpers.golden_weights(config)
+    gat_w, mlp_w = helpers.np_state(gat_w), helpers.np_state(mlp_w)
+    ph = res['person_heads'].cpu().numpy()
+    sample = [0, 63, 64, 130, 197, 264, 331, 398, 465, 511, 512, 600, 777, 901, 1000, 1023]
+    rep = OC.check_frames(cfg, [base[i % 64] for i in sample], gat_w, mlp_w,
+                          [scores[pb.node_off[i]:pb.node_off[i + 1]] for i in sample],
+                          [ph[pb.head_off[i]:pb.head_off[i] + npers[i]] for i in sample],
+                          [joints[poff[i]:poff[i + 1]] for i in sample])
+    print('full-size batch vs oracle:', rep)
+    assert rep['persons'] > 0
 
 
 def test_empty_and_degenerate_batches():
