@@ -58,10 +58,10 @@ class PoseEstimatorDataset(torch.utils.data.Dataset):
             self.data.append(x[0])
         # torch.stack([]) raises in the reference when nothing was kept (:287-298); keep that behaviour
         self.data = torch.stack(self.data)
+        # the reference builds its rows on the host and only moves them when a device is given (:291-298); its callers
+        # rely on that (test/reprojection_error.py:310-325 feeds them to a host-side MLP and numpy)
+        self.data = self.data.to(device='cpu' if device is None else device)
         self.orig_data = self.data
-        if device is not None:
-            self.data = self.data.to(device=device)
-            self.orig_data = self.data
 
     def __len__(self):
         return self.data.shape[0]

@@ -72,6 +72,7 @@ def make_frame(cfg: CameraConfig, seed: int, n_persons: int, *, drop_joint_p: fl
     frame: Dict[str, list] = {}
     for c in cams:
         skeletons = []
+        kept = []
         for p in range(n_persons):
             if drop_view_p > 0 and rng.random() < drop_view_p:
                 continue
@@ -93,10 +94,11 @@ def make_frame(cfg: CameraConfig, seed: int, n_persons: int, *, drop_joint_p: fl
                 sk[str(j)] = [j, u, v, valid, prob]
             if sk or keep_empty:
                 skeletons.append(sk)
+                kept.append(p)
         gt = []
-        if with_gt:
+        if with_gt:      # bodies_3D in cm, one entry per skeleton of this camera (test/sm_metrics.py:118-121 indexes them together)
             gt = [dict({str(j): (people[p, j] * 100.0).tolist() for j in range(N_JOINTS)}, **{'-1': [0, 0, 0]})
-                  for p in range(n_persons)]
+                  for p in kept]
         frame[cfg.camera_names[c]] = [json.dumps(skeletons), 0.0, 'no_image', gt]
     return frame
 

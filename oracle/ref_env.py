@@ -7,13 +7,16 @@ then the reference's own directories in the order its scripts append them
 (test/metrics_from_model.py:12,17,23), cwd = <reference>/test because the reference resolves
 '../tm_panoptic.pickle' relative to cwd (parameters.py:70).
 
-The reference tree only exists in the build container; nothing on the GPU box may call this.
+The reference tree only exists in the build container; on the GPU box the staged copy under baseline/_ref (same bytes,
+digests in tests/golden/drivers/reference_manifest.sha256.json) is what this activates.
 """
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get('B200POSE_REFERENCE_ROOT', '/root/reference')
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree itself (build container) or the unmodified copy staged by oracle/make_ref.py (travels to the GPU box)
+_STAGED = os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')
+REFERENCE_ROOT = os.environ.get('B200POSE_REFERENCE_ROOT') or ('/root/reference' if os.path.isdir('/root/reference/skeleton_matching') else _STAGED)
 
 
 def reference_available() -> bool:

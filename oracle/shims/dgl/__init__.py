@@ -56,8 +56,10 @@ def graph(data, num_nodes=None, idtype=torch.int64):
     return DGLGraph(src, dst, num_nodes, idtype)
 
 
-def save_graphs(path, graphs):
-    raise NotImplementedError("dgl shim: graph cache I/O is out of scope")
+def save_graphs(path, graphs, labels=None):
+    """The reference caches a non-test dataset next to the script (graph_generator.py:884-896). The cache only saves a
+    rebuild on the next run - it changes no result - so the shim writes nothing (has_cache() then stays False)."""
+    return None
 
 
 def load_graphs(path):

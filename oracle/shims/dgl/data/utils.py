@@ -2,8 +2,9 @@
 
 
 def save_info(path, info):
-    raise NotImplementedError
+    """Companion of dgl.save_graphs (graph_generator.py:896-899): a rebuild cache, nothing is written (see save_graphs)."""
+    return None
 
 
 def load_info(path):
-    raise NotImplementedError
+    raise NotImplementedError("dgl shim: no graph cache is ever written, so none can be loaded")
