@@ -192,6 +192,7 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
     return c;
 }
 
+#ifdef B200POSE_SELFTEST   // superseded / bring-up kernels: only in libb200pose_selftest.so (build.py --selftest), not in the product library
 // ------------------------------------------------------------------------------------------------
 // product kernel: TMA-fed, multi-stage
 // ------------------------------------------------------------------------------------------------
@@ -262,6 +263,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc_kernel(
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
+
+#endif  // B200POSE_SELFTEST
 
 // ------------------------------------------------------------------------------------------------
 // product kernel v2: persistent, double-buffered TMEM accumulators, TMA-store epilogue
@@ -684,6 +687,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     if (warp == 1) tmem_dealloc_n<NCTA>(tmem_base, ncols);
 }
 
+#ifdef B200POSE_SELFTEST   // superseded / bring-up kernels: only in libb200pose_selftest.so (build.py --selftest), not in the product library
 // ------------------------------------------------------------------------------------------------
 // Wide variant of the CTA-pair kernel for tall projections whose whole output width fits TMEM
 // (256 < N <= 512, i.e. 5..8 panels: the 400/420/320/336-wide GAT projections).
@@ -905,6 +909,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_wide_kernel(
     if (warp == 1) tmem_dealloc_n<2>(tmem_base, 512);
 }
 
+#endif  // B200POSE_SELFTEST
+
+#ifdef B200POSE_SELFTEST   // superseded / bring-up kernels: only in libb200pose_selftest.so (build.py --selftest), not in the product library
 // ------------------------------------------------------------------------------------------------
 // debug kernel: identical MMA + epilogue, but the tiles are written by ordinary stores (no TMA,
 // single stage). Used by the kernel self-test to separate tensor-map bugs from descriptor bugs.
@@ -1020,6 +1027,8 @@ __global__ void __launch_bounds__(256) gemm_split_simt_kernel(const GemmParams p
         }
     }
 }
+
+#endif  // B200POSE_SELFTEST
 
 // ------------------------------------------------------------------------------------------------
 // Small-M kernel (m <= 8 rows: the pose MLP of a single frame). With a handful of rows the projection is a
@@ -1296,6 +1305,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     p.w_hi = reinterpret_cast<const __nv_bfloat16*>(w_hi); p.w_lo = reinterpret_cast<const __nv_bfloat16*>(w_lo); p.ldw = ldw;
     p.bn = choose_bn(n);
     p.stages = 1;
+#ifdef B200POSE_SELFTEST
     if (impl == 1) {
         const int cols = (out_hi && ld_planes > n) ? ld_planes : n;     // also zero the K padding of the planes
         dim3 grid(ceil_div(cols, 64), ceil_div(m, 64));
@@ -1330,6 +1340,12 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
+#else
+    if (impl == 1 || impl == 2 || impl == 3 || impl == 6) {
+        set_error("linear: impl 1/2/3/6 are bring-up kernels of the self-test build (libb200pose_selftest.so), not part of the product library");
+        return B200POSE_E_UNSUPPORTED;
+    }
+#endif
     if ((impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight stream with A in registers: k split over the CTA's lanes, blocks of 32 / MMAX columns
         const int warps = ceil_div(kpad, 256);
@@ -1388,6 +1404,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+#ifdef B200POSE_SELFTEST
     // ---- wide pair kernel: tall projections whose whole width fits TMEM (5..8 panels): A streamed once per m-tile ----
     // Measured on B200 (GAT projections, 184320 rows): 1.43 ms per step against 1.20 ms for the two-n-tile pair kernel -
     // the 88 KB stages leave room for only two of them and the single-buffered accumulator exposes the epilogue, which
@@ -1418,6 +1435,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
             return B200POSE_OK;
         }
     }
+#endif
     q.tiles_n = ceil_div(q.panels_total, 4);
     q.tiles_m = ceil_div(m, kBM * ncta);
     // a handful of m-tiles (single-frame calls: ~180 graph nodes): one 64-column panel per tile, so that the k-loops of

@@ -13,6 +13,8 @@
 // converted exactly like Python's float(): a Clinger fast path for short decimals, strtod otherwise.
 // Pure host code (no CUDA calls): frames are parsed in parallel by std::thread workers.
 #include "common.cuh"
+#include <locale.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -163,6 +165,11 @@ static bool skip_value(Cur& c) {
     return c.fail("unterminated container");
 }
 
+static locale_t c_locale() {
+    static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    return loc;
+}
+
 // float(text) exactly as CPython does: correctly rounded. Fast path (Clinger): <= 15 significant digits and
 // |exp10| <= 22 are exact in double arithmetic; everything else goes through strtod.
 static bool parse_number(Cur& c, double& out) {
@@ -187,11 +194,19 @@ static bool parse_number(Cur& c, double& out) {
         while (p < c.end && *p >= '0' && *p <= '9') { if (ev < 10000) ev = ev * 10 + (*p - '0'); ++p; }
         exp10 += eneg ? -ev : ev;
     }
-    if (!any) {                               // NaN / Infinity / true / false / null: let strtod (or 0) decide
-        char* endp = nullptr;
-        out = strtod(s, &endp);
-        if (endp == s) { while (p < c.end && *p != ',' && *p != ']' && *p != '}') ++p; out = 0.0; c.p = p; return true; }
-        c.p = endp;
+    if (!any) {
+        // not a digit string: the literals Python's json module accepts in a number slot. The token is delimited inside
+        // [json, json + len) - the span need not be NUL-terminated - and compared explicitly (no strtod on caller memory).
+        const char* q = p;
+        while (q < c.end && *q != ',' && *q != ']' && *q != '}' && *q != ' ' && *q != '\n' && *q != '\t' && *q != '\r') ++q;
+        const size_t n = (size_t)(q - p);
+        auto is = [&](const char* lit) { return n == strlen(lit) && memcmp(p, lit, n) == 0; };
+        if (is("true")) out = 1.0;                    // float(True): what the reference's tensor / numpy stores make of it
+        else if (is("false")) out = 0.0;
+        else if (is("NaN")) out = NAN;
+        else if (is("Infinity")) out = neg ? -INFINITY : INFINITY;
+        else return c.fail("a joint entry is not a number (null or a malformed literal)");
+        c.p = q;
         return true;
     }
     static const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16,
@@ -227,8 +242,10 @@ static bool parse_number(Cur& c, double& out) {
     if (!done) {
         char buf[64];
         const size_t n = (size_t)(p - s);
-        if (n < sizeof(buf)) { memcpy(buf, s, n); buf[n] = 0; out = strtod(buf, nullptr); }
-        else { std::string t(s, n); out = strtod(t.c_str(), nullptr); }
+        // bounded NUL-terminated copy, parsed in the "C" locale whatever LC_NUMERIC the host application set (Qt viewers
+        // switch to the user's locale; a decimal comma would truncate every number here)
+        if (n < sizeof(buf)) { memcpy(buf, s, n); buf[n] = 0; out = strtod_l(buf, nullptr, c_locale()); }
+        else { std::string t(s, n); out = strtod_l(t.c_str(), nullptr, c_locale()); }
     }
     c.p = p;
     return true;

@@ -46,6 +46,21 @@ class PackedBatch:
     def n_edges(self) -> int:
         return self.n_heads + 5 * self.n_enodes
 
+    def validate(self) -> None:
+        """The declared frame plan (max_heads / max_enodes size shared-memory plans and the clustering scratch) must cover
+        every frame - a stale value in a hand-built or loaded batch would make kernels skip the frames that exceed it."""
+        if self.n_frames == 0:
+            return
+        H = np.diff(np.asarray(self.head_off, dtype=np.int64))
+        M = np.diff(np.asarray(self.node_off, dtype=np.int64)) - H
+        if len(H) != self.n_frames or (H < 0).any() or (M < 0).any():
+            raise ValueError('PackedBatch: head_off / node_off are not non-decreasing offset arrays of %d frames' % self.n_frames)
+        if int(H.max()) > self.max_heads or int(M.max()) > self.max_enodes:
+            raise ValueError('PackedBatch: a frame has %d heads / %d edge-nodes but the batch declares max_heads=%d, max_enodes=%d'
+                             % (int(H.max()), int(M.max()), self.max_heads, self.max_enodes))
+        if self.head_off[-1] != len(self.sk_cam):
+            raise ValueError('PackedBatch: head_off ends at %d but there are %d skeletons' % (int(self.head_off[-1]), len(self.sk_cam)))
+
     def input_bytes(self) -> int:
         return sum(a.nbytes for a in (self.sk_xy, self.sk_vp, self.sk_mask, self.sk_cam, self.head_off, self.node_off))
 

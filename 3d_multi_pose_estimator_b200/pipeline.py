@@ -26,6 +26,11 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def person_capacity(n_heads: int, min_views: int) -> int:
+    """Upper bound on the persons of a batch: disjoint components of >= min_views heads each."""
+    return max(n_heads // max(int(min_views), 1), 1)
+
+
 class Planes:
     """An fp32 matrix stored as hi/lo bf16 planes [rows, ld] (ld multiple of 64), zero padded."""
 
@@ -113,6 +118,7 @@ class HostBatch:
         pin = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).pin_memory() if pinned and torch.cuda.is_available() \
             else torch.from_numpy(np.ascontiguousarray(a)).to(dt)
         self.pb = pb
+        pb.validate()
         self.sk_xy = pin(pb.sk_xy, torch.float64)
         self.sk_vp = pin(pb.sk_vp, torch.float32)
         self.sk_mask = pin(pb.sk_mask.view(np.int32), torch.int32)
@@ -155,12 +161,14 @@ class HostBatch:
         cache[n_chunks] = out
         return out
 
-    def result_buffers(self, n_cameras: int, n_out: int):
-        """Pinned host buffers for the results of this batch (persons <= heads / 2: a person needs two views)."""
-        key = (n_cameras, n_out)
+    def result_buffers(self, n_cameras: int, n_out: int, min_views: int = 2):
+        """Pinned host buffers for the results of this batch. A person is a connected component of at least `min_views`
+        heads (parameters.min_number_of_views, skeleton_matching_utils.py:120) and components are disjoint, so there are at
+        most heads // min_views persons."""
+        key = (n_cameras, n_out, min_views)
         cache = self.__dict__.setdefault('_results', {})
         if key not in cache:
-            B, Pmax = self.pb.n_frames, max(self.pb.n_heads // 2, 1)
+            B, Pmax = self.pb.n_frames, person_capacity(self.pb.n_heads, min_views)
             mk = lambda shape, dt: (torch.empty(shape, dtype=dt).pin_memory() if torch.cuda.is_available() else torch.empty(shape, dtype=dt))
             cache[key] = dict(n_persons=mk((B,), torch.int32), person_off=mk((B + 1,), torch.int32),
                               person_sk=mk((Pmax, n_cameras), torch.int32), joints=mk((Pmax, max(n_out, 1)), torch.float32),
@@ -194,6 +202,20 @@ class GraphArrays:
         self.general = False
 
 
+def _on_own_device(fn):
+    """Public entry points run with the pipeline's device current: the kernels launch on that device's current stream and
+    cudaFuncSetAttribute is per device, so a PosePipeline('cuda:1') must not depend on what the caller left selected."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == self._dev_index_checked():
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class PosePipeline:
     """Weights + camera tables resident on one GPU; `infer()` runs a whole batch of frames.
 
@@ -220,6 +242,30 @@ class PosePipeline:
             self.gat = self.prepare_gat(gat_state) if gat_state is not None else None
             self.mlp = self.prepare_mlp(mlp_state) if mlp_state is not None else None
             torch.cuda.synchronize()
+
+    # the prepared weight planes; replacing them invalidates every captured CUDA graph (they hold the old plane addresses)
+    @property
+    def gat(self):
+        return self._gat
+
+    @gat.setter
+    def gat(self, layers):
+        self._gat = layers
+        self._weights_gen = getattr(self, '_weights_gen', 0) + 1
+
+    @property
+    def mlp(self):
+        return self._mlp
+
+    @mlp.setter
+    def mlp(self, layers):
+        self._mlp = layers
+        self._weights_gen = getattr(self, '_weights_gen', 0) + 1
+
+    def _dev_index_checked(self):
+        if self._dev_index is None:
+            self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return self._dev_index
 
     # ------------------------------------------------------------------ workspace
     def planes_ws(self, tag: str, rows: int, cols: int) -> Planes:
@@ -563,10 +609,12 @@ class PosePipeline:
             res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, res['person_sk'])
         return res
 
+    @_on_own_device
     def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):
         """graph build -> GAT -> clustering -> encoder -> MLP for every frame of a batch resident in HBM."""
         return self.stage_b(db, self.stage_a(db, with_coo=with_coo), want_triangulation=want_triangulation)
 
+    @_on_own_device
     def infer_host(self, hb: HostBatch, n_chunks: int = 1):
         """The public end-to-end call: pinned host buffers in, host results out.
 
@@ -591,7 +639,7 @@ class PosePipeline:
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 dbs.append(db); evs.append(ev)
-        out_bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0)
+        out_bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0, self.cfg.min_number_of_views)
         parts = []
         p_base = 0
 
@@ -640,8 +688,8 @@ class PosePipeline:
 
     # ------------------------------------------------------------------ low-latency path: one CUDA graph per batch shape
     def _stage_b_static(self, db: DeviceBatch, res: dict, p_bound: int, p_max: int):
-        """Stage 3 without the person-count readback: the person list is sized for p_bound = heads // 2 persons (a person
-        needs two views), the encoder and the MLP for p_max <= p_bound rows; rows past the real count keep person_sk = -1,
+        """Stage 3 without the person-count readback: the person list is sized for p_bound = heads // min_number_of_views
+        persons (disjoint components of at least that many heads), the encoder and the MLP for p_max <= p_bound rows; rows past the real count keep person_sk = -1,
         encode to zero rows with valid = 0 and are dropped on the host. This is what lets the whole step live in one CUDA
         graph."""
         Cn = self.cfg.n_cameras
@@ -655,6 +703,7 @@ class PosePipeline:
         joints = self.mlp_forward(x, p_max)
         return person_sk, valid, joints
 
+    @_on_own_device
     def infer_host_graph(self, hb: HostBatch, max_cached: int = 64):
         """The end-to-end call for live frames (one frame, or a few, per call): same inputs and outputs as infer_host, but
         the ~30 launches, the input copies and the result copies of a batch SHAPE (frames, heads, nodes) are captured once
@@ -666,7 +715,10 @@ class PosePipeline:
         pb = hb.pb
         if pb.n_heads == 0 or pb.n_nodes == pb.n_heads:          # nothing to match: the eager path handles the degenerate shapes
             return self.infer_host(hb)
-        key = (pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes)
+        # a captured graph bakes in everything its launches were given: the batch shape, but also the threshold, the
+        # kernel choices and the weight planes - all part of the key, so a change re-captures instead of replaying stale values
+        key = (pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes, self.threshold, self.cfg.min_number_of_views,
+               self.agg_impl, self.gemm_impl, self._weights_gen)
         cache = self.__dict__.setdefault('_graphs', collections.OrderedDict())
         ent = cache.get(key)
         cur = torch.cuda.current_stream(self.device)
@@ -680,10 +732,10 @@ class PosePipeline:
             d_in = {n: torch.empty_like(getattr(hb, n), device=self.device) for n in names}
             db = DeviceBatch(pb.n_frames, pb.n_heads, pb.n_nodes, pb.max_heads, pb.max_enodes, d_in['sk_xy'], d_in['sk_vp'],
                              d_in['sk_mask'], d_in['sk_cam'], d_in['head_off'], d_in['node_off'])
-            # heads // 2 bounds the person count (a person needs two views) and sizes the person list; the encoder and the MLP
+            # heads // min_number_of_views bounds the person count and sizes the person list; the encoder and the MLP
             # are captured for a tighter capacity - the count this shape showed, with head-room, in multiples of 8 rows (the
             # weight-stream kernel's step) - and a replay that finds more persons than that is redone eagerly and re-captured
-            p_bound = max(pb.n_heads // 2, 1)
+            p_bound = person_capacity(pb.n_heads, self.cfg.min_number_of_views)
             p_max = min(p_bound, max(8, (int(seen * 1.25) + 7) // 8 * 8))
             n_out = self.mlp[-1]['n']
             mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
@@ -722,9 +774,11 @@ class PosePipeline:
             self.__dict__.setdefault('_graph_person_hint', {})[key] = P
             del cache[key]
             return self.infer_host(hb)
-        return dict(n_persons=h_out['n_persons'], person_off=h_out['person_off'], person_sk=h_out['person_sk'][:P],
-                    n_persons_total=P, joints=h_out['joints'][:P], valid=h_out['valid'][:P])
+        # copies: the pinned buffers belong to the cached graph and the next replay of this shape overwrites them
+        return dict(n_persons=h_out['n_persons'].clone(), person_off=h_out['person_off'].clone(), person_sk=h_out['person_sk'][:P].clone(),
+                    n_persons_total=P, joints=h_out['joints'][:P].clone(), valid=h_out['valid'][:P].clone())
 
+    @_on_own_device
     def infer_frames(self, frames):
         """Live frames as the reference hands them around - a list of `{camera: [json_string, timestamp, ...]}` dicts (or one
         such dict) - to person proposals and joints on the host: native packing of the payload strings, one CUDA-graph
@@ -764,7 +818,7 @@ class PosePipeline:
             cur.wait_event(ev)
             res = self.infer(db)
             P = res['n_persons_total']
-            bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0)
+            bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0, self.cfg.min_number_of_views)
             bufs['n_persons'].copy_(res['n_persons'], non_blocking=True)
             bufs['person_off'].copy_(res['person_off'], non_blocking=True)
             if P > 0:

@@ -290,15 +290,10 @@ class MergedMultipleHumansDataset:
     def __len__(self):
         return len(self.graphs)
 
-    def get_dataset_name(self):
-        graphs_path = self.name + '_' + self.mode + '_alt_' + self.alt + '_s_' + str(self.limit) + '.bin'
-        info_path = self.name + '_info_' + self.mode + '_alt_' + self.alt + '_s_' + str(self.limit) + '.pkl'
-        return graphs_path, info_path
-
-    def has_cache(self):
+    def has_cache(self):                                        # no DGL cache files: every construction processes its inputs
         return False
 
-    def save(self):                                             # the reference skips the cache in test mode (:885)
+    def save(self):                                             # (the reference itself skips the cache in test mode, :885)
         return
 
     def download(self):

@@ -135,3 +135,63 @@ def test_pack_frames_fast_is_identical(config):
     inline = [{cam: [json.loads(p[0])] + list(p[1:]) for cam, p in f.items()} for f in frames[:3]]
     d, e = pack.pack_frames_fast(inline, cfg), pack.pack_frames(inline, cfg)
     assert all(np.array_equal(getattr(d, k), getattr(e, k)) for k in keys)
+
+
+def test_literals_locale_and_unterminated_spans():
+    """true / false in the valid / prob slots are 1.0 / 0.0 like the Python packer's numpy stores; null is an error (the
+    reference raises a TypeError on it); NaN / Infinity pass through; numbers parse the same under a decimal-comma
+    LC_NUMERIC; and the parser never reads past json + len (the C ABI takes a span, not a C string)."""
+    import ctypes as C
+    import locale
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    text = '[{"trackera": ["[{\\"3\\": [3, 100.5, 200.25, true, false], \\"4\\": [4, 1e400, -1e400, 1, 1]}]", 0.0]}]'
+    got = pack.pack_json(text, cfg)
+    want = pack.pack_frames(json.loads(text), cfg)
+    same(got, want)
+    assert got.sk_vp[0, 3].tolist() == [1.0, 0.0] and np.isinf(got.sk_xy[0, 4]).all()
+    nan_text = '[{"trackera": [[{"3": [3, NaN, -Infinity, 1, 1]}], 0.0]}]'
+    g2 = pack.pack_json(nan_text, cfg)
+    assert np.isnan(g2.sk_xy[0, 3, 0]) and g2.sk_xy[0, 3, 1] == -np.inf
+    with pytest.raises(libmod.B200PoseError):
+        pack.pack_json('[{"trackera": [[{"3": [3, null, 1.0, 1, 1]}], 0.0]}]', cfg)
+    # 17-significant-digit numbers take the strtod fallback: same bits under a decimal-comma locale
+    hard = '[{"trackera": [[{"3": [3, 123.45678901234567891, 0.30000000000000004441, 1, 1]}], 0.0]}]'
+    base = pack.pack_json(hard, cfg).sk_xy.copy()
+    old = locale.setlocale(locale.LC_NUMERIC)
+    try:
+        for name in ('de_DE.UTF-8', 'fr_FR.UTF-8', 'de_DE', 'C.UTF-8'):
+            try:
+                locale.setlocale(locale.LC_NUMERIC, name)
+                break
+            except locale.Error:
+                continue
+        assert np.array_equal(pack.pack_json(hard, cfg).sk_xy, base)
+    finally:
+        locale.setlocale(locale.LC_NUMERIC, old)
+    assert base[0, 3, 0] == 123.45678901234567891 and base[0, 3, 1] == 0.30000000000000004441
+    # the span ends in the middle of a number, with more digits (and no NUL) behind it in memory: a clean parse error
+    L = libmod.lib()
+    blob = b'[{"trackera": [[{"3": [3, 1.5, 2.5, 1, 0.123456789012345678' + b'9' * 64
+    buf = C.create_string_buffer(blob, len(blob))
+    names = (C.c_char_p * 1)(b'trackera'); idx = (C.c_int32 * 1)(0)
+    h = C.c_void_p()
+    rc = L.b200pose_pack_json(buf, len(blob) - 64, 1, names, idx, 1, C.byref(h))
+    assert rc != 0 and h.value is None
+
+
+def test_packed_batch_plan_is_validated():
+    """A batch whose declared max_heads / max_enodes do not cover its frames is rejected on the host (a kernel would skip
+    the frames that exceed the plan)."""
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    pm = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+    frames = [meta['frames']['p4a'], meta['frames']['p3']]
+    pb = pack.pack_frames(frames, cfg)
+    pb.validate()
+    pb.max_heads -= 1
+    with pytest.raises(ValueError):
+        pm.HostBatch(pb, pinned=False)
+    pb.max_heads += 1
+    pb.max_enodes = 3
+    with pytest.raises(ValueError):
+        pb.validate()
+    assert pm.person_capacity(20, 2) == 10 and pm.person_capacity(20, 1) == 20 and pm.person_capacity(20, 0) == 20 and pm.person_capacity(0, 2) == 1
