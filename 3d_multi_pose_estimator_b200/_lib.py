@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libb200pose.so')
 EXPORTS = ['b200pose_last_error', 'b200pose_version', 'b200pose_device_cc', 'b200pose_build_graph',
            'b200pose_node_features', 'b200pose_linear', 'b200pose_split_planes', 'b200pose_gat_aggregate',
            'b200pose_cluster', 'b200pose_cluster_pairs', 'b200pose_build_graph_pairs', 'b200pose_encode_persons', 'b200pose_triangulate', 'b200pose_gather_persons',
-           'b200pose_set_debug', 'b200pose_pack_json', 'b200pose_packed_sizes', 'b200pose_packed_copy', 'b200pose_packed_free']
+           'b200pose_set_debug', 'b200pose_pack_record', 'b200pose_pack_json', 'b200pose_packed_sizes', 'b200pose_packed_copy', 'b200pose_packed_free']
 
 
 class Cameras(C.Structure):
@@ -52,6 +52,7 @@ def lib():
         L.b200pose_encode_persons.argtypes = [i32, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp, vp]
         L.b200pose_triangulate.argtypes = [i32, vp, vp, vp, camp, i32, vp, vp, vp]
         L.b200pose_gather_persons.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, camp, vp, vp, vp]
+        L.b200pose_pack_record.argtypes = [i32, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
         L.b200pose_pack_json.argtypes = [C.c_char_p, C.c_int64, i32, C.POINTER(C.c_char_p), C.POINTER(i32), i32, C.POINTER(vp)]
         L.b200pose_packed_sizes.argtypes = [vp] + [C.POINTER(i32)] * 5
         L.b200pose_packed_copy.argtypes = [vp] * 8 + [i32]

@@ -458,6 +458,31 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int* __restr
     if (tid == 1023) out[n] = part[1023];
 }
 
+// One rank's results as the fixed-size record of the final gather (sharding.py): word 0 = persons, then n_persons of
+// every frame, the person list with batch-global skeleton ids, the joints as raw fp32 bits. The person count is read
+// on the device (person_off[n_frames]), so nothing here waits for the host; padding words are never read back.
+__global__ void __launch_bounds__(256) pack_record_kernel(
+    int n_frames, int n_cameras, int n_out, const int* __restrict__ n_persons, const int* __restrict__ person_off,
+    const int* __restrict__ person_sk, const float* __restrict__ joints, int ld_joints, int frames_cap, int persons_cap,
+    int head_base, int* __restrict__ rec)
+{
+    const int P = min(person_off[n_frames], persons_cap);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (tid == 0) rec[0] = person_off[n_frames];
+    for (int i = tid; i < n_frames; i += nthr) rec[1 + i] = n_persons[i];
+    int* sk = rec + 1 + frames_cap;
+    for (int i = tid; i < P * n_cameras; i += nthr) {
+        const int v = person_sk[i];
+        sk[i] = v >= 0 ? v + head_base : v;
+    }
+    float* jo = reinterpret_cast<float*>(sk + (size_t)persons_cap * n_cameras);
+    if (joints)
+        for (int i = tid; i < P * n_out; i += nthr) {
+            const int r = i / n_out, c = i - r * n_out;
+            jo[i] = joints[(size_t)r * ld_joints + c];
+        }
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -551,5 +576,23 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gather_persons(in
                                                                        cams->sm_slot, v_sm, cams->n_cameras, person_sk, person_frame);
         B2_CHECK_LAUNCH();
     }
+    return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_pack_record(int32_t n_frames, int32_t n_cameras, int32_t n_out,
+                                    const int32_t* n_persons, const int32_t* person_off, const int32_t* person_sk,
+                                    const float* joints, int32_t ld_joints, int32_t frames_cap, int32_t persons_cap,
+                                    int32_t head_base, int32_t* record, void* stream)
+{
+    B2_CHECK_ARG(n_persons && person_off && person_sk && record, "pack_record: null pointer");
+    B2_CHECK_ARG(n_frames >= 0 && n_frames <= frames_cap && persons_cap >= 0 && n_cameras >= 1 && n_out >= 0, "pack_record: bad sizes");
+    B2_CHECK_ARG(joints == nullptr || ld_joints >= n_out, "pack_record: ld_joints < n_out");
+    const long long work = (long long)persons_cap * (n_out > n_cameras ? n_out : n_cameras);
+    int blocks = (int)((work + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 592) blocks = 592;                 // 4 CTAs per SM: a copy of a few hundred KB
+    pack_record_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_frames, n_cameras, n_out, n_persons, person_off, person_sk, joints,
+                                                                   ld_joints, frames_cap, persons_cap, head_base, record);
+    B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

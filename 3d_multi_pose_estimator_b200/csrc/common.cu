@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...) {
 }  // namespace b200pose
 
 extern "C" __attribute__((visibility("default"))) const char* b200pose_last_error(void) { return b200pose::g_err; }
-extern "C" __attribute__((visibility("default"))) int b200pose_version(void) { return 100; }
+extern "C" __attribute__((visibility("default"))) int b200pose_version(void) { return 200; }
 extern "C" __attribute__((visibility("default"))) int b200pose_device_cc(void) {
     int dev = 0, major = 0, minor = 0;
     B2_CHECK_CUDA(cudaGetDevice(&dev));

@@ -2,7 +2,9 @@
 
 Frames are independent (the reference keeps no cross-frame state, test/metrics_from_model.py:120-300), so a batch
 is cut into contiguous blocks of frames, one block per rank, with weights and camera tables replicated. There is no
-collective on the hot path; the only exchange is ONE all-gather of fixed-size result records at the end of a step.
+collective on the hot path; the only exchange is the gather of fixed-size result records, issued asynchronously behind
+each step (ResultGather: one packing kernel + one NCCL all-gather on NCCL's own stream) and waited for once, at the end
+of the job.
 The record layout is plain int32 words so it travels through NCCL (device tensors) and gloo (CPU tensors, tests)
 alike: [n_persons_total | n_persons[F] | person_sk[Pcap, C] | joints[Pcap, J] as raw fp32 bits].
 """
@@ -47,6 +49,60 @@ def pack_record(n_persons: torch.Tensor, person_sk: torch.Tensor, joints: torch.
     if P and n_out:
         rec[o:o + P * n_out].view(torch.float32).view(P, n_out).copy_(joints)
     return rec
+
+
+def pack_record_device(res: dict, n_frames: int, frames_cap: int, persons_cap: int, n_cameras: int, n_out: int,
+                       out: torch.Tensor, head_base: int = 0, stream=None) -> torch.Tensor:
+    """pack_record for results resident on the GPU, as ONE kernel launch (b200pose_pack_record): no eager tensor ops, no
+    host-side person count - it reads person_off[n_frames] on the device - so it can be enqueued right behind the step that
+    produced `res` (PosePipeline.infer). `out`: int32 [record_words] device buffer."""
+    from . import _lib
+    joints = res.get('joints')
+    ld = int(joints.stride(0)) if joints is not None and joints.numel() else n_out
+    _lib.check(_lib.lib().b200pose_pack_record(n_frames, n_cameras, n_out, _lib.ptr(res['n_persons']), _lib.ptr(res['person_off']),
+                                               _lib.ptr(res['person_sk']),
+                                               _lib.ptr(joints) if joints is not None and joints.numel() else None, ld,
+                                               frames_cap, persons_cap, head_base, _lib.ptr(out), stream), 'pack_record')
+    return out
+
+
+class ResultGather:
+    """The job's one exchange, taken off the critical path: every step's record is packed by one kernel behind the step and
+    all-gathered asynchronously (NCCL's own stream waits for the packing kernel; the compute stream never waits for the
+    collective), `depth` steps in flight. finish() waits for what is outstanding - the "final gather" of SURVEY.md 8e."""
+
+    def __init__(self, world: int, frames_cap: int, persons_cap: int, n_cameras: int, n_out: int, device, depth: int = 4, group=None):
+        self.world, self.group, self.depth = world, group, depth
+        self.dims = (frames_cap, persons_cap, n_cameras, n_out)
+        words = record_words(*self.dims)
+        self.rec = [torch.empty(words, dtype=torch.int32, device=device) for _ in range(depth)]
+        self.out = [torch.empty(world * words, dtype=torch.int32, device=device) for _ in range(depth)]
+        self.work = [None] * depth
+        self.n = 0
+
+    def submit(self, res: dict, n_frames: int, head_base: int = 0, stream=None):
+        import torch.distributed as dist
+        k = self.n % self.depth
+        if self.work[k] is not None:
+            self.work[k].wait()                      # stream-level: the slot's previous gather must have read its record
+            self.work[k] = None
+        frames_cap, persons_cap, n_cameras, n_out = self.dims
+        pack_record_device(res, n_frames, frames_cap, persons_cap, n_cameras, n_out, self.rec[k], head_base, stream)
+        if self.world > 1:
+            self.work[k] = dist.all_gather_into_tensor(self.out[k], self.rec[k], group=self.group, async_op=True)
+        self.n += 1
+        return k
+
+    def finish(self):
+        """Waits for the outstanding gathers; returns the gathered records [world, words] of the last `depth` steps, oldest first."""
+        for w in self.work:
+            if w is not None:
+                w.wait()
+        self.work = [None] * self.depth
+        ks = [(i % self.depth) for i in range(max(0, self.n - self.depth), self.n)]
+        if self.world == 1:
+            return [self.rec[k].reshape(1, -1) for k in ks]
+        return [self.out[k].reshape(self.world, -1) for k in ks]
 
 
 def all_gather_records(rec: torch.Tensor, world: int, group=None) -> torch.Tensor:

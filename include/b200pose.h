@@ -228,6 +228,15 @@ int b200pose_gather_persons(int32_t n_frames, const int32_t* head_off, const int
                             const int32_t* sk_cam, int32_t v_sm, const b200pose_cameras* cams_host,
                             int32_t* person_sk, int32_t* person_frame, void* stream);
 
+/* Multi-GPU: one rank's results as the fixed-size int32 record of the final gather (frames are sharded,
+ * the only exchange is a gather of padded per-rank records; the reference has no counterpart - it is single-process).
+ *   record = [ P | n_persons[frames_cap] | person_sk[persons_cap, C] (+head_base where >= 0) | joints[persons_cap, n_out] fp32 bits ]
+ * P is read from person_off[n_frames] on the device, so the call needs no host-side person count. */
+int b200pose_pack_record(int32_t n_frames, int32_t n_cameras, int32_t n_out,
+                         const int32_t* n_persons, const int32_t* person_off, const int32_t* person_sk,
+                         const float* joints, int32_t ld_joints, int32_t frames_cap, int32_t persons_cap,
+                         int32_t head_base, int32_t* record, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-side frame packer (no GPU work): the reference's frame JSON - a list of frames
  * {camera: [json.dumps([skeleton, ...]), timestamp, ...]} as read by test/metrics_from_model.py:117-191, or one such

@@ -697,3 +697,36 @@ def test_infer_frames_from_reference_dicts():
         assert torch.equal(got['person_sk'], want['person_sk']) and torch.equal(got['person_off'], want['person_off'])
         if want['n_persons_total']:
             assert (got['joints'] - want['joints']).abs().max().item() <= 1e-5
+
+
+def test_result_record_kernel_matches_host_packing():
+    """The multi-GPU result record written by one kernel behind the step (b200pose_pack_record, person count read on the
+    device) holds what the eager packing (sharding.pack_record: the layout the gloo tests exchange) writes, and unpacks to
+    the step's results; ResultGather keeps `depth` records in flight."""
+    sharding = importlib.import_module('3d_multi_pose_estimator_b200.sharding')
+    pipe = get_pipe('panoptic')
+    cfg = pipe.cfg
+    tags, pb, db = golden_batch('panoptic')
+    res = pipe.infer(db)
+    P = res['n_persons_total']
+    assert P > 0
+    F, Fcap, Pcap = pb.n_frames, pb.n_frames + 3, pipeline_mod.person_capacity(pb.n_heads, cfg.min_number_of_views)
+    want = sharding.pack_record(res['n_persons'], res['person_sk'], res['joints'], Fcap, Pcap, cfg.n_cameras, 54, head_base=1000)
+    words = sharding.record_words(Fcap, Pcap, cfg.n_cameras, 54)
+    got = torch.full((words,), -7, dtype=torch.int32, device='cuda')
+    sharding.pack_record_device(res, F, Fcap, Pcap, cfg.n_cameras, 54, got, head_base=1000, stream=pipe._stream())
+    torch.cuda.synchronize()
+    a = sharding.unpack_records(got.reshape(1, -1), [F], Fcap, Pcap, cfg.n_cameras, 54)
+    b = sharding.unpack_records(want.reshape(1, -1), [F], Fcap, Pcap, cfg.n_cameras, 54)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a['joints'], res['joints'].cpu().numpy()) and a['n_persons'].tolist() == res['n_persons'].cpu().tolist()
+    g = sharding.ResultGather(1, Fcap, Pcap, cfg.n_cameras, 54, 'cuda', depth=2)
+    for i in range(5):
+        g.submit(res, F, head_base=i, stream=pipe._stream())
+    outs = g.finish()
+    torch.cuda.synchronize()
+    assert len(outs) == 2
+    last = sharding.unpack_records(outs[-1], [F], Fcap, Pcap, cfg.n_cameras, 54)
+    sk = res['person_sk'].cpu().numpy()
+    assert np.array_equal(last['person_sk'], np.where(sk >= 0, sk + 4, sk))
