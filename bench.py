@@ -25,8 +25,17 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 GOLDEN = os.path.join(REPO, 'tests', 'golden')
 
-METRIC = 'frames/sec (5-view, 4 persons/frame, 1024-frame batch)'
 UNIT = 'frames/s'
+RIG_NAMES = {'panoptic': 'Panoptic', 'arp3': 'ARP-lab (tm_arp.pickle, first three cameras)', 'arp6': 'ARP-lab (tm_arp.pickle, as shipped)',
+             'ring10': 'stress graph: synthetic ring', 'arp_robot2': 'ARP-lab robot cameras', 'pansub': 'Panoptic camera subset'}
+
+
+def describe(config, cfg, frames, persons):
+    """Metric name and workload description of THIS run (whatever --config / --frames / --persons say)."""
+    metric = 'frames/sec (%d-view, %d persons/frame, %d-frame batch)' % (cfg.V_sm, persons, frames)
+    workload = '%s %d-view, %d-frame batch, %d persons/frame, skeleton matching + MLP lift' % (
+        RIG_NAMES.get(config, config), cfg.V_sm, frames, persons)
+    return metric, workload
 
 
 def load_workload(config, n_frames, n_persons, seed0):
@@ -47,7 +56,7 @@ def load_weights(config, cfg):
     gat = W.make_gat_state(cfg.n_features_sm, meta['gat_seed'])
     gat['layers.4.fc2.weight'] = torch.from_numpy(npz['gat_last_fc2_weight'].copy())
     gat['layers.4.fc2.bias'] = torch.from_numpy(npz['gat_last_fc2_bias'].copy())
-    mlp = W.make_mlp_state(cfg.n_cameras * 18 * 14, 54, meta['mlp_seed'])
+    mlp = W.make_mlp_state(meta.get('mlp_in_dim', cfg.mlp_in), 54, meta['mlp_seed'])
     return gat, mlp
 
 
@@ -121,9 +130,48 @@ def _cpu_worker(args):
             return 0, time.perf_counter() - t0
 
 
-def cpu_reference_run(config, persons, gat_state, mlp_state, budget_s, n_frames=64, seed0=0, procs=None):
-    """The CPU arm: the oracle port of the reference path (oracle/pose_oracle.py) on `procs` host processes
-    (default: every core), each handling its own frames one at a time for ~budget_s seconds.
+def _cpu_worker_reference(args):
+    """One host process of the CPU arm running the UNMODIFIED reference (baseline/_ref or /root/reference, with the dgl /
+    pytransform3d shims) through its own driver's call sequence (oracle/ref_runner.py), one torch thread per process."""
+    config, lo, hi, persons, seed0, weights_path, budget_s = args
+    import contextlib
+    import io
+    from oracle import ref_runner
+    pkg = importlib.import_module('3d_multi_pose_estimator_b200')
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    cfg = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % config))
+    W = np.load(weights_path)
+    gw = {k[4:]: W[k] for k in W.files if k.startswith('gat/')}
+    mw = {k[4:]: W[k] for k in W.files if k.startswith('mlp/')}
+    frames = [synth.make_frame(cfg, seed0 + i, persons) for i in range(lo, hi)]
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):                 # the reference's modules print while they work
+        runner = ref_runner.ReferenceRunner(config, gw, mw, threads=1)
+        runner.run_frame(frames[0])                        # import-time tables, first-call allocations
+        n, t0 = 0, time.perf_counter()
+        while True:
+            for f in frames:
+                runner.run_frame(f)
+                n += 1
+                if time.perf_counter() - t0 > budget_s:
+                    return n, time.perf_counter() - t0
+
+
+def reference_kind():
+    """'reference' when the unmodified reference can be run here (reference tree or its staged copy), else 'port'."""
+    try:
+        from oracle import ref_runner
+        import cv2  # noqa: F401  (the reference needs it; same image on the GPU box)
+        import networkx  # noqa: F401
+        return 'reference' if ref_runner.available() else 'port'
+    except Exception:
+        return 'port'
+
+
+def cpu_reference_run(config, persons, gat_state, mlp_state, budget_s, n_frames=64, seed0=0, procs=None, kind='port', repeats=1):
+    """The CPU arm on `procs` host processes (default: every core), each handling its own frames one at a time for
+    ~budget_s seconds: kind 'reference' = the unmodified reference under the import shims (oracle/ref_runner.py),
+    kind 'port' = the oracle restatement (oracle/pose_oracle.py).
     Returns (frames/s, frames processed, seconds, processes)."""
     import multiprocessing as mp
     import tempfile
@@ -137,8 +185,8 @@ def cpu_reference_run(config, persons, gat_state, mlp_state, budget_s, n_frames=
     try:
         for k in saved:                           # inherited by the workers before they load their BLAS
             os.environ[k] = '1'
-        with mp.get_context('spawn').Pool(procs) as pool:
-            res = pool.map(_cpu_worker, jobs)
+        with mp.get_context('spawn').Pool(procs) as pool:                 # one pool for all repeats: workers import torch once
+            runs = [pool.map(_cpu_worker_reference if kind == 'reference' else _cpu_worker, jobs) for _ in range(repeats)]
     finally:
         for k, v in saved.items():
             if v is None:
@@ -146,9 +194,12 @@ def cpu_reference_run(config, persons, gat_state, mlp_state, budget_s, n_frames=
             else:
                 os.environ[k] = v
         os.unlink(tmp.name)
-    n = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)                 # workers run concurrently for ~budget_s; pool start-up is excluded
-    return n / busy, n, busy, procs
+    out = []
+    for res in runs:
+        n = sum(r[0] for r in res)
+        busy = max(r[1] for r in res)             # workers run concurrently for ~budget_s; pool start-up is excluded
+        out.append((n / busy, n, busy, procs))
+    return out[0] if repeats == 1 else out
 
 
 def algorithmic_work(pb, pipe_gat_dims, mlp_dims, n_persons):
@@ -173,51 +224,65 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--frames', type=int, default=1024)
+    ap.add_argument('--frames', type=int, default=1024, help='frames per GPU and step')
     ap.add_argument('--persons', type=int, default=4)
     ap.add_argument('--config', default='panoptic')
+    ap.add_argument('--total-frames', type=int, default=0,
+                    help='size of the whole job (e.g. 1000000 for BASELINE.json configs[2]): sets --steps to ceil(total / (gpus * frames)); '
+                         'every rank streams its share in chunks of --frames frames')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
     ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
     ap.add_argument('--latency-frames', type=int, default=200, help='single-frame calls timed for p50_frame_latency_ms')
+    ap.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'],
+                    help='CPU arm: the unmodified reference under the import shims (needs baseline/_ref or /root/reference) or the oracle port')
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    config_desc = {'workload': 'Panoptic 5-view, %d-frame batch, %d persons/frame, skeleton matching + MLP lift'
-                   % (args.frames, args.persons), 'camera_config': args.config, 'frames_per_gpu': args.frames,
-                   'persons_per_frame': args.persons, 'weights': 'random-init (seeded) + last-layer bias calibration',
-                   'l2': 'L2 flushed (256 MiB write) between timed iterations'}
+    if args.total_frames > 0:
+        args.steps = max(1, -(-args.total_frames // (max(world, 1) * args.frames)))
 
     if args.workload == 'triangulation':
         return triangulation_workload(args, rank, world, local_rank)
     if args.workload == 'train_batch':
         return train_batch_workload(args, rank, world, local_rank)
-    # ------------------------------------------------------------------ reference arm (CPU port)
+    pkg = importlib.import_module('3d_multi_pose_estimator_b200')
+    cfg0 = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
+    METRIC, workload = describe(args.config, cfg0, args.frames, args.persons)
+    config_desc = {'workload': workload, 'camera_config': args.config, 'views': cfg0.V_sm, 'frames_per_gpu': args.frames,
+                   'persons_per_frame': args.persons, 'weights': 'random-init (seeded) + last-layer bias calibration',
+                   'l2': 'L2 flushed (256 MiB write) between timed iterations'}
+    if args.total_frames > 0:
+        config_desc['job'] = '%d frames in total: %d steps of %d frames on each of %d GPUs (512 distinct frames per GPU, cycled)' % (
+            args.steps * world * args.frames, args.steps, args.frames, world)
+    kind = reference_kind() if args.cpu_kind == 'auto' else args.cpu_kind
+    kind_note = {'reference': 'the unmodified reference (baseline/_ref) under the dgl / pytransform3d import shims, its own driver call sequence '
+                              '(test/metrics_from_model.py:178-300), one single-threaded process per host core',
+                 'port': 'the numpy restatement of the reference path (oracle/pose_oracle.py), one single-threaded process per host core'}
+    # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == 'reference':
         if rank != 0:
             return
         import torch
-        pkg = importlib.import_module('3d_multi_pose_estimator_b200')
-        cfg = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
-        gat, mlp = load_weights(args.config, cfg)
-        n_steps = max(1, args.steps + args.warmup)
+        gat, mlp = load_weights(args.config, cfg0)
+        n_steps = max(1, min(args.steps, 8) + args.warmup)                 # bounded: a few minutes whatever --steps says
         budget = max(3.0, min(20.0, 90.0 / n_steps))
-        vals = []
-        for i in range(n_steps):
-            fps, n, dt, procs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=budget, n_frames=4 * (os.cpu_count() or 1))
-            if i >= args.warmup:
-                vals.append((fps, n, dt))
+        runs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=budget, n_frames=4 * (os.cpu_count() or 1), kind=kind,
+                                 repeats=n_steps + 1)[1:]           # [0] absorbs the workers' first-call costs
+        procs = runs[0][3]
+        vals = [(fps, n, dt) for i, (fps, n, dt, _) in enumerate(runs) if i >= args.warmup or len(runs) <= args.warmup]
         value = float(np.mean([v[0] for v in vals]))
         line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': 1e3 * args.frames / value, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32 (numpy), fp64 geometry', 'data': 'synthetic', 'config': config_desc,
-                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-                                 'sample': '%d frames per step over %d host processes (one frame at a time each, %.0f s per step); '
-                                           'ms_per_step extrapolated to the %d-frame batch' % (vals[-1][1], procs, budget, args.frames)},
+                'vs_baseline': None, 'dtype': 'f32 (torch CPU), fp64 geometry' if kind == 'reference' else 'f32 (numpy), fp64 geometry',
+                'data': 'synthetic', 'config': config_desc,
+                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': kind, 'what': kind_note[kind],
+                                 'sample': '%d frames per step over %d host processes (one frame at a time each, %.0f s per step, %d steps timed); '
+                                           'ms_per_step extrapolated to the %d-frame batch' % (vals[-1][1], procs, budget, len(vals), args.frames)},
                 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line))
         return
@@ -232,33 +297,29 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg, frames = load_workload(args.config, args.frames, args.persons, seed0=rank * args.frames)
+    distinct = args.frames if args.total_frames <= 0 else min(args.frames, 512)
+    cfg, frames = load_workload(args.config, distinct, args.persons, seed0=rank * args.frames)
     gat, mlp = load_weights(args.config, cfg)
     pb = pack.pack_frames(frames, cfg, keep_json=False)
+    if distinct < args.frames:                                   # a long job cycles over its distinct frames
+        pb = pb.tile(-(-args.frames // distinct)).slice(0, args.frames)
     hb = pm.HostBatch(pb)
     pipe = pm.PosePipeline(cfg, gat, mlp, device=dev, gemm_impl=args.gemm_impl)
     db = hb.to_device(dev)
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     sharding = importlib.import_module('3d_multi_pose_estimator_b200.sharding')
-    P_cap = pb.n_heads // 2 + 1
-
-    def gather_results(res):
-        """The one collective of a step: every rank's person counts, assignments and joints (fixed-size records)."""
-        if world == 1:
-            return
-        rec = sharding.pack_record(res['n_persons'], res['person_sk'], res['joints'], args.frames, P_cap, cfg.n_cameras, 54,
-                                   head_base=0)
-        sharding.all_gather_records(rec, world)
+    P_cap = pm.person_capacity(pb.n_heads, cfg.min_number_of_views)
+    n_out = pipe.mlp[-1]['n']
+    # the job's only exchange: every step's fixed-size record is packed by one kernel behind the step and all-gathered
+    # asynchronously; nothing on the compute stream waits for it until the end of the job ("final gather")
+    gather = sharding.ResultGather(world, args.frames, P_cap, cfg.n_cameras, n_out, dev, depth=4) if world > 1 else None
 
     def step_device():
         res = pipe.infer(db)
-        gather_results(res)
+        if gather is not None:
+            gather.submit(res, args.frames, head_base=rank * pb.n_heads, stream=pipe._stream())
         return res
-
-    def step_host():
-        out = pipe.infer_host(hb, n_chunks=args.chunks)
-        return out
 
     def barrier():
         if world > 1:
@@ -268,12 +329,16 @@ def main():
     # warm-up (also settles the caching allocator)
     for _ in range(warmup):
         res = step_device()
-        step_host()
+        pipe.infer_host(hb, n_chunks=args.chunks)
+    if gather is not None:
+        gather.finish()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- device-resident timing: one event pair per step, L2 flushed in between
+    # ---- device-resident timing: one event pair per step, L2 flushed in between; the wait for the outstanding gathers
+    # (the end of the job) is timed as well and counted into the job time
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     pipe.launches = 0
     barrier()
     for a, b in ev:
@@ -281,9 +346,19 @@ def main():
         a.record()
         res = step_device()
         b.record()
+    tail[0].record()
+    gathered = gather.finish() if gather is not None else None
+    tail[1].record()
     barrier()
-    launches = pipe.launches // max(1, args.steps)
-    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches = pipe.launches // max(1, args.steps) + (1 if gather is not None else 0)
+    tail_ms = float(tail[0].elapsed_time(tail[1]))
+    ms = (float(np.sum([a.elapsed_time(b) for a, b in ev])) + tail_ms) / args.steps
+    gather_ok = None
+    if gathered is not None and rank == 0:                       # the gathered records really hold every rank's results
+        last = sharding.unpack_records(gathered[-1], [args.frames] * world, args.frames, P_cap, cfg.n_cameras, n_out)
+        mine = res['n_persons'].cpu().numpy()
+        gather_ok = bool(np.array_equal(last['n_persons'][:args.frames], mine) and len(last['n_persons']) == world * args.frames
+                         and np.array_equal(last['joints'][:res['n_persons_total']], res['joints'].cpu().numpy()))
     # ---- end-to-end through the public host API: K batches streamed back to back; every step copies its inputs from
     # pinned host memory and reads its results back inside the timed region (the copy of step i+1 overlaps the compute of
     # step i: PosePipeline.infer_host_stream). Per-step activations (1.3 GB) are 10x the L2, so no flush is needed here.
@@ -377,41 +452,49 @@ def main():
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
         tc_peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        peak_src = 'measured' if peaks else 'fallback'
+        peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback of B200_PROFILING.md'
         P = res['n_persons_total']
         gat_dims = W.gat_layer_dims(cfg.n_features_sm)
         mlp_dims = [(l['k'], l['n']) for l in pipe.mlp]
         agg_bytes, gat_flops, mlp_flops = algorithmic_work(pb, gat_dims, mlp_dims, P)
+        traffic_all, traffic_tag = load_traffic(args)
         kernels = []
         for name, k_ms in kern.items():
             entry = {'kernel': name, 'ms_per_step': k_ms}
-            if name == 'gat_projection_gemm':
-                entry.update(bound='tensor', achieved=3 * gat_flops / k_ms / 1e9, peak=tc_peak, unit='TFLOP/s')
-            elif name == 'mlp_gemm':
-                entry.update(bound='tensor', achieved=3 * mlp_flops / k_ms / 1e9, peak=tc_peak, unit='TFLOP/s')
+            if name in ('gat_projection_gemm', 'mlp_gemm'):
+                fl = gat_flops if name == 'gat_projection_gemm' else mlp_flops
+                # executed = the three bf16 MMAs of the split (hi*hi + lo*hi + hi*lo); algorithmic = the fp32 GEMM they stand for
+                entry.update(bound='tensor', achieved=3 * fl / k_ms / 1e9, peak=tc_peak, unit='TFLOP/s',
+                             achieved_algorithmic=fl / k_ms / 1e9, frac_algorithmic=fl / k_ms / 1e9 / tc_peak)
             elif name == 'edge_softmax_aggregate':
                 entry.update(bound='hbm', achieved=agg_bytes / k_ms / 1e6, peak=hbm_peak, unit='GB/s')
             if 'achieved' in entry:
                 entry['frac'] = entry['achieved'] / entry['peak']
+            if traffic_all is not None and name in traffic_all:
+                entry['traffic'] = traffic_all[name]
+                entry['dram_gbs'] = traffic_all[name] / k_ms / 1e6
+                entry['dram_frac'] = entry['dram_gbs'] / hbm_peak
             kernels.append(entry)
         dominant = max([k for k in kernels if 'frac' in k], key=lambda k: k['ms_per_step'])
-        traffic = None
-        try:                                      # DRAM bytes of the class from the committed ncu capture (per step)
-            traffic = json.load(open(os.path.join(REPO, 'profiles', 'r01_traffic.json'))).get(dominant['kernel'])
-        except Exception:
-            pass
         roofline = {'kernel': dominant['kernel'], 'bound': dominant['bound'], 'achieved': dominant['achieved'],
-                    'peak': dominant['peak'], 'unit': dominant['unit'], 'frac': dominant['frac'], 'traffic': traffic,
-                    'traffic_note': 'dram bytes read+written per step by this kernel class, ncu --set full (profiles/r01_traffic.json)',
-                    'peak_source': peak_src + (' (bf16 sustained; achieved counts the 3 executed split-bf16 MMAs)'
-                                               if dominant['bound'] == 'tensor' else '')}
-        cpu_line = None
+                    'peak': dominant['peak'], 'unit': dominant['unit'], 'frac': dominant['frac'], 'traffic': dominant.get('traffic'),
+                    'traffic_note': traffic_tag,
+                    'peak_source': peak_src + (' (bf16 sustained; achieved counts the 3 executed split-bf16 MMAs, frac_algorithmic = %.3f)'
+                                               % dominant.get('frac_algorithmic', 0.0) if dominant['bound'] == 'tensor' else '')}
+        cpu_line = parity = None
         if world == 1:                            # the CPU arm is timed on rank 0 of single-GPU runs only
+            n_cpu = 4 * (os.cpu_count() or 1)
             cpu_fps, cpu_n, cpu_dt, cpu_procs = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=args.cpu_budget,
-                                                                   n_frames=4 * (os.cpu_count() or 1))
-            cpu_line = {'value': cpu_fps, 'unit': UNIT, 'cores': cpu_procs, 'kind': 'port',
+                                                                   n_frames=n_cpu, kind=kind)
+            cpu_line = {'value': cpu_fps, 'unit': UNIT, 'cores': cpu_procs, 'kind': kind, 'what': kind_note[kind],
                         'sample': '%d frames of the same workload over %d host processes, one frame at a time each, %.1f s'
                                   % (cpu_n, cpu_procs, cpu_dt)}
+            if kind == 'reference':               # the port next to it: what the checker itself costs
+                p_fps, p_n, p_dt, _ = cpu_reference_run(args.config, args.persons, gat, mlp, budget_s=min(args.cpu_budget, 8.0),
+                                                        n_frames=n_cpu, kind='port')
+                cpu_line['port_value'] = p_fps
+                cpu_line['port_sample'] = '%d frames, %.1f s' % (p_n, p_dt)
+            parity = parity_sample(cfg, frames, pb, res, gat, mlp)
         line = {'metric': METRIC, 'value': total_frames / ms_max * 1e3, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate; fp64 geometry', 'data': 'synthetic',
@@ -420,7 +503,10 @@ def main():
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_max, 'single_call_ms': single_ms,
                         'mode': 'streamed: copy of step i+1 overlaps compute of step i'},
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
-                'cpu_baseline': cpu_line,
+                'cpu_baseline': cpu_line, 'parity_sample': parity,
+                'final_gather': None if gather is None else {'mode': 'one packing kernel + one asynchronous all-gather per step, waited for once at '
+                                                                     'the end of the job', 'tail_ms': tail_ms, 'verified': gather_ok,
+                                                             'bytes_per_rank_and_step': 4 * sharding.record_words(args.frames, P_cap, cfg.n_cameras, n_out)},
                 'persons_found_per_frame': P / args.frames,
                 'dropin_driver_loop_frames_per_s': dropin_fps, 'json_pack_frames_per_s': json_fps,
                 'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
@@ -431,6 +517,42 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def load_traffic(args):
+    """DRAM bytes per step and kernel class from the committed ncu --set full capture (profiles/r02_traffic.json), used only
+    when it was taken on THIS workload; otherwise traffic is null (a number measured on another configuration or kernel
+    revision would be stale)."""
+    try:
+        t = json.load(open(os.path.join(REPO, 'profiles', 'r02_traffic.json')))
+    except Exception:
+        return None, 'no ncu capture committed for this workload'
+    w = t.get('workload', {})
+    if (w.get('config'), w.get('frames'), w.get('persons')) != (args.config, args.frames, args.persons):
+        return None, 'the committed ncu capture (%s) is of another workload: traffic not reported' % t.get('source', 'profiles/r02_traffic.json')
+    return t.get('classes', {}), 'dram__bytes_read.sum + dram__bytes_write.sum per step and kernel class, ncu --set full (%s, kernel set %s)' % (
+        t.get('source', 'profiles/r02_traffic.json'), t.get('kernel_set', '?'))
+
+
+def parity_sample(cfg, frames, pb, res, gat, mlp, sample=(0, 1, 2, 3)):
+    """Four frames of the batch the timed region just processed, checked against the oracle AFTER the timed region (scores
+    1e-4 relative, person assignment on the GPU's scores exact, joints 0.5 mm): the benchmark asserts something about its
+    own outputs. Part of the cpu_baseline leg (rank 0, N = 1) - the one place bench.py may execute oracle/."""
+    try:
+        from oracle import check as OC
+        scores = res['scores'].cpu().numpy()
+        ph, npers = res['person_heads'].cpu().numpy(), res['n_persons'].cpu().numpy()
+        poff, joints = res['person_off'].cpu().numpy(), res['joints'].cpu().numpy()
+        sample = [i for i in sample if i < pb.n_frames]
+        rep = OC.check_frames(cfg, [frames[i % len(frames)] for i in sample], {k: v.numpy() for k, v in gat.items()},
+                              {k: v.numpy() for k, v in mlp.items()},
+                              [scores[pb.node_off[i]:pb.node_off[i + 1]] for i in sample],
+                              [ph[pb.head_off[i]:pb.head_off[i] + npers[i]] for i in sample],
+                              [joints[poff[i]:poff[i + 1]] for i in sample])
+        return {'status': 'ok', 'frames': rep['frames'], 'persons': rep['persons'], 'worst_score_rel': rep['worst_score_rel'],
+                'worst_joint_mm': rep['worst_joint_mm']}
+    except AssertionError as e:
+        return {'status': 'FAILED', 'why': str(e)}
 
 
 def triangulation_workload(args, rank, world, local_rank):
@@ -655,7 +777,7 @@ def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
                                   torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
         model.load_state_dict(gat_state)
         model = model.to(dev)
-        mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)
+        mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.mlp_in, output_dimensions=54)
         mlp.load_state_dict(mlp_state)
         mlp = mlp.to(dev)
         for f in frames[:8]:

@@ -52,3 +52,55 @@ def activate(configuration='PANOPTIC', parameters_override=None):
         mod.parameters = parameters_override(mod.parameters)
     sys.modules['parameters'] = mod
     return mod.parameters
+
+
+CONFIGS = ('panoptic', 'arp3', 'ring10', 'arp6', 'arp_robot2', 'pansub')
+
+
+def activate_config(config):
+    """The named configurations of the goldens and of bench.py, as `parameters` of the unmodified reference:
+    panoptic = PANOPTIC as shipped; arp6 = ARPLAB as shipped; arp3 = ARPLAB cut to its first three cameras (BASELINE.json
+    configs[2]); arp_robot2 = ARPLAB with the robot-cameras-only lines of parameters.py:110-112; pansub = PANOPTIC with a
+    permuted 4-of-5 skeleton-matching set and a 3-camera pose-estimator set; ring10 = a synthetic 10-camera ring
+    (BASELINE.json configs[4]) whose TransformManager pickle is written to a temporary file."""
+    tm_arp = os.path.join(REFERENCE_ROOT, 'tm_arp.pickle')
+    tm_pan = os.path.join(REFERENCE_ROOT, 'tm_panoptic.pickle')
+    if config == 'panoptic':
+        return activate('PANOPTIC', lambda p: p._replace(transformations_path=tm_pan))
+    if config == 'arp6':
+        return activate('ARPLAB', lambda p: p._replace(transformations_path=tm_arp))
+    if config == 'arp3':
+        return activate('ARPLAB', lambda p: p._replace(
+            cameras=[0, 1, 2], camera_names=p.camera_names[:3], used_cameras=p.camera_names[:3],
+            used_cameras_skeleton_matching=p.camera_names[:3], transformations_path=tm_arp))
+    if config == 'arp_robot2':
+        return activate('ARPLAB', lambda p: p._replace(
+            used_cameras=['orinbot_l', 'orinbot_r'], used_cameras_skeleton_matching=['orinbot_l', 'orinbot_r'],
+            transformations_path=tm_arp))
+    if config == 'pansub':
+        return activate('PANOPTIC', lambda p: p._replace(
+            used_cameras_skeleton_matching=['trackerd', 'trackerb', 'trackere', 'trackerc'],
+            used_cameras=['trackerb', 'trackere', 'trackerd'], transformations_path=tm_pan))
+    if config == 'ring10':
+        import importlib
+        import pickle
+        import tempfile
+        repo = os.path.dirname(_HERE)
+        if repo not in sys.path:
+            sys.path.insert(0, repo)
+        sys.path.insert(0, os.path.join(_HERE, 'shims'))
+        from pytransform3d.transform_manager import TransformManager
+        cfg = importlib.import_module('3d_multi_pose_estimator_b200').ring_config(10)
+        tm = TransformManager.__new__(TransformManager)
+        tm.transforms = {('root', n): cfg.T_root2cam[i] for i, n in enumerate(cfg.camera_names)}
+        f = tempfile.NamedTemporaryFile(prefix='tm_ring10_', suffix='.pickle', delete=False)
+        pickle.dump(tm, f)
+        f.close()
+        V = 10
+        return activate('PANOPTIC', lambda p: p._replace(
+            cameras=list(range(V)), camera_names=cfg.camera_names, used_cameras=cfg.camera_names,
+            used_cameras_skeleton_matching=cfg.camera_names,
+            fx=[float(x) for x in cfg.fx], fy=[float(x) for x in cfg.fy], cx=[float(x) for x in cfg.cx],
+            cy=[float(x) for x in cfg.cy],
+            kd0=[0.] * V, kd1=[0.] * V, kd2=[0.] * V, p1=[0.] * V, p2=[0.] * V, transformations_path=f.name))
+    raise ValueError(config)

@@ -66,44 +66,7 @@ def _cases(config):
 
 def _activate(config):
     from oracle import ref_env
-    b200 = __import__('importlib').import_module('3d_multi_pose_estimator_b200')
-    if config == 'panoptic':
-        return ref_env.activate('PANOPTIC')
-    if config == 'arp3':
-        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_arp.pickle')
-        return ref_env.activate('ARPLAB', lambda p: p._replace(
-            cameras=[0, 1, 2], camera_names=p.camera_names[:3], used_cameras=p.camera_names[:3],
-            used_cameras_skeleton_matching=p.camera_names[:3], transformations_path=tm_path))
-    if config == 'arp6':
-        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_arp.pickle')
-        return ref_env.activate('ARPLAB', lambda p: p._replace(transformations_path=tm_path))
-    if config == 'arp_robot2':
-        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_arp.pickle')
-        return ref_env.activate('ARPLAB', lambda p: p._replace(
-            used_cameras=['orinbot_l', 'orinbot_r'], used_cameras_skeleton_matching=['orinbot_l', 'orinbot_r'],
-            transformations_path=tm_path))
-    if config == 'pansub':
-        tm_path = os.path.join(ref_env.REFERENCE_ROOT, 'tm_panoptic.pickle')
-        return ref_env.activate('PANOPTIC', lambda p: p._replace(
-            used_cameras_skeleton_matching=['trackerd', 'trackerb', 'trackere', 'trackerc'],
-            used_cameras=['trackerb', 'trackere', 'trackerd'], transformations_path=tm_path))
-    if config == 'ring10':
-        # synthetic 10-camera rig: pickle a shim TransformManager for the reference to load
-        sys.path.insert(0, os.path.join(REPO, 'oracle', 'shims'))
-        from pytransform3d.transform_manager import TransformManager
-        cfg = b200.ring_config(10)
-        tm = TransformManager.__new__(TransformManager)
-        tm.transforms = {('root', n): cfg.T_root2cam[i] for i, n in enumerate(cfg.camera_names)}
-        tm_path = '/tmp/tm_ring10.pickle'
-        pickle.dump(tm, open(tm_path, 'wb'))
-        V = 10
-        return ref_env.activate('PANOPTIC', lambda p: p._replace(
-            cameras=list(range(V)), camera_names=cfg.camera_names, used_cameras=cfg.camera_names,
-            used_cameras_skeleton_matching=cfg.camera_names,
-            fx=[float(x) for x in cfg.fx], fy=[float(x) for x in cfg.fy], cx=[float(x) for x in cfg.cx],
-            cy=[float(x) for x in cfg.cy],
-            kd0=[0.] * V, kd1=[0.] * V, kd2=[0.] * V, p1=[0.] * V, p2=[0.] * V, transformations_path=tm_path))
-    raise ValueError(config)
+    return ref_env.activate_config(config)
 
 
 def build_reference_models(parameters, n_feats):
