@@ -642,6 +642,325 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_kernel(A
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shape-specialised frame-resident kernel: the product path for the layer shapes of the shipped model
+// (heads x dim = 10x40, 8x40, 5x30; train_skeleton_matching.py:45-46). Same algorithm, same summation order and the
+// same arithmetic as gat_aggregate_frame_kernel above - the outputs are bit-identical - but every size is a
+// compile-time constant and the instruction stream is cut down, because the generic kernel is issue-bound, not
+// memory-bound (ncu, profiles/r02_agg_before.md: 56 % issue-slot utilisation at 3.9 warps per scheduler, 125 k
+// warp-instructions per frame of which 11 % are the FMAs):
+//   * the head rows arrive as ONE bulk copy (they are contiguous, a1|a2 tails included: no separate attention table);
+//   * row / plane addresses are formed once per destination, column offsets are immediates;
+//   * the K padding of the output planes is written by the lanes that idle in the last column group (no extra pass);
+//   * barrier waits poll without reading the clock; no debug switches, no fp32 side output (those take the generic kernel).
+// ------------------------------------------------------------------------------------------------
+template <int H, int D> struct FrameShape {
+    static constexpr int HD = H * D;
+    static constexpr int LDZ = (HD + 2 * H + 3) & ~3;
+    static constexpr int VEC = (HD % 4 == 0) ? 4 : ((HD % 2 == 0) ? 2 : 1);
+    static constexpr int NV = HD / VEC;                       // column vectors per row
+    static constexpr int KMAX = (NV + 31) / 32;               // column vectors per lane
+    static constexpr int LDP = (HD + 63) / 64 * 64;           // row pitch of the output planes
+    static constexpr int NVP = LDP / VEC;                     // column vectors per plane row, K padding included
+};
+
+struct FramePlanS { int ring, zh, ze, a1e, wh, lsth, prs, total_floats; };
+
+template <int H, int D>
+__host__ __device__ inline FramePlanS frame_plan_s(int max_heads, int max_enodes) {
+    using S = FrameShape<H, D>;
+    FramePlanS f;
+    const int e_heads = max_heads + 2 * max_enodes;
+    int o = 0;
+    f.ring = o; o += kSlots * kChunkRows * S::LDZ;            // bulk-copy destinations first: 16-byte aligned
+    f.zh = o; o += max_heads * S::LDZ;                        // head rows, a1|a2 included
+    f.ze = o; o += S::LDZ;                                    // layer 0: the shared edge-node row
+    f.a1e = o; o += (max_enodes * H + 3) & ~3;
+    f.wh = o; o += (e_heads * H + 3) & ~3;
+    f.lsth = o; o += (e_heads + 3) & ~3;
+    f.prs = o; o += (2 * max_enodes + 3) & ~3;
+    f.total_floats = o;
+    return f;
+}
+
+__device__ __forceinline__ void agg_mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins == (1u << 28)) __trap();                  // a lost copy becomes an error, not a hang
+    }
+}
+
+template <int VEC> __device__ __forceinline__ void store_planes_vec(__nv_bfloat16* oh, __nv_bfloat16* ol, const float (&a)[VEC]) {
+    if constexpr (VEC == 4) {
+        uint32_t h0, l0, h1, l1;
+        split_pack2(a[0], a[1], h0, l0);
+        split_pack2(a[2], a[3], h1, l1);
+        *reinterpret_cast<uint2*>(oh) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(ol) = make_uint2(l0, l1);
+    } else if constexpr (VEC == 2) {
+        uint32_t h0, l0;
+        split_pack2(a[0], a[1], h0, l0);
+        *reinterpret_cast<uint32_t*>(oh) = h0;
+        *reinterpret_cast<uint32_t*>(ol) = l0;
+    } else {
+        __nv_bfloat16 h, l;
+        split_bf16(a[0], h, l);
+        oh[0] = h; ol[0] = l;
+    }
+}
+template <int VEC> __device__ __forceinline__ void store_planes_zero(__nv_bfloat16* oh, __nv_bfloat16* ol) {
+    if constexpr (VEC == 4) { *reinterpret_cast<uint2*>(oh) = make_uint2(0, 0); *reinterpret_cast<uint2*>(ol) = make_uint2(0, 0); }
+    else if constexpr (VEC == 2) { *reinterpret_cast<uint32_t*>(oh) = 0u; *reinterpret_cast<uint32_t*>(ol) = 0u; }
+    else { oh[0] = __float2bfloat16_rn(0.f); ol[0] = __float2bfloat16_rn(0.f); }
+}
+
+template <int H, int D, bool L0>
+__global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel(AggParams p, int max_heads, int max_enodes)
+{
+    using S = FrameShape<H, D>;
+    constexpr int HD = S::HD, LDZ = S::LDZ, VEC = S::VEC, NV = S::NV, KMAX = S::KMAX, LDP = S::LDP, NVP = S::NVP;
+    using V = typename VecT<VEC>::type;
+    extern __shared__ __align__(128) float smem_f[];
+    __shared__ __align__(8) uint64_t bar_full[kSlots];
+    __shared__ __align__(8) uint64_t bar_empty[kSlots];
+    __shared__ __align__(8) uint64_t bar_wh;                  // the heads' softmax weights (phase 1b) are complete
+    __shared__ __align__(8) uint64_t bar_heads;               // the head rows (bulk copy) have landed
+    const int b = blockIdx.x;
+    const int n0 = __ldg(p.node_off + b);
+    const int Nb = __ldg(p.node_off + b + 1) - n0;
+    if (Nb == 0) return;
+    const int h0 = __ldg(p.head_off + b);
+    const int Hb = __ldg(p.head_off + b + 1) - h0;
+    const int Mb = Nb - Hb;
+    const int Eh = Hb + 2 * Mb;                             // in-edges of the head destinations (CSR: head rows come first)
+    const int e0 = h0 + 5 * (n0 - h0);                      // first edge (CSR position) of the frame
+    const FramePlanS f = frame_plan_s<H, D>(max_heads, max_enodes);
+    float* ring = smem_f + f.ring;
+    float* zh = smem_f + f.zh;
+    float* zE = smem_f + f.ze;
+    float* a1e = smem_f + f.a1e;
+    float* wh = smem_f + f.wh;
+    int* lsth = reinterpret_cast<int*>(smem_f + f.lsth);
+    int* prs = reinterpret_cast<int*>(smem_f + f.prs);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool streamed = !L0 && Mb > 0;
+    const int n_chunks = (Mb + kChunkRows - 1) / kChunkRows;
+    // the frame's head rows are contiguous (layer 0: rows h0.. of the compact matrix), its edge-node rows follow them
+    const float* zheads = p.z + (size_t)(L0 ? h0 : n0) * LDZ;
+    const float* zen = L0 ? p.z + (size_t)p.n_heads_total * LDZ : p.z + (size_t)(n0 + Hb) * LDZ;
+    auto issue_chunk = [&](int c) {                         // one thread: bulk copy of chunk c into ring slot c % kSlots
+        const int rows = min(kChunkRows, Mb - c * kChunkRows);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)(LDZ * 4);
+        const uint32_t bar = agg_smem_u32(&bar_full[c % kSlots]);
+        agg_mbar_expect_tx(bar, bytes);
+        agg_bulk_load(agg_smem_u32(ring + (size_t)(c % kSlots) * kChunkRows * LDZ), zen + (size_t)c * kChunkRows * LDZ, bytes, bar);
+    };
+    if (tid == kFrameWarps * 32) {                          // lane 0 of the producer warp
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) { agg_mbar_init(agg_smem_u32(&bar_full[s]), 1); agg_mbar_init(agg_smem_u32(&bar_empty[s]), kFrameWarps); }
+        agg_mbar_init(agg_smem_u32(&bar_wh), kFrameWarps + 1);
+        agg_mbar_init(agg_smem_u32(&bar_heads), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t hb_bytes = (uint32_t)Hb * (uint32_t)(LDZ * 4);
+        agg_mbar_expect_tx(agg_smem_u32(&bar_heads), hb_bytes + (L0 ? (uint32_t)(LDZ * 4) : 0u));
+        agg_bulk_load(agg_smem_u32(zh), zheads, hb_bytes, agg_smem_u32(&bar_heads));
+        if (L0) agg_bulk_load(agg_smem_u32(zE), zen, (uint32_t)(LDZ * 4), agg_smem_u32(&bar_heads));
+        if (streamed)
+            for (int c = 0; c < kSlots && c < n_chunks; ++c) issue_chunk(c);
+    }
+    // ---- phase 1a: a1 of the edge-nodes, the heads' in-edge lists, (h1, h2) of every edge-node: small gathers through
+    // cp.async, issued back to back and waited for once ----
+    if (!L0)
+        for (int i = tid; i < Mb * H; i += kFrameThreads) {
+            const int r = i / H, c = i - r * H;
+            agg_cp_async4(agg_smem_u32(a1e + i), zen + (size_t)r * LDZ + HD + c);
+        }
+    for (int i = tid; i < Eh; i += kFrameThreads) agg_cp_async4(agg_smem_u32(lsth + i), p.col + e0 + i);
+    for (int k = tid; k < Mb; k += kFrameThreads) {
+        const int q = e0 + Eh + 3 * k;                      // CSR: 3 in-edges per edge-node after the head rows: h1, h2, self
+        agg_cp_async4(agg_smem_u32(prs + 2 * k), p.col + q);
+        agg_cp_async4(agg_smem_u32(prs + 2 * k + 1), p.col + q + 1);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                        // tables visible; the barriers are initialised past this point
+    agg_mbar_wait_spin(agg_smem_u32(&bar_heads), 0u);
+    // ---- phase 1b: softmax weights of the heads' in-edges, per attention head (gat2.py:78-88) ----
+    for (int q = tid; q < Hb * H; q += kFrameThreads) {
+        const int v = q / H, hh = q - v * H;
+        const int beg = __ldg(p.row_ptr + n0 + v) - e0;
+        const int deg = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg;
+        const float a2v = zh[v * LDZ + HD + H + hh];
+        float* wv = wh + (size_t)beg * H + hh;
+        float m = -INFINITY;
+        for (int i = 0; i < deg; ++i) {
+            const int u = lsth[beg + i] - n0;
+            const float a1u = (u < Hb) ? zh[u * LDZ + HD + hh] : (L0 ? zE[HD + hh] : a1e[(u - Hb) * H + hh]);
+            const float e = leaky(a1u + a2v, p.alpha);
+            wv[i * H] = e;
+            m = fmaxf(m, e);
+        }
+        float den = 0.f;
+        for (int i = 0; i < deg; ++i) {
+            const float e = soft_exp(wv[i * H] - m);
+            wv[i * H] = e;
+            den += e;
+        }
+        for (int i = 0; i < deg; ++i) wv[i * H] = soft_div(wv[i * H], den);
+    }
+    __syncwarp();
+    if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_wh));
+    // ---- phase 2 ----
+    if (wid == kFrameWarps) {
+        if (lane == 0 && streamed) {
+            for (int c = kSlots; c < n_chunks; ++c) {
+                const int s = c % kSlots;
+                agg_mbar_wait_spin(agg_smem_u32(&bar_empty[s]), (uint32_t)(c / kSlots - 1) & 1u);
+                issue_chunk(c);
+            }
+        }
+        return;
+    }
+    // lane geometry: column vector cv = lane + 32 j, first column cv * VEC, attention head of that column
+    int hj[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) hj[j] = min(H - 1, ((lane + 32 * j) * VEC) / D);
+    const int lcol = lane * VEC;
+    auto col_ok = [&](int j) -> bool { return 32 * (j + 1) <= NV ? true : lane + 32 * j < NV; };      // compile-time true for full groups
+    auto pad_ok = [&](int j) -> bool { return lane + 32 * j < NVP; };
+    float acc[kFrameOwn][KMAX][VEC];
+    int hbeg[kFrameOwn], hdeg[kFrameOwn], hcur[kFrameOwn];
+#pragma unroll
+    for (int t = 0; t < kFrameOwn; ++t) {
+        const int h = wid + t * kFrameWarps;
+        hbeg[t] = 0; hdeg[t] = 0; hcur[t] = 1;
+        if (h < Hb) {
+            hbeg[t] = __ldg(p.row_ptr + n0 + h) - e0;
+            hdeg[t] = __ldg(p.row_ptr + n0 + h + 1) - e0 - hbeg[t];
+        }
+    }
+    auto init_acc = [&]() {
+        agg_mbar_wait_spin(agg_smem_u32(&bar_wh), 0u);
+#pragma unroll
+        for (int t = 0; t < kFrameOwn; ++t) {
+            const int h = wid + t * kFrameWarps;
+            const float* zr = zh + (size_t)(h < Hb ? h : 0) * LDZ + lcol;
+            const float* wr = wh + (size_t)hbeg[t] * H;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+                float zv[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) zv[q] = 0.f;
+                float a = 0.f;
+                if (h < Hb && col_ok(j)) {
+                    *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zr + 32 * VEC * j);
+                    a = wr[hj[j]];
+                }
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
+            }
+        }
+    };
+    if (n_chunks == 0) init_acc();
+    const int lh = lane < H ? lane : 0;                     // attention head whose edge-node softmax this lane computes
+    const float alpha = p.alpha, act_slope = p.act_slope;
+    __nv_bfloat16* const out_hi = p.act_hi + (size_t)n0 * LDP + lcol;
+    __nv_bfloat16* const out_lo = p.act_lo + (size_t)n0 * LDP + lcol;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int k0 = c * kChunkRows, k1 = min(Mb, k0 + kChunkRows);
+        const int slot = c % kSlots;
+        const float* rows = zE;
+        if (!L0) {
+            agg_mbar_wait_spin(agg_smem_u32(&bar_full[slot]), (uint32_t)(c / kSlots) & 1u);
+            rows = ring + (size_t)slot * kChunkRows * LDZ;
+        }
+        // (a) the edge-node destination of this warp: in-edges (h1 -> e), (h2 -> e), (e -> e)
+        const int k = k0 + wid;
+        if (k < k1) {
+            const int h1 = prs[2 * k] - n0, h2 = prs[2 * k + 1] - n0;
+            const float* re = L0 ? rows : rows + (size_t)(k - k0) * LDZ;
+            const float* r1 = zh + (size_t)h1 * LDZ;
+            const float* r2 = zh + (size_t)h2 * LDZ;
+            const float a2e = re[HD + H + lh];
+            const float e1 = leaky(r1[HD + lh] + a2e, alpha);
+            const float e2 = leaky(r2[HD + lh] + a2e, alpha);
+            const float e3 = leaky(re[HD + lh] + a2e, alpha);
+            const float m = fmaxf(fmaxf(e1, e2), e3);
+            const float x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m), x3 = soft_exp(e3 - m);
+            const float den = (0.f + x1 + x2) + x3;
+            const float s1 = soft_div(x1, den), s2 = soft_div(x2, den), s3 = soft_div(x3, den);
+            __nv_bfloat16* oh = out_hi + (size_t)(Hb + k) * LDP;
+            __nv_bfloat16* ol = out_lo + (size_t)(Hb + k) * LDP;
+#pragma unroll
+            for (int j = 0; j < KMAX; ++j) {
+                const float w1 = __shfl_sync(0xffffffffu, s1, hj[j]);
+                const float w2 = __shfl_sync(0xffffffffu, s2, hj[j]);
+                const float w3 = __shfl_sync(0xffffffffu, s3, hj[j]);
+                if (col_ok(j)) {
+                    float z1[VEC], z2[VEC], ze[VEC], o[VEC];
+                    *reinterpret_cast<V*>(z1) = *reinterpret_cast<const V*>(r1 + lcol + 32 * VEC * j);
+                    *reinterpret_cast<V*>(z2) = *reinterpret_cast<const V*>(r2 + lcol + 32 * VEC * j);
+                    *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + lcol + 32 * VEC * j);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) o[q] = leaky_le1(fmaf(w3, ze[q], fmaf(w2, z2[q], fmaf(w1, z1[q], 0.f))), act_slope);
+                    store_planes_vec<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j, o);
+                } else if (NVP > NV && pad_ok(j)) {
+                    store_planes_zero<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j);        // K padding of the planes stays zero
+                }
+            }
+        }
+        // (b) contributions of the chunk's rows to the owned heads, ascending edge id
+        if (c == 0) init_acc();
+#pragma unroll
+        for (int t = 0; t < kFrameOwn; ++t) {
+            while (hcur[t] < hdeg[t]) {
+                const int pos = hbeg[t] + hcur[t];
+                const int kk = lsth[pos] - n0 - Hb;
+                if (kk >= k1) break;
+                const float* re = (L0 ? rows : rows + (size_t)(kk - k0) * LDZ) + lcol;
+                const float* wp = wh + (size_t)pos * H;
+#pragma unroll
+                for (int j = 0; j < KMAX; ++j) {
+                    if (!col_ok(j)) continue;
+                    float ze[VEC];
+                    *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + 32 * VEC * j);
+                    const float a = wp[hj[j]];
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, ze[q], acc[t][j][q]);
+                }
+                ++hcur[t];
+            }
+        }
+        if (streamed) {                                     // this warp is done with the slot
+            __syncwarp();
+            if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_empty[slot]));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kFrameOwn; ++t) {
+        const int h = wid + t * kFrameWarps;
+        if (h >= Hb) continue;
+        __nv_bfloat16* oh = out_hi + (size_t)h * LDP;
+        __nv_bfloat16* ol = out_lo + (size_t)h * LDP;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            if (col_ok(j)) {
+                float o[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o[q] = leaky_le1(acc[t][j][q], act_slope);
+                store_planes_vec<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j, o);
+            } else if (NVP > NV && pad_ok(j)) {
+                store_planes_zero<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j);
+            }
+        }
+    }
+}
+
 // last layer (heads*dim == 1): one thread per destination node, sigmoid fused (gat2.py:143-145)
 __global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
     int n_nodes_total, const int* __restrict__ row_ptr, const int* __restrict__ col,
@@ -1139,9 +1458,37 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     // CTA's serial latency (25 us per layer for a Panoptic frame); the large-frame kernel spreads a frame over its edge and
     // head units (8 CTAs for 20 heads / 160 edge-nodes: 10-16 us), so tiny batches take it.
     const bool tiny_batch = impl == 0 && n_frames * 8 <= 148 && 3 * heads <= 32;
-    // ---- frame-resident kernel: one CTA per frame, whenever the frame plan fits in shared memory ----
-    if (((impl == 0 && !tiny_batch) || impl == 3) && max_heads_per_frame > 0 && max_enodes_per_frame > 0 &&
-        max_heads_per_frame <= kFrameOwn * kFrameWarps && HD / vec <= 32 * 4) {
+    // ---- frame-resident kernels: one CTA per frame, whenever the frame plan fits in shared memory ----
+    const bool frame_path = ((impl == 0 && !tiny_batch) || impl == 3 || impl == 5) && max_heads_per_frame > 0 && max_enodes_per_frame > 0 &&
+                            max_heads_per_frame <= kFrameOwn * kFrameWarps && HD / vec <= 32 * 4;
+    // shape-specialised kernel (the shipped layer shapes, planes out, LeakyReLU slope in [0, 1]); impl 5 forces the generic one
+    if (frame_path && impl != 5 && act_hi && !raw_f32 && p.dbg == 0 && act_slope >= 0.f && act_slope <= 1.f) {
+        auto launch_s = [&](auto kern, const FramePlanS f, int ldz_s, int ldp_s, bool* taken) -> int {
+            *taken = false;
+            const size_t smem_s = (size_t)f.total_floats * sizeof(float);
+            if (ldz != ldz_s || ld_planes != ldp_s || smem_s > 220 * 1024) return B200POSE_OK;
+            *taken = true;
+            B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            kern<<<n_frames, kFrameThreads, smem_s, st>>>(p, max_heads_per_frame, max_enodes_per_frame);
+            B2_CHECK_LAUNCH();
+            return B200POSE_OK;
+        };
+        bool taken = false;
+        int rc = B200POSE_OK;
+#define B2_TRY_SHAPE(HH, DD)                                                                                                        \
+        if (!taken && heads == HH && dim == DD) {                                                                                   \
+            using S_ = FrameShape<HH, DD>;                                                                                           \
+            rc = layer0 ? launch_s(gat_aggregate_frame_s_kernel<HH, DD, true>, frame_plan_s<HH, DD>(max_heads_per_frame, max_enodes_per_frame), S_::LDZ, S_::LDP, &taken) \
+                        : launch_s(gat_aggregate_frame_s_kernel<HH, DD, false>, frame_plan_s<HH, DD>(max_heads_per_frame, max_enodes_per_frame), S_::LDZ, S_::LDP, &taken); \
+            if (rc != B200POSE_OK) return rc;                                                                                        \
+        }
+        B2_TRY_SHAPE(10, 40)
+        B2_TRY_SHAPE(8, 40)
+        B2_TRY_SHAPE(5, 30)
+#undef B2_TRY_SHAPE
+        if (taken) return B200POSE_OK;
+    }
+    if (frame_path) {
         const FramePlan f = frame_plan(max_heads_per_frame, max_enodes_per_frame, HD, heads, ldz);
         const size_t smem_frame = (size_t)f.total_floats * sizeof(float);
         if (smem_frame <= 220 * 1024) {
@@ -1157,13 +1504,13 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
             return launch_frame(gat_aggregate_frame_kernel<1, 4>);
         }
     }
-    if (impl == 3) {
-        set_error("gat_aggregate: impl 3 (frame-resident kernel) needs frames of at most %d heads whose plan fits in shared memory "
+    if (impl == 3 || impl == 5) {
+        set_error("gat_aggregate: impl 3 / 5 (frame-resident kernels) need frames of at most %d heads whose plan fits in shared memory "
                   "(%d heads, %d edge-nodes per frame here)", kFrameOwn * kFrameWarps, max_heads_per_frame, max_enodes_per_frame);
         return B200POSE_E_UNSUPPORTED;
     }
-    B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel), 2 (large-frame kernel) or 3 (frame-resident kernel, "
-                 "frames of at most 32 heads whose plan fits in shared memory)");
+    B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel), 2 (large-frame kernel), 3 (frame-resident kernel, "
+                 "frames of at most 32 heads whose plan fits in shared memory) or 5 (its generic, not shape-specialised form)");
     // ---- gather kernel: work unit = (frame, chunk of destination nodes). ---- In-degree of a head is 1 + H_b - n_g <= H_b and of an
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;

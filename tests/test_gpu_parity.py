@@ -159,22 +159,28 @@ def test_gat_scores_vs_reference(config, agg_impl):
     print('worst relative score error', config, worst)
 
 
-def test_aggregation_kernels_agree_bitwise():
-    """The frame-resident and the gather aggregation kernels sum every output element in the same order
-    (ascending reference edge id), so their layer outputs are bit-identical."""
-    pipe = get_pipe('panoptic')
-    tags, pb, db = golden_batch('panoptic')
+@pytest.mark.parametrize('config', ['panoptic', 'arp3', 'arp6', 'pansub'])
+def test_aggregation_kernels_agree_bitwise(config):
+    """The frame-resident kernels (shape-specialised product kernel and its generic form) and the gather kernel sum every
+    output element in the same order (ascending reference edge id) with the same arithmetic, so their outputs are
+    bit-identical: the final scores of the product path (planes out: the specialised kernel) and, with the fp32 layer
+    outputs requested (the generic kernels), every layer."""
+    pipe = get_pipe(config)
+    tags, pb, db = golden_batch(config)
     g = pipe.build_graph(db, with_coo=False)
-    outs = []
-    for impl in (3, 1):                 # 3 = frame-resident kernel forced (a batch this small would dispatch to the large-frame kernel)
-        pipe.agg_impl = impl
+    outs, finals = [], []
+    for impl in (3, 5, 1):              # 3 = frame-resident, shape-specialised where the shape is compiled in (a batch this small would
+        pipe.agg_impl = impl            # otherwise take the large-frame kernel); 5 = its generic form; 1 = gather kernel
         try:
+            finals.append(pipe.gat_forward(db, g).cpu().numpy().copy())
             scores, raws = pipe.gat_forward(db, g, keep_layers=True)
         finally:
             pipe.agg_impl = 0
         outs.append([r.cpu().numpy() for r in raws] + [scores.cpu().numpy()])
-    for a, b in zip(*outs):
-        assert np.array_equal(a, b)
+    for a, b, c in zip(*outs):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(finals[0], finals[1]) and np.array_equal(finals[0], finals[2])
+    assert np.array_equal(finals[0], outs[0][-1])
 
 
 @pytest.mark.parametrize('config', helpers.CONFIGS)
