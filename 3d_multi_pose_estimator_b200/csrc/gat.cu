@@ -51,8 +51,20 @@ template <int VEC> __device__ __forceinline__ void load_vec(const float* p, floa
 // Softmax arithmetic of both aggregation kernels: exp(x) for x <= 0 through the SFU (ex2.approx, ~2 ulp) and the
 // normalisation through the SFU reciprocal - a softmax weight that is off by 1e-7 relative moves a score by far less
 // than the 1e-4 tolerance, and the precise expf/IEEE division cost ~25 issue slots per weight in issue-bound kernels.
-__device__ __forceinline__ float soft_exp(float x) { return __expf(x); }
-__device__ __forceinline__ float soft_div(float x, float d) { return __fdividef(x, d); }
+// Written as PTX so that every aggregation kernel executes exactly these instructions (their outputs are compared
+// bit for bit): ex2.approx.ftz of x*log2(e) - two instructions, no denormal range code - and one SFU reciprocal per
+// denominator, shared by the weights that are divided by it (the asm is not volatile: the compiler merges equal rcp's).
+__device__ __forceinline__ float soft_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float soft_rcp(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r;
+}
+__device__ __forceinline__ float soft_div(float x, float d) { return x * soft_rcp(d); }
 
 constexpr int kAggWarps = 8;
 
@@ -683,16 +695,17 @@ __host__ __device__ inline FramePlanS frame_plan_s(int max_heads, int max_enodes
     return f;
 }
 
-__device__ __forceinline__ void agg_mbar_wait_spin(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void agg_mbar_wait_spin(uint32_t bar, uint32_t parity, uint32_t hint = 1000u) {
     uint32_t done = 0, spins = 0;
     while (true) {
+        // the hint lets the hardware park the warp for up to ~1 us instead of returning to the polling loop at once
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(hint) : "memory");
         if (done) break;
-        if (++spins == (1u << 28)) __trap();                  // a lost copy becomes an error, not a hang
+        if (++spins == (1u << 24)) __trap();                  // a lost copy becomes an error, not a hang
     }
 }
 
@@ -774,6 +787,10 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel
         if (streamed)
             for (int c = 0; c < kSlots && c < n_chunks; ++c) issue_chunk(c);
     }
+    // the CSR bounds phase 1b needs are requested now, so their latency overlaps the staging
+    const float alpha = p.alpha, act_slope = p.act_slope;
+    int rp_beg = 0, rp_end = 0;
+    if (tid < Hb * H) { rp_beg = __ldg(p.row_ptr + n0 + tid / H); rp_end = __ldg(p.row_ptr + n0 + tid / H + 1); }
     // ---- phase 1a: a1 of the edge-nodes, the heads' in-edge lists, (h1, h2) of every edge-node: small gathers through
     // cp.async, issued back to back and waited for once ----
     if (!L0)
@@ -793,15 +810,15 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel
     // ---- phase 1b: softmax weights of the heads' in-edges, per attention head (gat2.py:78-88) ----
     for (int q = tid; q < Hb * H; q += kFrameThreads) {
         const int v = q / H, hh = q - v * H;
-        const int beg = __ldg(p.row_ptr + n0 + v) - e0;
-        const int deg = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg;
+        const int beg = (q == tid ? rp_beg : __ldg(p.row_ptr + n0 + v)) - e0;
+        const int deg = (q == tid ? rp_end : __ldg(p.row_ptr + n0 + v + 1)) - e0 - beg;
         const float a2v = zh[v * LDZ + HD + H + hh];
         float* wv = wh + (size_t)beg * H + hh;
         float m = -INFINITY;
         for (int i = 0; i < deg; ++i) {
             const int u = lsth[beg + i] - n0;
             const float a1u = (u < Hb) ? zh[u * LDZ + HD + hh] : (L0 ? zE[HD + hh] : a1e[(u - Hb) * H + hh]);
-            const float e = leaky(a1u + a2v, p.alpha);
+            const float e = leaky_le1(a1u + a2v, alpha);
             wv[i * H] = e;
             m = fmaxf(m, e);
         }
@@ -868,7 +885,6 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel
     };
     if (n_chunks == 0) init_acc();
     const int lh = lane < H ? lane : 0;                     // attention head whose edge-node softmax this lane computes
-    const float alpha = p.alpha, act_slope = p.act_slope;
     __nv_bfloat16* const out_hi = p.act_hi + (size_t)n0 * LDP + lcol;
     __nv_bfloat16* const out_lo = p.act_lo + (size_t)n0 * LDP + lcol;
     for (int c = 0; c < n_chunks; ++c) {
@@ -887,9 +903,9 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel
             const float* r1 = zh + (size_t)h1 * LDZ;
             const float* r2 = zh + (size_t)h2 * LDZ;
             const float a2e = re[HD + H + lh];
-            const float e1 = leaky(r1[HD + lh] + a2e, alpha);
-            const float e2 = leaky(r2[HD + lh] + a2e, alpha);
-            const float e3 = leaky(re[HD + lh] + a2e, alpha);
+            const float e1 = leaky_le1(r1[HD + lh] + a2e, alpha);        // 0 <= alpha <= 1 here (dispatch): same value as leaky()
+            const float e2 = leaky_le1(r2[HD + lh] + a2e, alpha);
+            const float e3 = leaky_le1(re[HD + lh] + a2e, alpha);
             const float m = fmaxf(fmaxf(e1, e2), e3);
             const float x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m), x3 = soft_exp(e3 - m);
             const float den = (0.f + x1 + x2) + x3;
@@ -958,6 +974,328 @@ __global__ void __launch_bounds__(kFrameThreads, 1) gat_aggregate_frame_s_kernel
                 store_planes_zero<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent form of the shape-specialised kernel: one CTA per SM walks frames b = blockIdx.x, += gridDim.x with the
+// per-frame set-up taken off the consumers' path. 18 warps:
+//   warps 0..15  consumers  - exactly the chunk loop of gat_aggregate_frame_s_kernel (same order, same arithmetic:
+//                             bit-identical outputs);
+//   warp 16      streamer   - bulk copies of the edge-node rows into the ring, one running chunk sequence across frame
+//                             boundaries, so the first chunks of frame f+1 are in flight while frame f is finished;
+//   warp 17      preparer   - for frame f+1, into the other of two table sets: head rows (bulk copy), a1 of the
+//                             edge-nodes, in-edge lists, (h1, h2) pairs, CSR bounds and the heads' softmax weights.
+// With one CTA per frame those ~4 us of dependent loads, staging and weights sat in front of every frame's streaming at
+// 4 warps per scheduler; here they run beside the previous frame's arithmetic.
+// ------------------------------------------------------------------------------------------------
+
+struct FramePlanP { int ring, set0, set_stride, zh, ze, wh, lsth, prs, meta, a1e, total_floats; };   // zh..a1e: offsets inside a set
+
+template <int H, int D, int W>
+__host__ __device__ inline FramePlanP frame_plan_p(int max_heads, int max_enodes, int slots) {
+    using S = FrameShape<H, D>;
+    FramePlanP f;
+    const int e_heads = max_heads + 2 * max_enodes;
+    int o = 0;
+    f.ring = o; o += slots * W * S::LDZ;                      // a chunk = one edge-node row per consumer warp
+    f.set0 = o;
+    int q = 0;
+    f.zh = q; q += max_heads * S::LDZ;
+    f.ze = q; q += S::LDZ;
+    f.wh = q; q += (e_heads * H + 3) & ~3;
+    f.lsth = q; q += (e_heads + 3) & ~3;
+    f.prs = q; q += (2 * max_enodes + 3) & ~3;
+    f.meta = q; q += (8 + 2 * max_heads + 3) & ~3;           // n0, h0, Hb, Mb, e0, then (beg, deg) of every head's CSR row
+    f.a1e = q; q += (max_enodes * H + 3) & ~3;               // a1 of the edge-nodes (input of the heads' softmax weights)
+    f.set_stride = q;
+    o += 2 * q;
+    f.total_floats = o;
+    return f;
+}
+
+// W consumer warps, each owning OWN head destinations (frames of at most W * OWN heads): 20 x 1 for frames of up to 20
+// heads (5 views x 4 persons) - one head per warp balances part (b), and 22 warps hide the per-chunk latency chain
+// better than 18 - and 16 x 2 up to 32 heads (the register file holds 18 warps with two heads' accumulators each).
+template <int H, int D, bool L0, int W, int OWN>
+__global__ void __launch_bounds__((W + 2) * 32, 1) gat_aggregate_frame_p_kernel(AggParams p, int max_heads, int max_enodes, int slots, uint32_t hint)
+{
+    using S = FrameShape<H, D>;
+    constexpr int HD = S::HD, LDZ = S::LDZ, VEC = S::VEC, NV = S::NV, KMAX = S::KMAX, LDP = S::LDP, NVP = S::NVP;
+    using V = typename VecT<VEC>::type;
+    extern __shared__ __align__(128) float smem_f[];
+    __shared__ __align__(8) uint64_t bar_full[kSlots];
+    __shared__ __align__(8) uint64_t bar_empty[kSlots];
+    __shared__ __align__(8) uint64_t bar_rows[2];             // head rows of a set have landed (bulk copy)
+    __shared__ __align__(8) uint64_t bar_tab_full[2];         // a set is complete (preparer -> consumers)
+    __shared__ __align__(8) uint64_t bar_tab_empty[2];        // a set is free again (consumers -> preparer)
+    __shared__ __align__(8) uint64_t bar_wh[2];               // the heads' softmax weights of a set are complete (consumers -> consumers)
+    const FramePlanP f = frame_plan_p<H, D, W>(max_heads, max_enodes, slots);
+    float* ring = smem_f + f.ring;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; ++s) { agg_mbar_init(agg_smem_u32(&bar_full[s]), 1); agg_mbar_init(agg_smem_u32(&bar_empty[s]), W); }
+        for (int k = 0; k < 2; ++k) {
+            agg_mbar_init(agg_smem_u32(&bar_rows[k]), 1);
+            agg_mbar_init(agg_smem_u32(&bar_tab_full[k]), 1);
+            agg_mbar_init(agg_smem_u32(&bar_tab_empty[k]), W);
+            agg_mbar_init(agg_smem_u32(&bar_wh[k]), W);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const float alpha = p.alpha, act_slope = p.act_slope;
+
+    if (wid == W) {
+        // ===================== streamer: the ring, one chunk sequence over all frames of this CTA =====================
+        if (L0 || lane != 0) return;
+        int g = 0;                                                        // running chunk index
+        for (int b = blockIdx.x; b < p.n_frames; b += G) {
+            const int n0 = __ldg(p.node_off + b), n1 = __ldg(p.node_off + b + 1);
+            const int Hb = __ldg(p.head_off + b + 1) - __ldg(p.head_off + b);
+            const int Mb = n1 - n0 - Hb;
+            const float* zen = p.z + (size_t)(n0 + Hb) * LDZ;
+            const int n_chunks = (Mb + W - 1) / W;
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const int s = g % slots;
+                if (g >= slots) agg_mbar_wait_spin(agg_smem_u32(&bar_empty[s]), (uint32_t)(g / slots - 1) & 1u, hint);
+                const int rows = min(W, Mb - c * W);
+                const uint32_t bytes = (uint32_t)rows * (uint32_t)(LDZ * 4);
+                const uint32_t bar = agg_smem_u32(&bar_full[s]);
+                agg_mbar_expect_tx(bar, bytes);
+                agg_bulk_load(agg_smem_u32(ring + (size_t)s * W * LDZ), zen + (size_t)c * W * LDZ, bytes, bar);
+            }
+        }
+        return;
+    }
+    if (wid == W + 1) {
+        // ===================== preparer: table set (i & 1) of local frame i =====================
+        int i = 0;
+        for (int b = blockIdx.x; b < p.n_frames; b += G, ++i) {
+            const int k = i & 1;
+            float* set = smem_f + f.set0 + (size_t)k * f.set_stride;
+            float* zh = set + f.zh; float* zE = set + f.ze; float* a1e = set + f.a1e;
+            int* lsth = reinterpret_cast<int*>(set + f.lsth);
+            int* prs = reinterpret_cast<int*>(set + f.prs);
+            int* meta = reinterpret_cast<int*>(set + f.meta);
+            if (i >= 2) agg_mbar_wait_spin(agg_smem_u32(&bar_tab_empty[k]), (uint32_t)(i / 2 - 1) & 1u, hint);
+            const int n0 = __ldg(p.node_off + b), Nb = __ldg(p.node_off + b + 1) - n0;
+            const int h0 = __ldg(p.head_off + b), Hb = __ldg(p.head_off + b + 1) - h0;
+            const int Mb = Nb - Hb, Eh = Hb + 2 * Mb, e0 = h0 + 5 * (n0 - h0);
+            const float* zheads = p.z + (size_t)(L0 ? h0 : n0) * LDZ;
+            const float* zen = L0 ? p.z + (size_t)p.n_heads_total * LDZ : p.z + (size_t)(n0 + Hb) * LDZ;
+            if (Nb > 0) {
+                if (lane == 0) {
+                    const uint32_t hb_bytes = (uint32_t)Hb * (uint32_t)(LDZ * 4);
+                    const uint32_t bar = agg_smem_u32(&bar_rows[k]);
+                    agg_mbar_expect_tx(bar, hb_bytes + (L0 ? (uint32_t)(LDZ * 4) : 0u));
+                    agg_bulk_load(agg_smem_u32(zh), zheads, hb_bytes, bar);
+                    if (L0) agg_bulk_load(agg_smem_u32(zE), zen, (uint32_t)(LDZ * 4), bar);
+                }
+                // CSR bounds of the head rows (requested first: phase 1b and the consumers need them)
+                for (int v = lane; v < Hb; v += 32) {
+                    const int beg = __ldg(p.row_ptr + n0 + v) - e0;
+                    meta[8 + 2 * v] = beg;
+                    meta[8 + 2 * v + 1] = __ldg(p.row_ptr + n0 + v + 1) - e0 - beg;
+                }
+                if (!L0)
+                    for (int t = lane; t < Mb * H; t += 32) {
+                        const int r = t / H, c = t - r * H;
+                        agg_cp_async4(agg_smem_u32(a1e + t), zen + (size_t)r * LDZ + HD + c);
+                    }
+                for (int t = lane; t < Eh; t += 32) agg_cp_async4(agg_smem_u32(lsth + t), p.col + e0 + t);
+                for (int t = lane; t < Mb; t += 32) {
+                    const int q = e0 + Eh + 3 * t;
+                    agg_cp_async4(agg_smem_u32(prs + 2 * t), p.col + q);
+                    agg_cp_async4(agg_smem_u32(prs + 2 * t + 1), p.col + q + 1);
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+            }
+            if (lane == 0) {
+                meta[0] = n0; meta[1] = h0; meta[2] = Hb; meta[3] = Mb; meta[4] = e0;
+                if (Nb == 0) agg_mbar_arrive(agg_smem_u32(&bar_rows[k]));      // an empty frame still uses up one phase of its set's barriers
+            }
+            __syncwarp();
+            if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_tab_full[k]));
+        }
+        return;
+    }
+    // ===================== consumers =====================
+    int hj[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) hj[j] = min(H - 1, ((lane + 32 * j) * VEC) / D);
+    const int lcol = lane * VEC;
+    auto col_ok = [&](int j) -> bool { return 32 * (j + 1) <= NV ? true : lane + 32 * j < NV; };
+    auto pad_ok = [&](int j) -> bool { return lane + 32 * j < NVP; };
+    const int lh = lane < H ? lane : 0;
+    int g = 0;                                                            // running chunk index (matches the streamer's)
+    int i = 0;
+    for (int b = blockIdx.x; b < p.n_frames; b += G, ++i) {
+        const int ks = i & 1;
+        float* set = smem_f + f.set0 + (size_t)ks * f.set_stride;
+        const float* zh = set + f.zh; const float* zE = set + f.ze; float* wh = set + f.wh; const float* a1e = set + f.a1e;
+        const int* lsth = reinterpret_cast<const int*>(set + f.lsth);
+        const int* prs = reinterpret_cast<const int*>(set + f.prs);
+        const int* meta = reinterpret_cast<const int*>(set + f.meta);
+        agg_mbar_wait_spin(agg_smem_u32(&bar_tab_full[ks]), (uint32_t)(i / 2) & 1u, hint);
+        const int n0 = meta[0], Hb = meta[2], Mb = meta[3];
+        if (Hb + Mb > 0) {
+            agg_mbar_wait_spin(agg_smem_u32(&bar_rows[ks]), (uint32_t)(i / 2) & 1u, hint);     // acquires the copied head rows
+            const int n_chunks = (Mb + W - 1) / W;
+            // softmax weights of the heads' in-edges, per attention head (gat2.py:78-88): the consumers' own share, reported
+            // through bar_wh; only part (b) below reads them, so nobody waits before its first edge-node destination is done
+            for (int q = tid; q < Hb * H; q += W * 32) {
+                const int v = q / H, hh = q - v * H;
+                const int beg = meta[8 + 2 * v], deg = meta[8 + 2 * v + 1];
+                const float a2v = zh[v * LDZ + HD + H + hh];
+                float* wv = wh + (size_t)beg * H + hh;
+                float m = -INFINITY;
+                for (int t = 0; t < deg; ++t) {
+                    const int u = lsth[beg + t] - n0;
+                    const float a1u = (u < Hb) ? zh[u * LDZ + HD + hh] : (L0 ? zE[HD + hh] : a1e[(u - Hb) * H + hh]);
+                    const float e = leaky_le1(a1u + a2v, alpha);
+                    wv[t * H] = e;
+                    m = fmaxf(m, e);
+                }
+                float den = 0.f;
+                for (int t = 0; t < deg; ++t) {
+                    const float e = soft_exp(wv[t * H] - m);
+                    wv[t * H] = e;
+                    den += e;
+                }
+                for (int t = 0; t < deg; ++t) wv[t * H] = soft_div(wv[t * H], den);
+            }
+            __syncwarp();
+            if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_wh[ks]));
+            float acc[OWN][KMAX][VEC];
+            int hbeg[OWN], hdeg[OWN], hcur[OWN];
+#pragma unroll
+            for (int t = 0; t < OWN; ++t) {
+                const int h = wid + t * W;
+                hbeg[t] = 0; hdeg[t] = 0; hcur[t] = 1;
+                if (h < Hb) { hbeg[t] = meta[8 + 2 * h]; hdeg[t] = meta[8 + 2 * h + 1]; }
+            }
+            auto init_acc = [&]() {
+                agg_mbar_wait_spin(agg_smem_u32(&bar_wh[ks]), (uint32_t)(i / 2) & 1u, hint);
+#pragma unroll
+                for (int t = 0; t < OWN; ++t) {
+                    const int h = wid + t * W;
+                    const float* zr = zh + (size_t)(h < Hb ? h : 0) * LDZ + lcol;
+                    const float* wr = wh + (size_t)hbeg[t] * H;
+#pragma unroll
+                    for (int j = 0; j < KMAX; ++j) {
+                        float zv[VEC];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) zv[q] = 0.f;
+                        float a = 0.f;
+                        if (h < Hb && col_ok(j)) {
+                            *reinterpret_cast<V*>(zv) = *reinterpret_cast<const V*>(zr + 32 * VEC * j);
+                            a = wr[hj[j]];
+                        }
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, zv[q], 0.f);
+                    }
+                }
+            };
+            if (n_chunks == 0) init_acc();
+            __nv_bfloat16* const out_hi = p.act_hi + (size_t)n0 * LDP + lcol;
+            __nv_bfloat16* const out_lo = p.act_lo + (size_t)n0 * LDP + lcol;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int k0 = c * W, k1 = min(Mb, k0 + W);
+                const float* rows = zE;
+                int slot = 0;
+                if (!L0) {
+                    slot = g % slots;
+                    agg_mbar_wait_spin(agg_smem_u32(&bar_full[slot]), (uint32_t)(g / slots) & 1u, hint);
+                    rows = ring + (size_t)slot * W * LDZ;
+                }
+                // (a) the edge-node destination of this warp: in-edges (h1 -> e), (h2 -> e), (e -> e)
+                const int k = k0 + wid;
+                if (k < k1) {
+                    const int h1 = prs[2 * k] - n0, h2 = prs[2 * k + 1] - n0;
+                    const float* re = L0 ? rows : rows + (size_t)(k - k0) * LDZ;
+                    const float* r1 = zh + (size_t)h1 * LDZ;
+                    const float* r2 = zh + (size_t)h2 * LDZ;
+                    const float a2e = re[HD + H + lh];
+                    const float e1 = leaky_le1(r1[HD + lh] + a2e, alpha);
+                    const float e2 = leaky_le1(r2[HD + lh] + a2e, alpha);
+                    const float e3 = leaky_le1(re[HD + lh] + a2e, alpha);
+                    const float m = fmaxf(fmaxf(e1, e2), e3);
+                    const float x1 = soft_exp(e1 - m), x2 = soft_exp(e2 - m), x3 = soft_exp(e3 - m);
+                    const float den = (0.f + x1 + x2) + x3;
+                    const float s1 = soft_div(x1, den), s2 = soft_div(x2, den), s3 = soft_div(x3, den);
+                    __nv_bfloat16* oh = out_hi + (size_t)(Hb + k) * LDP;
+                    __nv_bfloat16* ol = out_lo + (size_t)(Hb + k) * LDP;
+#pragma unroll
+                    for (int j = 0; j < KMAX; ++j) {
+                        const float w1 = __shfl_sync(0xffffffffu, s1, hj[j]);
+                        const float w2 = __shfl_sync(0xffffffffu, s2, hj[j]);
+                        const float w3 = __shfl_sync(0xffffffffu, s3, hj[j]);
+                        if (col_ok(j)) {
+                            float z1[VEC], z2[VEC], ze[VEC], o[VEC];
+                            *reinterpret_cast<V*>(z1) = *reinterpret_cast<const V*>(r1 + lcol + 32 * VEC * j);
+                            *reinterpret_cast<V*>(z2) = *reinterpret_cast<const V*>(r2 + lcol + 32 * VEC * j);
+                            *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + lcol + 32 * VEC * j);
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) o[q] = leaky_le1(fmaf(w3, ze[q], fmaf(w2, z2[q], fmaf(w1, z1[q], 0.f))), act_slope);
+                            store_planes_vec<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j, o);
+                        } else if (NVP > NV && pad_ok(j)) {
+                            store_planes_zero<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j);
+                        }
+                    }
+                }
+                // (b) contributions of the chunk's rows to the owned heads, ascending edge id
+                if (c == 0) init_acc();
+#pragma unroll
+                for (int t = 0; t < OWN; ++t) {
+                    while (hcur[t] < hdeg[t]) {
+                        const int pos = hbeg[t] + hcur[t];
+                        const int kk = lsth[pos] - n0 - Hb;
+                        if (kk >= k1) break;
+                        const float* re = (L0 ? rows : rows + (size_t)(kk - k0) * LDZ) + lcol;
+                        const float* wp = wh + (size_t)pos * H;
+#pragma unroll
+                        for (int j = 0; j < KMAX; ++j) {
+                            if (!col_ok(j)) continue;
+                            float ze[VEC];
+                            *reinterpret_cast<V*>(ze) = *reinterpret_cast<const V*>(re + 32 * VEC * j);
+                            const float a = wp[hj[j]];
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) acc[t][j][q] = fmaf(a, ze[q], acc[t][j][q]);
+                        }
+                        ++hcur[t];
+                    }
+                }
+                if (!L0) {                                      // this warp is done with the slot
+                    __syncwarp();
+                    if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_empty[slot]));
+                    ++g;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < OWN; ++t) {
+                const int h = wid + t * W;
+                if (h >= Hb) continue;
+                __nv_bfloat16* oh = out_hi + (size_t)h * LDP;
+                __nv_bfloat16* ol = out_lo + (size_t)h * LDP;
+#pragma unroll
+                for (int j = 0; j < KMAX; ++j) {
+                    if (col_ok(j)) {
+                        float o[VEC];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) o[q] = leaky_le1(acc[t][j][q], act_slope);
+                        store_planes_vec<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j, o);
+                    } else if (NVP > NV && pad_ok(j)) {
+                        store_planes_zero<VEC>(oh + 32 * VEC * j, ol + 32 * VEC * j);
+                    }
+                }
+            }
+        }
+        else if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_wh[ks]));          // an empty frame still uses up one phase of its set's barriers
+        __syncwarp();
+        if (lane == 0) agg_mbar_arrive(agg_smem_u32(&bar_tab_empty[ks]));       // the set may be overwritten
     }
 }
 
@@ -1459,10 +1797,10 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     // head units (8 CTAs for 20 heads / 160 edge-nodes: 10-16 us), so tiny batches take it.
     const bool tiny_batch = impl == 0 && n_frames * 8 <= 148 && 3 * heads <= 32;
     // ---- frame-resident kernels: one CTA per frame, whenever the frame plan fits in shared memory ----
-    const bool frame_path = ((impl == 0 && !tiny_batch) || impl == 3 || impl == 5) && max_heads_per_frame > 0 && max_enodes_per_frame > 0 &&
+    const bool frame_path = ((impl == 0 && !tiny_batch) || impl == 3 || impl == 5 || impl == 6) && max_heads_per_frame > 0 && max_enodes_per_frame > 0 &&
                             max_heads_per_frame <= kFrameOwn * kFrameWarps && HD / vec <= 32 * 4;
     // shape-specialised kernel (the shipped layer shapes, planes out, LeakyReLU slope in [0, 1]); impl 5 forces the generic one
-    if (frame_path && impl != 5 && act_hi && !raw_f32 && p.dbg == 0 && act_slope >= 0.f && act_slope <= 1.f) {
+    if (frame_path && impl != 5 && act_hi && !raw_f32 && p.dbg == 0 && act_slope >= 0.f && act_slope <= 1.f && alpha >= 0.f && alpha <= 1.f) {
         auto launch_s = [&](auto kern, const FramePlanS f, int ldz_s, int ldp_s, bool* taken) -> int {
             *taken = false;
             const size_t smem_s = (size_t)f.total_floats * sizeof(float);
@@ -1473,8 +1811,51 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
             B2_CHECK_LAUNCH();
             return B200POSE_OK;
         };
+        // persistent form first (one CTA per SM, set-up of frame f+1 beside the arithmetic of frame f); impl 6 forces the
+        // one-CTA-per-frame form
+        auto launch_p = [&](auto kern, auto plan_fn, int warps, int ldz_s, int ldp_s, bool* taken) -> int {
+            *taken = false;
+            if (impl == 6 || ldz != ldz_s || ld_planes != ldp_s) return B200POSE_OK;
+            int slots = kSlots;
+            size_t smem_p = 0;
+            for (; slots >= 2; --slots) {
+                smem_p = (size_t)plan_fn(max_heads_per_frame, max_enodes_per_frame, slots).total_floats * sizeof(float);
+                if (smem_p <= 226 * 1024) break;
+            }
+            if (slots < 2) return B200POSE_OK;
+            *taken = true;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int grid = n_frames < sms ? n_frames : sms;
+            B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+            const uint32_t hint = 1000u;       // try_wait suspend hint [ns]; 0 .. 100000 measured the same
+            kern<<<grid, (warps + 2) * 32, smem_p, st>>>(p, max_heads_per_frame, max_enodes_per_frame, slots, hint);
+            B2_CHECK_LAUNCH();
+            return B200POSE_OK;
+        };
         bool taken = false;
         int rc = B200POSE_OK;
+        // consumer warps: one per head where the register file allows it (measured on 1024 Panoptic frames, 20 heads each:
+        // 16 warps x 2 heads 0.470 ms, 20 x 1 0.422 ms, 24 x 1 0.436 ms per step)
+        const bool w20 = max_heads_per_frame <= 20;
+        const bool w24 = !w20 && max_heads_per_frame <= 24;
+#define B2_TRY_SHAPE_P(HH, DD)                                                                                                      \
+        if (!taken && heads == HH && dim == DD) {                                                                                   \
+            using S_ = FrameShape<HH, DD>;                                                                                           \
+            if (w24) rc = layer0 ? launch_p(gat_aggregate_frame_p_kernel<HH, DD, true, 24, 1>, frame_plan_p<HH, DD, 24>, 24, S_::LDZ, S_::LDP, &taken)  \
+                                 : launch_p(gat_aggregate_frame_p_kernel<HH, DD, false, 24, 1>, frame_plan_p<HH, DD, 24>, 24, S_::LDZ, S_::LDP, &taken); \
+            else if (w20) rc = layer0 ? launch_p(gat_aggregate_frame_p_kernel<HH, DD, true, 20, 1>, frame_plan_p<HH, DD, 20>, 20, S_::LDZ, S_::LDP, &taken)  \
+                                 : launch_p(gat_aggregate_frame_p_kernel<HH, DD, false, 20, 1>, frame_plan_p<HH, DD, 20>, 20, S_::LDZ, S_::LDP, &taken); \
+            else rc = layer0 ? launch_p(gat_aggregate_frame_p_kernel<HH, DD, true, 16, 2>, frame_plan_p<HH, DD, 16>, 16, S_::LDZ, S_::LDP, &taken)      \
+                             : launch_p(gat_aggregate_frame_p_kernel<HH, DD, false, 16, 2>, frame_plan_p<HH, DD, 16>, 16, S_::LDZ, S_::LDP, &taken);     \
+            if (rc != B200POSE_OK) return rc;                                                                                        \
+        }
+        B2_TRY_SHAPE_P(10, 40)
+        B2_TRY_SHAPE_P(8, 40)
+        B2_TRY_SHAPE_P(5, 30)
+#undef B2_TRY_SHAPE_P
+        if (taken) return B200POSE_OK;
 #define B2_TRY_SHAPE(HH, DD)                                                                                                        \
         if (!taken && heads == HH && dim == DD) {                                                                                   \
             using S_ = FrameShape<HH, DD>;                                                                                           \
@@ -1504,13 +1885,13 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
             return launch_frame(gat_aggregate_frame_kernel<1, 4>);
         }
     }
-    if (impl == 3 || impl == 5) {
-        set_error("gat_aggregate: impl 3 / 5 (frame-resident kernels) need frames of at most %d heads whose plan fits in shared memory "
+    if (impl == 3 || impl == 5 || impl == 6) {
+        set_error("gat_aggregate: impl 3 / 5 / 6 (frame-resident kernels) need frames of at most %d heads whose plan fits in shared memory "
                   "(%d heads, %d edge-nodes per frame here)", kFrameOwn * kFrameWarps, max_heads_per_frame, max_enodes_per_frame);
         return B200POSE_E_UNSUPPORTED;
     }
     B2_CHECK_ARG(impl >= 0 && impl <= 2, "gat_aggregate: impl must be 0 (auto), 1 (gather kernel), 2 (large-frame kernel), 3 (frame-resident kernel, "
-                 "frames of at most 32 heads whose plan fits in shared memory) or 5 (its generic, not shape-specialised form)");
+                 "frames of at most 32 heads whose plan fits in shared memory) 5 (its generic, not shape-specialised form) or 6 (shape-specialised, one CTA per frame instead of persistent)");
     // ---- gather kernel: work unit = (frame, chunk of destination nodes). ---- In-degree of a head is 1 + H_b - n_g <= H_b and of an
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;

@@ -169,17 +169,17 @@ def test_aggregation_kernels_agree_bitwise(config):
     tags, pb, db = golden_batch(config)
     g = pipe.build_graph(db, with_coo=False)
     outs, finals = [], []
-    for impl in (3, 5, 1):              # 3 = frame-resident, shape-specialised where the shape is compiled in (a batch this small would
-        pipe.agg_impl = impl            # otherwise take the large-frame kernel); 5 = its generic form; 1 = gather kernel
+    for impl in (3, 6, 5, 1):           # 3 = frame-resident: persistent shape-specialised kernel where the shape is compiled in (a batch this
+        pipe.agg_impl = impl            # small would otherwise take the large-frame kernel); 6 = its one-CTA-per-frame form; 5 = generic; 1 = gather
         try:
             finals.append(pipe.gat_forward(db, g).cpu().numpy().copy())
             scores, raws = pipe.gat_forward(db, g, keep_layers=True)
         finally:
             pipe.agg_impl = 0
         outs.append([r.cpu().numpy() for r in raws] + [scores.cpu().numpy()])
-    for a, b, c in zip(*outs):
-        assert np.array_equal(a, b) and np.array_equal(a, c)
-    assert np.array_equal(finals[0], finals[1]) and np.array_equal(finals[0], finals[2])
+    for layer in zip(*outs):
+        assert all(np.array_equal(layer[0], x) for x in layer[1:])
+    assert all(np.array_equal(finals[0], x) for x in finals[1:])
     assert np.array_equal(finals[0], outs[0][-1])
 
 
@@ -736,3 +736,34 @@ def test_result_record_kernel_matches_host_packing():
     last = sharding.unpack_records(outs[-1], [F], Fcap, Pcap, cfg.n_cameras, 54)
     sk = res['person_sk'].cpu().numpy()
     assert np.array_equal(last['person_sk'], np.where(sk >= 0, sk + 4, sk))
+
+
+def test_persistent_aggregation_ragged_batch_bitwise():
+    """The persistent aggregation kernel walks several frames per CTA (more frames than SMs) with the table sets of
+    consecutive frames double-buffered: a ragged batch - 1 to 6 persons, missing views, frames without detections or with one
+    camera only in between - must give bit for bit the scores of the gather kernel and of the one-CTA-per-frame kernel."""
+    pipe = get_pipe('panoptic')
+    cfg = pipe.cfg
+    base = []
+    for i in range(61):
+        if i % 13 == 5:
+            base.append({})                                                 # no detections at all
+        elif i % 17 == 3:
+            base.append(helpers.synth.make_frame(cfg, 3000 + i, 3, camera_order=[i % 5]))      # one camera: heads but no edge-node
+        else:
+            base.append(helpers.synth.make_frame(cfg, 3000 + i, 1 + i % 6, drop_view_p=0.1 * (i % 4), drop_joint_p=0.05 * (i % 3)))
+    base = [{c: f[c] for c in f if json.loads(f[c][0])} for f in base]
+    pb = pack_mod.pack_frames(base, cfg, keep_json=False).tile(9)            # 549 frames: 3.7 per SM, uneven
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    g = pipe.build_graph(db, with_coo=False)
+    outs = []
+    for impl in (3, 6, 1):
+        pipe.agg_impl = impl
+        try:
+            outs.append(pipe.gat_forward(db, g).cpu().numpy().copy())
+        finally:
+            pipe.agg_impl = 0
+    assert np.isfinite(outs[0]).all()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    again = pipe.gat_forward(db, g).cpu().numpy()                          # the dispatch (549 frames: persistent kernel), run to run
+    assert np.array_equal(again, outs[0])
