@@ -233,5 +233,5 @@ def pack_frames_fast(frames: Sequence[Dict[str, list]], cfg: CameraConfig, keep_
             all_sk.append(f_sk); all_idx.append(f_idx)
         pb.skeletons, pb.skeleton_index = all_sk, all_idx
     else:
-        pb.skeletons = pb.skeleton_index = None
+        pb.skeletons = None                 # skeleton_index stays: it came with the packed arrays, no Python object was built for it
     return pb

@@ -84,6 +84,7 @@ class GAT2(nn.Module):
             self.__dict__['_plist'] = plist
         key = tuple((p.data_ptr(), p._version) for p in plist)
         if self._prepared is None or key != self._prepared_key:
+            rt.sync_live()
             self._prepared = ctx.prepare_gat({k: v for k, v in self.state_dict().items()})
             self._prepared_key = key
         return self._prepared
@@ -94,8 +95,23 @@ class GAT2(nn.Module):
         ctx = rt.context()
         if not hasattr(g, '_b200'):
             raise TypeError('GAT2.forward needs a graph built by the B200 graph_generator drop-in')
-        db, arrays = g._b200
         layers = self._weights(ctx)
+        # the whole-frame submissions of the dataset drop-in use these weights from now on - when the model is the shipped
+        # kind (the pipeline's activation constants) - and this call is answered from the submission of its own graph
+        P = rt.pipeline
+        shipped = (abs(self.alpha - P.GAT_ALPHA) < 1e-12 and abs(self.activation.negative_slope - P.GAT_ACT_SLOPE) < 1e-12
+                   and self.final_activation is not None)
+        if shipped:
+            rt.note_model('gat', self, self._prepared_key, layers)
+        lv = getattr(g, '_live', None)
+        if lv is not None and shipped and lv.fresh() and lv.key[0] == id(self) and lv.key[1] == self._prepared_key \
+                and dict.__contains__(g.ndata, 'h') and inputs.data_ptr() == g.ndata['h'].data_ptr():
+            out = lv.scores()
+            if out is not None:
+                lv.scores_ptr = out.data_ptr()
+                return out.reshape(-1, 1, 1)
+        rt.sync_live()
+        db, arrays = g._b200
         feats = g.ndata['h']
         if inputs.data_ptr() == feats.data_ptr() or (inputs.shape == feats.shape and inputs.device == feats.device
                                                      and torch.equal(inputs, feats)):

@@ -66,6 +66,87 @@ def _frame_to_device(frame, keep_json=True):
     return ctx, pb, rt.pipeline.HostBatch(pb).to_device(ctx.device)
 
 
+class _Lazy(dict):
+    """A dict whose values are produced on first access (the feature matrix of a live frame is 650 KB that the driver
+    loop only hands back to the model; the edge attributes are never read by it at all)."""
+
+    def __init__(self, factories):
+        dict.__init__(self)
+        self._factories = dict(factories)
+
+    def __missing__(self, key):
+        if key not in self._factories:
+            raise KeyError(key)
+        self[key] = v = self._factories[key]()
+        return v
+
+    def _all(self):
+        for k in self._factories:
+            self[k]
+        return self
+
+    def __contains__(self, key):
+        return key in self._factories or dict.__contains__(self, key)
+
+    def __iter__(self):
+        return dict.__iter__(self._all())
+
+    def __len__(self):
+        return dict.__len__(self._all())
+
+    def keys(self):
+        return dict.keys(self._all())
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+
+class LazyHeads(dict):
+    """`jsons_for_head` of a live frame: head id -> skeleton dict, parsed camera by camera when a head is asked for (the
+    packed arrays came from the native packer, so no Python object exists for a skeleton until the driver wants one)."""
+
+    def __init__(self, frame, head_cam, head_idx):
+        dict.__init__(self)
+        self._frame, self._head_cam, self._head_idx, self._parsed = frame, head_cam, head_idx, {}
+
+    def __missing__(self, head):
+        if not (0 <= head < len(self._head_cam)):
+            raise KeyError(head)
+        cam = self._head_cam[head]
+        lst = self._parsed.get(cam)
+        if lst is None:
+            payload = self._frame[cam][0]
+            lst = self._parsed[cam] = json.loads(payload) if isinstance(payload, str) else payload
+        self[head] = sk = lst[self._head_idx[head]]
+        return sk
+
+    def _all(self):
+        for h in range(len(self._head_cam)):
+            self[h]
+        return self
+
+    def __contains__(self, head):
+        return isinstance(head, int) and 0 <= head < len(self._head_cam)
+
+    def __iter__(self):
+        return dict.__iter__(self._all())
+
+    def __len__(self):
+        return len(self._head_cam)
+
+    def keys(self):
+        return dict.keys(self._all())
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+
 class B200Graph:
     """What `dgl.graph((src, dst), num_nodes, idtype=int32)` is to the reference's callers
     (graph_generator.py:867-870), backed by device tensors produced by b200pose_build_graph /
@@ -128,6 +209,81 @@ class B200Graph:
     @property
     def device(self):
         return self.ndata['h'].device
+
+
+class _LiveNodeData(_Lazy):
+    """ndata of a live frame: 'h' aliases the feature buffer of the frame's submission while that is the latest of its
+    shape, and is recomputed from the packed frame if somebody still reads it after the buffer was reused."""
+
+    def __init__(self, graph):
+        _Lazy.__init__(self, {'h': graph._features})
+        self._graph = graph
+        self._aliased = False
+
+    def __getitem__(self, key):
+        if key == 'h' and self._aliased and not self._graph._live.fresh():
+            dict.pop(self, 'h', None)
+            self._aliased = False
+        return _Lazy.__getitem__(self, key)
+
+
+class LiveGraph(B200Graph):
+    """The graph of a frame that was submitted as a whole (3d_multi_pose_estimator_b200/live.py): same interface, but the
+    feature matrix and the edge attributes are only materialised if somebody reads them, and `_live` lets GAT2 /
+    get_person_proposal_from_network_output / PoseEstimatorDataset / PoseEstimatorMLP answer from the submission."""
+
+    def __init__(self, handle, frame):
+        self._live = handle
+        self._frame = frame
+        pb = handle.pb
+        self._n, self._e = pb.n_nodes, pb.n_edges
+        self.batch_size = 1
+        self._node_shift = None
+        self._own = None
+        self.ndata = _LiveNodeData(self)
+        self.edata = _Lazy({'rel_type': self._rel_type, 'norm': self._norm})
+
+    @property
+    def _b200(self):
+        if self._live.fresh():
+            return self._live.ent.db, self._live.ent.arrays
+        if self._own is None:                                   # the submission's buffers have been reused: rebuild from the packed frame
+            ctx = rt.context()
+            rt.sync_live()
+            db = rt.pipeline.HostBatch(self._live.pb, pinned=False).to_device(ctx.device)
+            self._own = (db, ctx.build_graph(db, with_coo=True))
+        return self._own
+
+    def _features(self):
+        f = self._live.features()                               # materialised inside the submission (valid while it is the latest of its shape)
+        if f is not None:
+            self.ndata._aliased = True
+            return f
+        ctx = rt.context()
+        db, _ = self._b200
+        return ctx.node_features_f32(db)
+
+    def _rel_type(self):
+        H = self._live.pb.n_heads
+        rel = torch.ones(self._e, dtype=torch.int64, device=rt.context().device)
+        rel[:H] = 0
+        rel[H + 4::5] = 2
+        return rel
+
+    def _norm(self):
+        return torch.ones((self._e, 1), dtype=torch.float32, device=rt.context().device)
+
+    def edges(self):
+        if self._live.fresh():
+            torch.cuda.current_stream(rt.context().device).wait_event(self._live.ent.ev_a)
+        return B200Graph.edges(self)
+
+    def nodes(self):
+        return torch.arange(self._n, dtype=torch.int32, device=rt.context().device)
+
+    @property
+    def device(self):
+        return rt.context().device
 
 
 class HumanGraphFromView:
@@ -270,6 +426,25 @@ class MergedMultipleHumansDataset:
             if idx == self.limit:
                 break
             idx += 1
+            lv = rt.live() if type(json_view) is dict else None
+            if lv is not None:
+                # the models the driver runs are known: submit the whole frame (graph, GAT, clustering, encoder, MLP) now;
+                # the driver's later calls are answered from the submission
+                cfg = rt.config()
+                pb = rt.pack.pack_frames_fast([json_view], cfg, keep_json=False)
+                handle = lv.submit(pb) if pb.skeleton_index is not None else None
+                if handle is not None:
+                    head_cam = [cfg.camera_names[int(c)] for c in pb.sk_cam]
+                    handle.frame, handle.head_cam, handle.head_idx = json_view, head_cam, list(pb.skeleton_index[0])
+                    self.jsons_for_head = LazyHeads(json_view, head_cam, handle.head_idx)
+                    self.skeleton_index = dict(enumerate(handle.head_idx))
+                    H, N = pb.n_heads, pb.n_nodes
+                    self.graphs.append(LiveGraph(handle, json_view))
+                    self.labels.append(th.zeros((N - H, 1), dtype=th.float64))
+                    self.data['edge_nodes_indices'].append(th.arange(H, N, dtype=th.int64).unsqueeze(1))
+                    self.data['nodes_camera'].append(head_cam + [''] * (N - H))
+                    continue
+            rt.sync_live()
             ctx, pb, db = _frame_to_device(json_view)
             # like the reference, the head bookkeeping always reflects the last frame seen (:573-605)
             self.jsons_for_head = dict(enumerate(pb.skeletons[0]))

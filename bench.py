@@ -420,10 +420,11 @@ def main():
         p50_dict_ms = 1e3 * float(np.median(lat))
     # ---- the reference driver's own per-frame loop on the drop-in modules (JSON strings in, python dicts out):
     # what an unmodified test/metrics_from_model.py gets with the shadow directory first on sys.path (rank 0 only)
-    dropin_fps = None
+    dropin_fps = dropin_detail = None
     if rank == 0 and args.latency_frames > 0:
         try:
-            dropin_fps = dropin_driver_loop(cfg, frames[:48], gat, mlp)
+            dropin_detail = dropin_driver_loop(cfg, frames[:48], gat, mlp)
+            dropin_fps = dropin_detail['frames_per_s']
         except Exception as e:                                  # an extra line of the report, never the reason a bench fails
             dropin_fps = 'failed: %s' % e
     # ---- host-side ingest: the native JSON packer on the text of 512 of these frames (all host threads; rank 0 only)
@@ -508,7 +509,7 @@ def main():
                                                                      'the end of the job', 'tail_ms': tail_ms, 'verified': gather_ok,
                                                              'bytes_per_rank_and_step': 4 * sharding.record_words(args.frames, P_cap, cfg.n_cameras, n_out)},
                 'persons_found_per_frame': P / args.frames,
-                'dropin_driver_loop_frames_per_s': dropin_fps, 'json_pack_frames_per_s': json_fps,
+                'dropin_driver_loop_frames_per_s': dropin_fps, 'dropin_driver_loop': dropin_detail, 'json_pack_frames_per_s': json_fps,
                 'p50_frame_latency_ms': p50_ms, 'p99_frame_latency_ms': p99_ms, 'p50_frame_latency_eager_ms': p50_eager_ms,
                 'p50_frame_latency_from_dict_ms': p50_dict_ms,
                 'latency_note': 'one frame per call, host buffers in / host results out: infer_host_graph (CUDA graph per batch '
@@ -762,33 +763,17 @@ def _timed(fn):
 
 
 def dropin_driver_loop(cfg, frames, gat_state, mlp_state):
-    """frames/s of the loop body of the reference's test/metrics_from_model.py:178-300, one frame at a time, written against
-    the drop-in modules under their reference names (tests/test_dropin_gpu.run_frame is that loop body)."""
-    import contextlib
-    import io
-    import torch
+    """The loop body of the reference's test/metrics_from_model.py:178-300, one frame at a time, on the drop-in modules under
+    their reference names (scripts/dropin_steps.py times every step): frames/s, and how much of a frame is the driver script's
+    own Python (JSON re-encoding per camera and per person, its host<->device copies) against the drop-in modules' share."""
+    sys.path.insert(0, os.path.join(REPO, 'scripts'))
     sys.path.insert(0, os.path.join(REPO, 'tests'))
-    with contextlib.redirect_stdout(io.StringIO()):             # the reference's modules print while they work; stdout is the JSON line's
-        import dropin_env
-        from test_dropin_gpu import run_frame
-        mods = dropin_env.activate(cfg)
-        dev = torch.device('cuda')
-        model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
-                                  torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
-        model.load_state_dict(gat_state)
-        model = model.to(dev)
-        mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.mlp_in, output_dimensions=54)
-        mlp.load_state_dict(mlp_state)
-        mlp = mlp.to(dev)
-        for f in frames[:8]:
-            run_frame(mods, cfg, model, mlp, f)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for f in frames:
-            run_frame(mods, cfg, model, mlp, f)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    return len(frames) / dt
+    import dropin_steps
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    full = [synth.make_frame(cfg, 50000 + i, max(1, len(json.loads(next(iter(f.values()))[0])))) for i, f in enumerate(frames)]
+    r = dropin_steps.measure(cfg, full, gat_state, mlp_state)
+    r.pop('steps')
+    return r
 
 
 def profile_classes(pipe, db, pm, torch):

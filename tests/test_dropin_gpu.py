@@ -153,3 +153,74 @@ def test_proposals_accept_python_lists_and_custom_threshold():
     hg = mods['graph_generator'].HumanGraphFromView(scenario.jsons_for_head[0], scenario.data['nodes_camera'][0][0], '3')
     assert hg.n_nodes == 1 and hg.src_nodes == [0] and hg.num_joints == len(scenario.jsons_for_head[0])
     assert np.array_equal(hg.features.cpu().numpy()[0], npz[tag + '/feats'][0])
+
+
+def test_live_frames_fall_back_when_the_submission_cannot_answer():
+    """The whole-frame submissions behind the drop-in modules (live.py) must never answer a call they do not match: a graph
+    whose submission was overtaken by the next frame of the same shape, another threshold, scores that are not the
+    submission's, a person that is not a proposal, changed weights - each takes the eager path and still gives the
+    reference's result."""
+    config = 'panoptic'
+    cfg, npz, meta = helpers.load_golden(config)
+    mods = dropin_env.activate(cfg)
+    rt = mods['rt']
+    gat_state, mlp_state = helpers.golden_weights(config)
+    device = torch.device('cuda')
+    model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(),
+                              torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
+    model.load_state_dict(gat_state)
+    model = model.to(device)
+    mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=meta['mlp_in_dim'], output_dimensions=54)
+    mlp.load_state_dict(mlp_state)
+    mlp = mlp.to(device)
+    names = cfg.used_sm_names
+    arr = lambda fo: np.array([[-1 if p[c] is None else p[c] for c in names] for p in fo], dtype=np.int32).reshape(-1, len(names))
+    for tag in ('p4a', 'p4b'):                                   # first frames: eager, they tell the runtime which models run
+        run_frame(mods, cfg, model, mlp, meta['frames'][tag])
+    assert rt.live() is not None
+    gg, smu = mods['graph_generator'], mods['skeleton_matching_utils']
+    fa = {c: [v[0], v[1]] for c, v in meta['frames']['p4a'].items()}
+    fb = {c: [v[0], v[1]] for c, v in meta['frames']['p4b'].items()}          # same shape as p4a: reuses its graphs
+    sa = gg.MergedMultipleHumansDataset(fa, mode='test', alt='3', debug=True, verbose=False)
+    ga = sa.graphs[0]
+    assert hasattr(ga, '_live') and ga._live.fresh()
+    feats_a = ga.ndata['h']
+    sb = gg.MergedMultipleHumansDataset(fb, mode='test', alt='3', debug=True, verbose=False)
+    assert not ga._live.fresh() and sb.graphs[0]._live.fresh()
+    # the overtaken graph still gives its own frame's features, scores and proposals
+    assert np.array_equal(ga.ndata['h'].cpu().numpy(), npz['p4a/feats'])
+    out_a = torch.squeeze(model(ga.ndata['h'].float(), ga))
+    idx = npz['p4a/indices']
+    ref = npz['p4a/scores']
+    assert (np.abs(out_a.cpu().numpy()[idx] - ref[idx]) / np.abs(ref[idx])).max() <= 1e-4
+    pa = smu.get_person_proposal_from_network_output(out_a, ga, None, sa.data['nodes_camera'][0], sa.jsons_for_head, 0.5)
+    assert np.array_equal(arr(pa), npz['p4a/proposals'])
+    # the fresh one answers from its submission; another threshold or foreign scores do not
+    gb = sb.graphs[0]
+    out_b = torch.squeeze(model(gb.ndata['h'].float(), gb))
+    pb_ = smu.get_person_proposal_from_network_output(out_b, gb, None, sb.data['nodes_camera'][0], sb.jsons_for_head, 0.5)
+    assert np.array_equal(arr(pb_), npz['p4b/proposals'])
+    assert smu.get_person_proposal_from_network_output(out_b, gb, None, sb.data['nodes_camera'][0], None, 1.5) == []
+    fuzz = torch.from_numpy(npz['fuzz/1/scores']).cuda() if meta['fuzz_tags'][1] == 'p4b' else None
+    other = torch.from_numpy(npz['p4b/scores']).cuda()
+    po = smu.get_person_proposal_from_network_output(other, gb, None, sb.data['nodes_camera'][0], None, 0.5)
+    assert np.array_equal(arr(po), npz['p4b/proposals'])
+    # a person that is not one of the proposals (heads 0 and 5 of two cameras, whatever the clustering said): encoded eagerly
+    ds = mods['pose_estimator_dataset_from_json']
+    h0, h1 = 0, next(h for h, c in enumerate(sb.data['nodes_camera'][0]) if c != sb.data['nodes_camera'][0][0])
+    raw = {sb.data['nodes_camera'][0][h0]: [json.dumps([sb.jsons_for_head[h0]])],
+           sb.data['nodes_camera'][0][h1]: [json.dumps([sb.jsons_for_head[h1]])]}
+    row = ds.PoseEstimatorDataset(raw, list(range(cfg.n_cameras)), list(range(18)), save=False)[0][0]
+    import importlib
+    O = importlib.import_module('oracle.pose_oracle')
+    want = O.encode_person({c: json.loads(v[0])[0] for c, v in raw.items()}, O.CameraTables(cfg))
+    assert np.abs(row.cpu().numpy() - want).max() <= 1e-6
+    # changed weights: the next frame is eager again and correct for the NEW weights
+    with torch.no_grad():
+        model.layers[4].fc2.bias.add_(0.25)
+    sc = gg.MergedMultipleHumansDataset(fa, mode='test', alt='3', debug=True, verbose=False)
+    out_c = torch.squeeze(model(sc.graphs[0].ndata['h'].float(), sc.graphs[0])).cpu().numpy()
+    gat_np = helpers.np_state(gat_state)
+    gat_np['layers.4.fc2.bias'] = gat_np['layers.4.fc2.bias'] + np.float32(0.25)
+    ref_c = O.gat_forward(gat_np, npz['p4a/feats'], npz['p4a/src'], npz['p4a/dst'])
+    assert (np.abs(out_c[idx] - ref_c[idx]) / np.abs(ref_c[idx])).max() <= 1e-4
