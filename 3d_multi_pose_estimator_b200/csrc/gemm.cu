@@ -311,7 +311,7 @@ struct GemmParams2 {
     int dbg;                                 // kernel bring-up switches (b200pose_set_debug): 1 = no stores, 2 = hi*hi only, 4 = no epilogue math
 };
 
-struct TileInfo { int m0, n0, bn; };
+struct TileInfo { int m0, n0, bn, n_eff; };   // n_eff: the tile's valid width rounded up to the MMA granule (16) - what is actually multiplied
 // Tile walk of one CTA (or CTA pair). Work is dealt out in "visits": visit s covers group_n consecutive
 // n-tiles of one m-tile, and worker c takes visits c, c + workers, ... With group_n == tiles_n (tall GEMMs:
 // many m-tiles) a worker sweeps every n-tile of an m-tile back to back, so the A tile is fetched from HBM once
@@ -344,6 +344,9 @@ __device__ __forceinline__ TileInfo tile_info(const GemmParams2& p, int tile) {
     t.m0 = mb * kBM * NCTA;
     t.n0 = 64 * (nb * base + min(nb, rem));
     t.bn = 64 * (base + (nb < rem ? 1 : 0));
+    // the last n-tile of a projection whose width is not a multiple of 64 (400, 420, 336, 160, 150 ...): columns past
+    // round_up(N, 16) are K-padding zeros times anything - not issued (N = 400: 144 instead of 192 columns, -11 % MMA work)
+    t.n_eff = min(t.bn, ((p.N - t.n0 + 15) >> 4) << 4);
     return t;
 }
 
@@ -451,8 +454,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
             int it = 0;
             for (TileWalk<NCTA> w(p); w.valid(); w.next(p)) {
                 const TileInfo t = tile_info<NCTA>(p, w.tile(p));
-                const int b_rows = t.bn / NCTA;                               // this CTA's share of the W tile
-                const int m_cta = t.m0 + (int)rank * kBM, n_cta = t.n0 + (int)rank * b_rows;
+                const int b_rows = t.bn / NCTA;                               // rows of the box this CTA loads per stage
+                // this CTA's share of the W tile starts at its half of the columns that are multiplied (n_eff), not of the box
+                const int m_cta = t.m0 + (int)rank * kBM, n_cta = t.n0 + (int)rank * (t.n_eff / NCTA);
                 const uint32_t tx = NCTA * (2 * a_bytes + 2 * (uint32_t)b_rows * kBK * 2);   // bytes landing for the whole pair
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
             int it = 0, i = 0;
             for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
                 const TileInfo t = tile_info<NCTA>(p, w.tile(p));
-                const uint32_t idesc = make_idesc_n<NCTA>(t.bn);
+                const uint32_t idesc = make_idesc_n<NCTA>(t.n_eff);
                 const int a = i & 1;
                 mbar_wait(smem_u32(&bar_acc_empty[a]), ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
