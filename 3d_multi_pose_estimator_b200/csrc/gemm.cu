@@ -308,6 +308,7 @@ struct GemmParams2 {
     int stages, stage_bn;                    // pipeline depth, widest tile (smem / TMEM sizing)
     const float* bias; float slope, out_scale;
     int has_f32, has_planes;
+    const int* m_dev;                        // when set: the number of valid rows lives on the device (M is then the capacity the maps were made for)
     int dbg;                                 // kernel bring-up switches (b200pose_set_debug): 1 = no stores, 2 = hi*hi only, 4 = no epilogue math
 };
 
@@ -320,9 +321,9 @@ struct TileInfo { int m0, n0, bn, n_eff; };   // n_eff: the tile's valid width r
 template <int NCTA>
 struct TileWalk {
     int visit, j, groups_per_m, total_visits;
-    __device__ __forceinline__ TileWalk(const GemmParams2& p) {
+    __device__ __forceinline__ TileWalk(const GemmParams2& p, int tiles_m) {
         groups_per_m = (p.tiles_n + p.group_n - 1) / p.group_n;
-        total_visits = p.tiles_m * groups_per_m;
+        total_visits = tiles_m * groups_per_m;
         visit = blockIdx.x / NCTA; j = 0;
     }
     __device__ __forceinline__ bool valid() const { return visit < total_visits; }
@@ -422,6 +423,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rows to compute: the host's count, or - launched for a capacity - the count a previous kernel left on the device
+    const int M_rows = p.m_dev ? min(p.M, __ldg(p.m_dev)) : p.M;
+    const int tiles_m = p.m_dev ? (M_rows + kBM * NCTA - 1) / (kBM * NCTA) : p.tiles_m;
     const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const uint32_t a_bytes = kBM * kBK * 2;                                  // 16 KB per plane (this CTA's 128 rows)
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         // ================= TMA producer (every CTA loads its own operand halves) =================
         if (lane == 0) {
             int it = 0;
-            for (TileWalk<NCTA> w(p); w.valid(); w.next(p)) {
+            for (TileWalk<NCTA> w(p, tiles_m); w.valid(); w.next(p)) {
                 const TileInfo t = tile_info<NCTA>(p, w.tile(p));
                 const int b_rows = t.bn / NCTA;                               // rows of the box this CTA loads per stage
                 // this CTA's share of the W tile starts at its half of the columns that are multiplied (n_eff), not of the box
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         // ================= MMA issuer (leader CTA only when paired) =================
         if (lane == 0 && leader) {
             int it = 0, i = 0;
-            for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
+            for (TileWalk<NCTA> w(p, tiles_m); w.valid(); w.next(p), ++i) {
                 const TileInfo t = tile_info<NCTA>(p, w.tile(p));
                 const uint32_t idesc = make_idesc_n<NCTA>(t.n_eff);
                 const int a = i & 1;
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
         bool stores_pending = false;
         const bool slope_le1 = p.slope >= 0.f && p.slope <= 1.f;
         const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
-        for (TileWalk<NCTA> w(p); w.valid(); w.next(p), ++i) {
+        for (TileWalk<NCTA> w(p, tiles_m); w.valid(); w.next(p), ++i) {
             const TileInfo t = tile_info<NCTA>(p, w.tile(p));
             const int a = i & 1;
             mbar_wait(smem_u32(&bar_acc_full[a]), (uint32_t)(i >> 1) & 1u);
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                 __syncwarp();
                 if (lane == 0) {
                     const int row0 = t.m0 + (int)rank * kBM + q * 32;
-                    if (row0 < p.M && !(p.dbg & 1)) {
+                    if (row0 < M_rows && !(p.dbg & 1)) {
                         if (p.has_f32) {
                             if (col0 < p.N) tma_store_2d(&map_o_f32, stage_f32, col0, row0);
                             if (col0 + 32 < p.N) tma_store_2d(&map_o_f32, stage_f32 + 4096u, col0 + 32, row0);
@@ -1283,13 +1287,14 @@ static int choose_bn(int n) {
 using namespace b200pose;
 
 
-extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
-                               const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
-                               const float* bias, int32_t m, int32_t n, int32_t k, float slope, float out_scale,
-                               float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
-                               int32_t impl, void* stream)
+static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                       const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                       const float* bias, int32_t m, const int32_t* m_dev, int32_t n, int32_t k, float slope, float out_scale,
+                       float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                       int32_t impl, void* stream)
 {
     B2_CHECK_ARG(a_hi && a_lo && w_hi && w_lo, "linear: null operand");
+    if (m_dev) B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5, "linear_n: only the persistent kernels read the row count from the device");
     B2_CHECK_ARG(m >= 0 && n >= 1 && k >= 1, "linear: bad shape m=%d n=%d k=%d", m, n, k);
     const int kpad = ceil_div(k, kBK) * kBK;
     B2_CHECK_ARG(lda % 64 == 0 && ldw % 64 == 0 && lda >= kpad && ldw >= kpad, "linear: lda/ldw must be multiples of 64 >= round_up(k,64)");
@@ -1350,7 +1355,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         return B200POSE_E_UNSUPPORTED;
     }
 #endif
-    if ((impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
+    if (!m_dev && (impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight stream with A in registers: k split over the CTA's lanes, blocks of 32 / MMAX columns
         const int warps = ceil_div(kpad, 256);
         const int cols = out_hi ? ld_planes : n;
@@ -1365,7 +1370,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         };
         return m <= 4 ? launch_stream(gemm_stream_kernel<4>, 8) : launch_stream(gemm_stream_kernel<8>, 4);
     }
-    if ((impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
+    if (!m_dev && (impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight-streaming small-M kernel: as many CTAs as fit at once (the A staging is per CTA), every warp takes columns
         const size_t smem = (size_t)m * kpad * sizeof(float);
         const int cols = out_hi ? ld_planes : n;
@@ -1392,7 +1397,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
     const int ncta = (impl == 5 || impl == 6) ? 2 : (impl == 4) ? 1 : (m > 4 * kBM ? 2 : 1);
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.k_last = ceil_div(k - (kpad / kBK - 1) * kBK, kUmmaK); q.bias = bias; q.slope = slope; q.out_scale = out_scale;
-    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags;
+    q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags; q.m_dev = m_dev;
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo;
@@ -1476,4 +1481,23 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint
         B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_tc2_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo, q));
     }
     return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                               const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                               const float* bias, int32_t m, int32_t n, int32_t k, float slope, float out_scale,
+                               float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                               int32_t impl, void* stream)
+{
+    return linear_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, m, nullptr, n, k, slope, out_scale, out_f32, ld_out, out_hi, out_lo, ld_planes, impl, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_linear_n(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                                 const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                                 const float* bias, int32_t m_capacity, const int32_t* m_dev, int32_t n, int32_t k, float slope, float out_scale,
+                                 float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                                 int32_t impl, void* stream)
+{
+    B2_CHECK_ARG(m_dev, "linear_n: null row-count pointer");
+    return linear_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, m_capacity, m_dev, n, k, slope, out_scale, out_f32, ld_out, out_hi, out_lo, ld_planes, impl, stream);
 }

@@ -233,11 +233,12 @@ __global__ void __launch_bounds__(kLiftThreads) lift_person_kernel(
     int n_persons, const int* __restrict__ person_sk, const double* __restrict__ sk_xy, const float* __restrict__ sk_vp,
     const uint32_t* __restrict__ sk_mask, LiftTables t, int n_slots, int median_axis,
     float* __restrict__ x_f32, int ld_f32, __nv_bfloat16* __restrict__ x_hi, __nv_bfloat16* __restrict__ x_lo, int ld_planes,
-    uint8_t* __restrict__ valid, double* __restrict__ xyz, uint8_t* __restrict__ mask)
+    uint8_t* __restrict__ valid, double* __restrict__ xyz, uint8_t* __restrict__ mask, const int* __restrict__ n_dev)
 {
     extern __shared__ __align__(16) unsigned char lift_raw[];
     __shared__ float red[kLiftThreads / 32];
     const int person = blockIdx.x;
+    if (n_dev && person >= __ldg(n_dev)) return;            // launched for a capacity: the real count lives on the device
     const int tid = threadIdx.x;
     const int C = t.n_cameras;
     const int row_len = ENCODE ? kJ * 14 * n_slots : 0;
@@ -430,10 +431,10 @@ static LiftTables make_tables(const b200pose_cameras* cams) {
     return t;
 }
 
-extern "C" __attribute__((visibility("default"))) int b200pose_encode_persons(int32_t n_persons, const int32_t* person_sk, const double* sk_xy, const float* sk_vp,
-                                       const uint32_t* sk_mask, const b200pose_cameras* cams,
-                                       float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
-                                       uint8_t* valid, void* stream)
+static int encode_persons_impl(int32_t n_persons, const int32_t* n_persons_dev, const int32_t* person_sk, const double* sk_xy, const float* sk_vp,
+                               const uint32_t* sk_mask, const b200pose_cameras* cams,
+                               float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
+                               uint8_t* valid, void* stream)
 {
     B2_CHECK_ARG(person_sk && sk_xy && sk_vp && sk_mask && cams, "encode_persons: null input");
     B2_CHECK_ARG(cams->n_cameras <= B200POSE_MAX_CAMERAS, "encode_persons: too many cameras");
@@ -446,9 +447,26 @@ extern "C" __attribute__((visibility("default"))) int b200pose_encode_persons(in
     B2_CHECK_CUDA(cudaFuncSetAttribute(lift_person_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     lift_person_kernel<true><<<n_persons, kLiftThreads, L.total, (cudaStream_t)stream>>>(
         n_persons, person_sk, sk_xy, sk_vp, sk_mask, make_tables(cams), cams->v_pe, 0, x_f32, ld_f32,
-        reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), ld_planes, valid, nullptr, nullptr);
+        reinterpret_cast<__nv_bfloat16*>(x_hi), reinterpret_cast<__nv_bfloat16*>(x_lo), ld_planes, valid, nullptr, nullptr, n_persons_dev);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_encode_persons(int32_t n_persons, const int32_t* person_sk, const double* sk_xy, const float* sk_vp,
+                                       const uint32_t* sk_mask, const b200pose_cameras* cams,
+                                       float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
+                                       uint8_t* valid, void* stream)
+{
+    return encode_persons_impl(n_persons, nullptr, person_sk, sk_xy, sk_vp, sk_mask, cams, x_f32, ld_f32, x_hi, x_lo, ld_planes, valid, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_encode_persons_n(int32_t capacity, const int32_t* n_persons_dev, const int32_t* person_sk,
+                                         const double* sk_xy, const float* sk_vp, const uint32_t* sk_mask, const b200pose_cameras* cams,
+                                         float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
+                                         uint8_t* valid, void* stream)
+{
+    B2_CHECK_ARG(n_persons_dev, "encode_persons_n: null count pointer");
+    return encode_persons_impl(capacity, n_persons_dev, person_sk, sk_xy, sk_vp, sk_mask, cams, x_f32, ld_f32, x_hi, x_lo, ld_planes, valid, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int b200pose_triangulate(int32_t n_persons, const int32_t* person_sk, const double* sk_xy,
@@ -463,7 +481,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_triangulate(int32
     B2_CHECK_CUDA(cudaFuncSetAttribute(lift_person_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     lift_person_kernel<false><<<n_persons, kLiftThreads, L.total, (cudaStream_t)stream>>>(
         n_persons, person_sk, sk_xy, nullptr, sk_mask, make_tables(cams), cams->n_cameras, median_axis, nullptr, 0,
-        nullptr, nullptr, 0, nullptr, xyz, mask);
+        nullptr, nullptr, 0, nullptr, xyz, mask, nullptr);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

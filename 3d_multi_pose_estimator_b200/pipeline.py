@@ -337,12 +337,18 @@ class PosePipeline:
 
     # ------------------------------------------------------------------ kernels
     def linear(self, a: Planes, m: int, w: Planes, bias, n: int, k: int, slope: float, scale: float = 1.0,
-               out_f32: Optional[torch.Tensor] = None, out_planes: Optional[Planes] = None):
+               out_f32: Optional[torch.Tensor] = None, out_planes: Optional[Planes] = None, m_dev: Optional[torch.Tensor] = None):
+        """out = act(A W^T + b). With `m_dev` (an int32 device scalar) `m` is only the capacity of the buffers: the kernel reads
+        the number of valid rows from the device, so no host round trip is needed to size the launch."""
         self.launches += 1
-        check(self.L.b200pose_linear(ptr(a.hi), ptr(a.lo), a.ld, ptr(w.hi), ptr(w.lo), w.ld, ptr(bias), m, n, k,
-                                     slope, scale, ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-                                     ptr(out_planes.hi) if out_planes else None, ptr(out_planes.lo) if out_planes else None,
-                                     out_planes.ld if out_planes else 0, self.gemm_impl, self._stream()), 'linear')
+        tail = (ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                ptr(out_planes.hi) if out_planes else None, ptr(out_planes.lo) if out_planes else None,
+                out_planes.ld if out_planes else 0, self.gemm_impl, self._stream())
+        if m_dev is None:
+            check(self.L.b200pose_linear(ptr(a.hi), ptr(a.lo), a.ld, ptr(w.hi), ptr(w.lo), w.ld, ptr(bias), m, n, k, slope, scale, *tail), 'linear')
+        else:
+            check(self.L.b200pose_linear_n(ptr(a.hi), ptr(a.lo), a.ld, ptr(w.hi), ptr(w.lo), w.ld, ptr(bias), m, ptr(m_dev), n, k, slope, scale,
+                                           *tail), 'linear_n')
 
     def build_graph(self, db: DeviceBatch, with_coo=True) -> GraphArrays:
         g = GraphArrays(db, self.device, with_coo)
@@ -458,14 +464,19 @@ class PosePipeline:
                                              self._stream()), 'gather_persons')
         return P, person_off, person_sk[:P], person_frame[:P]
 
-    def encode_persons(self, db: DeviceBatch, P: int, person_sk, want_f32=False):
+    def encode_persons(self, db: DeviceBatch, P: int, person_sk, want_f32=False, n_dev: Optional[torch.Tensor] = None):
+        """MLP input rows of P persons. With `n_dev` (int32 device scalar) P is a capacity and the kernel handles the
+        persons the device-side count names."""
         x = self.planes_ws('mlp_x', P, self.cfg.mlp_in)
         valid = torch.empty(max(P, 1), dtype=torch.uint8, device=self.device)
         xf = torch.zeros((max(P, 1), self.cfg.mlp_in), dtype=torch.float32, device=self.device) if want_f32 else None
         self.launches += 1
-        check(self.L.b200pose_encode_persons(P, ptr(person_sk), ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), self.cams.ref,
-                                             ptr(xf), self.cfg.mlp_in if want_f32 else 0, ptr(x.hi), ptr(x.lo), x.ld, ptr(valid),
-                                             self._stream()), 'encode_persons')
+        args = (ptr(person_sk), ptr(db.sk_xy), ptr(db.sk_vp), ptr(db.sk_mask), self.cams.ref,
+                ptr(xf), self.cfg.mlp_in if want_f32 else 0, ptr(x.hi), ptr(x.lo), x.ld, ptr(valid), self._stream())
+        if n_dev is None:
+            check(self.L.b200pose_encode_persons(P, *args), 'encode_persons')
+        else:
+            check(self.L.b200pose_encode_persons_n(P, ptr(n_dev), *args), 'encode_persons_n')
         return x, valid[:P], (xf[:P] if want_f32 else None)
 
     def triangulate(self, db: DeviceBatch, P: int, person_sk):
@@ -538,7 +549,8 @@ class PosePipeline:
                                           ptr(xyz), ptr(mask), self._stream()), 'triangulate')
         return xyz[0].cpu().numpy(), mask[0].cpu().numpy()
 
-    def mlp_forward(self, x: Planes, P: int, scale: float = 10.0, layers=None, slope: float = MLP_SLOPE) -> torch.Tensor:
+    def mlp_forward(self, x: Planes, P: int, scale: float = 10.0, layers=None, slope: float = MLP_SLOPE,
+                    m_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
         """PoseEstimatorMLP.forward (utils/mlp.py:8-31); `scale` is the x10 the callers apply
         (metrics_from_model.py:282), fused into the last epilogue."""
         layers = layers if layers is not None else self.mlp
@@ -547,7 +559,7 @@ class PosePipeline:
         # A live frame's handful of persons: the layers are weight streams (116 MB for 9 layers), served by the kernel that
         # keeps up to 8 rows of A in registers; 9..32 rows go through it 8 at a time - the second pass over a layer's
         # weights (at most 38 MB) comes out of L2
-        chunks = [(0, P)] if P <= 8 or P > 32 else [(r, min(r + 8, P)) for r in range(0, P, 8)]
+        chunks = [(0, P)] if P <= 8 or P > 32 or m_dev is not None else [(r, min(r + 8, P)) for r in range(0, P, 8)]
 
         def rows(pl: Planes, r0, r1):
             v = Planes.__new__(Planes)
@@ -559,10 +571,10 @@ class PosePipeline:
             for r0, r1 in chunks:
                 xi = x if len(chunks) == 1 else rows(x, r0, r1)
                 if last:
-                    self.linear(xi, r1 - r0, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out[r0:r1])
+                    self.linear(xi, r1 - r0, lay['w'], lay['b'], lay['n'], lay['k'], 1.0, scale, out_f32=out[r0:r1], m_dev=m_dev)
                 else:
                     self.linear(xi, r1 - r0, lay['w'], lay['b'], lay['n'], lay['k'], slope,
-                                out_planes=y if len(chunks) == 1 else rows(y, r0, r1))
+                                out_planes=y if len(chunks) == 1 else rows(y, r0, r1), m_dev=m_dev)
             x = y
         return out[:P, :n_out]
 
@@ -609,10 +621,43 @@ class PosePipeline:
             res['tri_xyz'], res['tri_mask'] = self.triangulate(db, P, res['person_sk'])
         return res
 
+    def stage_b_nosync(self, db: DeviceBatch, res: dict):
+        """Stage 3 enqueued without reading the person count back: person list, encoder and MLP are launched for the
+        capacity heads // min_number_of_views and take the real count from the device (person_off[B], written by the scan
+        of stage 2). Outputs are capacity-sized; `res['n_persons_dev']` is the count (an int32 device scalar) and
+        person_count(res) reads it when the host finally wants it."""
+        if db.n_heads == 0 or self.mlp is None:
+            return self.stage_b(db, res)
+        cap = person_capacity(db.n_heads, self.cfg.min_number_of_views)
+        Cn = self.cfg.n_cameras
+        person_sk = torch.empty((cap, Cn), dtype=torch.int32, device=self.device)
+        person_frame = torch.empty(cap, dtype=torch.int32, device=self.device)
+        self.launches += 1
+        check(self.L.b200pose_gather_persons(db.n_frames, ptr(db.head_off), ptr(res['person_heads']), ptr(res['n_persons']),
+                                             ptr(res['person_off']), 0, ptr(db.sk_cam), self.cfg.V_sm, self.cams.ref,
+                                             ptr(person_sk), ptr(person_frame), self._stream()), 'gather_persons')
+        n_dev = res['person_off'][db.n_frames:db.n_frames + 1]
+        x, valid, _ = self.encode_persons(db, cap, person_sk, n_dev=n_dev)
+        joints = self.mlp_forward(x, cap, m_dev=n_dev)
+        res.update(person_sk=person_sk, person_frame=person_frame, valid=valid, joints=joints, n_persons_dev=n_dev, n_persons_total=None)
+        return res
+
+    @staticmethod
+    def person_count(res: dict) -> int:
+        """Number of persons of a result (reads the device-side count of a sync-free step once)."""
+        if res.get('n_persons_total') is None:
+            res['n_persons_total'] = int(res['n_persons_dev'].item())
+        return res['n_persons_total']
+
     @_on_own_device
-    def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False):
-        """graph build -> GAT -> clustering -> encoder -> MLP for every frame of a batch resident in HBM."""
-        return self.stage_b(db, self.stage_a(db, with_coo=with_coo), want_triangulation=want_triangulation)
+    def infer(self, db: DeviceBatch, with_coo: bool = False, want_triangulation: bool = False, sync: bool = True):
+        """graph build -> GAT -> clustering -> encoder -> MLP for every frame of a batch resident in HBM. sync=False enqueues
+        the whole step without a host round trip (stage_b_nosync): the rows of person_sk / joints / valid past
+        person_count(res) are unspecified."""
+        res = self.stage_a(db, with_coo=with_coo)
+        if not sync and not want_triangulation:
+            return self.stage_b_nosync(db, res)
+        return self.stage_b(db, res, want_triangulation=want_triangulation)
 
     @_on_own_device
     def infer_host(self, hb: HostBatch, n_chunks: int = 1):

@@ -138,6 +138,14 @@ int b200pose_linear(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                     float* out_f32, int32_t ld_out,
                     uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
                     int32_t impl, void* stream);
+/* b200pose_linear for a CAPACITY of rows (the buffers and tensor maps cover m_capacity rows) with the number of valid
+ * rows read from the device when the kernel starts: m-tiles past it are not computed. */
+int b200pose_linear_n(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                      const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
+                      const float* bias, int32_t m_capacity, const int32_t* m_dev, int32_t n, int32_t k,
+                      float slope, float out_scale,
+                      float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
+                      int32_t impl, void* stream);
 
 /* Kernel bring-up switches for the persistent GEMM (results become WRONG; used by scripts/gemm_probe.py to attribute time):
  * bit 0 = skip the output stores, bit 1 = issue only the hi*hi MMA, bit 2 = skip the epilogue arithmetic. Returns the old value. */
@@ -210,6 +218,14 @@ int b200pose_encode_persons(int32_t n_persons, const int32_t* person_sk,
                             const b200pose_cameras* cams_host,
                             float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
                             uint8_t* valid, void* stream);
+/* The same, launched for a CAPACITY of persons with the real count left on the device by the previous stage
+ * (person_off[B] of b200pose_gather_persons): rows >= *n_persons_dev are not touched. Lets a whole step be enqueued
+ * without the host reading the person count back (the reference has no counterpart: it is one frame at a time). */
+int b200pose_encode_persons_n(int32_t capacity, const int32_t* n_persons_dev, const int32_t* person_sk,
+                              const double* sk_xy, const float* sk_vp, const uint32_t* sk_mask,
+                              const b200pose_cameras* cams_host,
+                              float* x_f32, int32_t ld_f32, uint16_t* x_hi, uint16_t* x_lo, int32_t ld_planes,
+                              uint8_t* valid, void* stream);
 
 /* Stage 3b. Triangulation baseline: triangulate() (utils/pose_estimator_utils.py:52-75) fed as
  * test/metrics_from_triangulation.py:237-249 does (all present joints, camera order = camera index):

@@ -767,3 +767,26 @@ def test_persistent_aggregation_ragged_batch_bitwise():
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     again = pipe.gat_forward(db, g).cpu().numpy()                          # the dispatch (549 frames: persistent kernel), run to run
     assert np.array_equal(again, outs[0])
+
+
+def test_sync_free_step_matches_the_synchronous_one():
+    """infer(sync=False) launches stage 3 for the person capacity and lets the kernels read the count from the device
+    (b200pose_encode_persons_n / b200pose_linear_n): same persons, same assignment and - bit for bit - the same joints as the
+    step that reads the count back, on a ragged batch, on a batch without any person, and at the full 1024-frame size."""
+    pipe = get_pipe('panoptic')
+    cfg = pipe.cfg
+    frames = [helpers.synth.make_frame(cfg, 9100 + i, 1 + i % 5, drop_view_p=0.1 * (i % 3)) for i in range(40)] + [{}]
+    frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
+    small = pack_mod.pack_frames(frames, cfg, keep_json=False)
+    none = pack_mod.pack_frames([{c: v for c, v in frames[0].items() if c == list(frames[0])[0]}], cfg, keep_json=False)   # one camera: no person
+    for pb in (small, none, small.tile(25)):
+        db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+        want = pipe.infer(db)
+        got = pipe.infer(db, sync=False)
+        P = pipeline_mod.PosePipeline.person_count(got)
+        assert P == want['n_persons_total']
+        assert torch.equal(got['n_persons'], want['n_persons']) and torch.equal(got['person_off'], want['person_off'])
+        if P:
+            assert torch.equal(got['person_sk'][:P], want['person_sk'])
+            assert torch.equal(got['valid'][:P], want['valid'])
+            assert torch.equal(got['joints'][:P], want['joints'])
