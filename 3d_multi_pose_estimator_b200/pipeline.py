@@ -200,6 +200,7 @@ class GraphArrays:
         # The aggregation kernels only need what both builders guarantee: heads first, three in-edges (h1, h2, self) per
         # edge-node, in-edges of a node in ascending edge id.
         self.general = False
+        self.pending = None       # side stream the builder was launched on (build_graph(overlap=True)), until wait_graph() joins it
 
 
 def _on_own_device(fn):
@@ -350,13 +351,33 @@ class PosePipeline:
             check(self.L.b200pose_linear_n(ptr(a.hi), ptr(a.lo), a.ld, ptr(w.hi), ptr(w.lo), w.ld, ptr(bias), m, ptr(m_dev), n, k, slope, scale,
                                            *tail), 'linear_n')
 
-    def build_graph(self, db: DeviceBatch, with_coo=True) -> GraphArrays:
+    def build_graph(self, db: DeviceBatch, with_coo=True, overlap: bool = False) -> GraphArrays:
+        """overlap=True launches the builder on a side stream: nothing reads the graph before the first aggregation, so it
+        runs beside the head features and the two layer-0 projections; `wait_graph(g)` joins it."""
         g = GraphArrays(db, self.device, with_coo)
         self.launches += 1
+        if overlap:
+            cur = torch.cuda.current_stream(self.device)
+            side = self.__dict__.get('_side_stream')
+            if side is None:
+                side = self.__dict__['_side_stream'] = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)                               # the packed batch (and, in a capture, the fork point)
+            with torch.cuda.stream(side):
+                check(self.L.b200pose_build_graph(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(db.sk_cam), self.cams.ref,
+                                                  ptr(g.src), ptr(g.dst), ptr(g.row_ptr), ptr(g.col), ptr(g.pairs), ptr(g.node_cam),
+                                                  self._stream()), 'build_graph')
+            g.pending = side
+            return g
         check(self.L.b200pose_build_graph(db.n_frames, ptr(db.head_off), ptr(db.node_off), ptr(db.sk_cam), self.cams.ref,
                                           ptr(g.src), ptr(g.dst), ptr(g.row_ptr), ptr(g.col), ptr(g.pairs), ptr(g.node_cam),
                                           self._stream()), 'build_graph')
         return g
+
+    def wait_graph(self, g: GraphArrays):
+        side = getattr(g, 'pending', None)
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g.pending = None
 
     def build_graph_pairs(self, db: DeviceBatch, pairs, with_coo=True) -> GraphArrays:
         """Graphs of a block-diagonal batch from explicit edge-node lists (process_training topology,
@@ -397,6 +418,7 @@ class PosePipeline:
                   raw: Optional[torch.Tensor], act: Optional[Planes], scores: Optional[torch.Tensor],
                   alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE):
         self.launches += 1
+        self.wait_graph(g)
         check(self.L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
                                             1 if layer0 else 0, db.max_heads, db.max_enodes, alpha, act_slope, ptr(raw),
@@ -587,8 +609,9 @@ class PosePipeline:
             return dict(graph=None, scores=torch.zeros(1, dtype=torch.float32, device=self.device),
                         person_heads=torch.zeros((1, self.cfg.V_sm), **i32), n_persons=torch.zeros(db.n_frames, **i32),
                         person_off=torch.zeros(db.n_frames + 1, **i32))
-        g = self.build_graph(db, with_coo=with_coo)
+        g = self.build_graph(db, with_coo=with_coo, overlap=True)
         scores = self.gat_forward(db, g) if db.n_nodes > 0 else torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.wait_graph(g)
         person_heads, n_persons = self.cluster(db, g, scores)
         person_off = torch.empty(db.n_frames + 1, dtype=torch.int32, device=self.device)
         self.launches += 1
