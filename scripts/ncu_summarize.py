@@ -31,7 +31,8 @@ def launches(path):
 
 
 COLS = [('gpu__time_duration.sum', 'us', 1e-3), ('dram__bytes_read.sum', 'dram rd MB', 1e-6), ('dram__bytes_write.sum', 'dram wr MB', 1e-6),
-        ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram %', 1), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor active %', 1),
+        ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram %', 1), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor active %', 1),
+        ('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'fp64 pipe %', 1), ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue active %', 1),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps active %', 1), ('launch__waves_per_multiprocessor', 'waves/SM', 1),
         ('lts__t_sector_hit_rate.pct', 'L2 hit %', 1), ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %', 1),
         ('launch__registers_per_thread', 'regs', 1)]
@@ -66,5 +67,29 @@ def full(path):
         print('| %s | %s | ' % (short(r[ki]), r[gi]) + ' | '.join(vals) + ' |')
 
 
+def traffic(path):
+    """DRAM bytes per kernel CLASS of the step (read + written), as JSON: what bench.py reports as roofline.traffic."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index('Kernel Name')
+    ri, wi = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    out, phase = {}, 'gat'
+    for r in rows[2:]:
+        if len(r) != len(hdr):
+            continue
+        k = short(r[ki])
+        b = float(r[ri].replace(',', '')) * scale.get(units[ri], 1.0) + float(r[wi].replace(',', '')) * scale.get(units[wi], 1.0)
+        if k.startswith('cluster_kernel'):
+            phase = 'mlp'
+        cls = ('gat_projection_gemm' if phase == 'gat' else 'mlp_gemm') if k.startswith('gemm_') else \
+              'edge_softmax_aggregate' if k.startswith('gat_aggregate') else 'encode_dlt' if k.startswith('lift_person') else \
+              'cluster' if k.startswith(('cluster_kernel', 'exclusive_scan', 'gather_persons')) else \
+              'node_features' if k.startswith('head_features') else 'graph_build' if k.startswith('build_graph') else k
+        out[cls] = out.get(cls, 0.0) + b
+    print(json.dumps({k: round(v) for k, v in out.items()}, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](sys.argv[2])
