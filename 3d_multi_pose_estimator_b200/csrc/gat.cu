@@ -1896,8 +1896,9 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     // edge-node 3; the frame with the most heads also has the most nodes: N_b <= H_b + H_b^2/2.
     const int mh = max_heads_per_frame > 0 ? max_heads_per_frame : 1;
     p.max_deg = mh < 3 ? 3 : mh;
-    // ---- large frames: fused edge-chunk + head units, every z row read from HBM once ----
-    if (((impl == 0 && (mh > 48 || tiny_batch)) || impl == 2) && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
+    // ---- large frames (more heads than the frame-resident kernels take: > 32): fused edge-chunk + head units, every z row read
+    // from HBM once. Measured on 256 six-camera ARP frames: 48 heads 1.13 ms against 3.66 ms for the gather kernel, 36 heads 0.70 / 2.18 ----
+    if (((impl == 0 && (mh > kFrameOwn * kFrameWarps || tiny_batch)) || impl == 2) && max_enodes_per_frame > 0 && 3 * heads <= 32 && HD / vec <= 32 * 4 && ldz <= 128 * kRowIters) {
         p.stage_cap = kLargeStageCap;
         p.edge_units = ceil_div(max_enodes_per_frame, kLargeChunk);
         p.head_units = ceil_div(mh, kLargeHeads);

@@ -496,7 +496,7 @@ def test_stress_frame_10_views_16_persons():
     assert np.isfinite(res['joints'].cpu().numpy()).all()
 
 
-@pytest.mark.parametrize('config,persons,impls', [('ring10', (16, 9, 6, 2, 12), (0, 1)), ('panoptic', None, (2, 3)), ('arp3', None, (2, 1))])
+@pytest.mark.parametrize('config,persons,impls', [('ring10', (16, 9, 6, 2, 12), (0, 1)), ('arp6', (8, 6, 7, 3), (0, 1)), ('panoptic', None, (2, 3)), ('arp3', None, (2, 1))])
 def test_large_frame_aggregation_agrees_with_other_kernels(config, persons, impls):
     """The large-frame aggregation kernel (staged head rows, cp.async row rings, fixed-reference softmax for heads with
     many in-edges) against the gather / frame-resident kernels, layer by layer: ragged batches of 160-, 90-, 60-,
@@ -510,7 +510,7 @@ def test_large_frame_aggregation_agrees_with_other_kernels(config, persons, impl
         frames = [helpers.synth.make_frame(cfg, 777 + i, n) for i, n in enumerate(persons)]
         frames = [{c: f[c] for c in f if json.loads(f[c][0])} for f in frames]
         pb = pack_mod.pack_frames(frames, cfg)
-        assert pb.max_heads > 48
+        assert pb.max_heads > 32                                  # beyond the frame-resident kernels: the dispatch takes the large-frame kernel
         db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
     g = pipe.build_graph(db, with_coo=False)
     outs = []
