@@ -857,14 +857,20 @@ class PosePipeline:
         return self.infer_host_graph(HostBatch(pack_frames_fast(frames, self.cfg, keep_json=False), pinned=False))
 
     def infer_host_stream(self, batches):
-        """Generator over host batches: yields the host results of each batch, in order. The host->device copy of
-        batch i+1 is enqueued on a copy stream before batch i is computed, so in steady state the copies ride under
-        the compute of the previous batch (the serving loop of a camera rig: pack frames -> infer -> consume)."""
+        """Generator over host batches: yields the host results of each batch, in order (the serving loop of a camera rig or
+        of a recorded sequence: pack frames -> infer -> consume). Three things overlap in steady state: the host->device
+        copy of batch i+1 (copy stream), the compute of batch i - enqueued as one sync-free step, so the GPU never waits for
+        the host inside it - and the result read-back of batch i-1 (its own stream: first the per-frame person counts, then,
+        once the host knows the total, exactly the persons' rows). Results of batch i are yielded after batch i+1 has been
+        enqueued; the last batch is flushed at the end."""
         cur = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
-        cs = self._copy_stream
+        if getattr(self, '_d2h_stream', None) is None:
+            self._d2h_stream = torch.cuda.Stream(self.device)
+        cs, ds = self._copy_stream, self._d2h_stream
         it = iter(batches)
+        n_out = self.mlp[-1]['n'] if self.mlp is not None else 0
 
         def prefetch():
             try:
@@ -879,24 +885,66 @@ class PosePipeline:
                 ev.record(cs)
             return hb, db, ev
 
-        nxt = prefetch()
-        while nxt is not None:
-            hb, db, ev = nxt
-            nxt = prefetch()                                   # the next batch's copy is in flight during this compute
+        # pinned result buffers: three rotating sets per batch size (a batch's results are handed out while the next batch
+        # computes and the one after is being enqueued), owned by the pipeline - the same HostBatch may be streamed repeatedly.
+        # A yielded result stays valid until two more batches have been yielded.
+        pool = self.__dict__.setdefault('_stream_results', {})
+        turn = [0]
+
+        def result_set(hb):
+            B, cap = hb.pb.n_frames, person_capacity(hb.pb.n_heads, self.cfg.min_number_of_views)
+            key = (B, cap, n_out)
+            sets = pool.get(key)
+            if sets is None:
+                mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+                sets = pool[key] = [dict(n_persons=mk((B,), torch.int32), person_off=mk((B + 1,), torch.int32),
+                                         person_sk=mk((cap, self.cfg.n_cameras), torch.int32), joints=mk((cap, max(n_out, 1)), torch.float32),
+                                         valid=mk((cap,), torch.uint8)) for _ in range(3)]
+            turn[0] += 1
+            return sets[turn[0] % 3]
+
+        def enqueue(hb, db, ev):
+            """Compute of one batch + the read-back of its person counts; nothing here waits for the GPU."""
             cur.wait_event(ev)
-            res = self.infer(db)
-            P = res['n_persons_total']
-            bufs = hb.result_buffers(self.cfg.n_cameras, self.mlp[-1]['n'] if self.mlp is not None else 0, self.cfg.min_number_of_views)
-            bufs['n_persons'].copy_(res['n_persons'], non_blocking=True)
-            bufs['person_off'].copy_(res['person_off'], non_blocking=True)
+            res = self.infer(db, sync=False)
+            if res.get('n_persons_dev') is not None and 'joints' in res:
+                res['joints'] = res['joints'].clone()            # 'mlp_out' is a shared workspace: the next batch overwrites it
+            done = torch.cuda.Event()
+            done.record(cur)
+            bufs = result_set(hb)
+            with torch.cuda.stream(ds):
+                ds.wait_event(done)
+                bufs['n_persons'].copy_(res['n_persons'], non_blocking=True)
+                bufs['person_off'].copy_(res['person_off'], non_blocking=True)
+                counts = torch.cuda.Event()
+                counts.record(ds)
+            return hb, res, bufs, counts
+
+        def finalize(hb, res, bufs, counts):
+            counts.synchronize()
+            P = int(bufs['person_off'][hb.pb.n_frames]) if hb.pb.n_heads > 0 else 0
+            res['n_persons_total'] = P
             if P > 0:
-                bufs['person_sk'][:P].copy_(res['person_sk'], non_blocking=True)
-                if 'joints' in res:
-                    bufs['joints'][:P].copy_(res['joints'], non_blocking=True)
-                    bufs['valid'][:P].copy_(res['valid'], non_blocking=True)
-            cur.synchronize()
+                with torch.cuda.stream(ds):
+                    bufs['person_sk'][:P].copy_(res['person_sk'][:P], non_blocking=True)
+                    if 'joints' in res:
+                        bufs['joints'][:P].copy_(res['joints'][:P], non_blocking=True)
+                        bufs['valid'][:P].copy_(res['valid'][:P], non_blocking=True)
+                ds.synchronize()
             out = dict(n_persons=bufs['n_persons'], person_off=bufs['person_off'], person_sk=bufs['person_sk'][:P], n_persons_total=P)
             if self.mlp is not None:
                 out['joints'] = bufs['joints'][:P]
                 out['valid'] = bufs['valid'][:P]
-            yield out
+            return out
+
+        nxt = prefetch()
+        pending = None
+        while nxt is not None:
+            hb, db, ev = nxt
+            nxt = prefetch()                                   # the next batch's copy is in flight during this compute
+            job = enqueue(hb, db, ev)
+            if pending is not None:
+                yield finalize(*pending)                       # batch i-1 is read back while batch i computes
+            pending = job
+        if pending is not None:
+            yield finalize(*pending)
