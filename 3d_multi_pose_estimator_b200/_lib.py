@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libb200pose.so')
 EXPORTS = ['b200pose_last_error', 'b200pose_version', 'b200pose_device_cc', 'b200pose_build_graph',
            'b200pose_node_features', 'b200pose_linear', 'b200pose_split_planes', 'b200pose_gat_aggregate',
            'b200pose_cluster', 'b200pose_cluster_pairs', 'b200pose_build_graph_pairs', 'b200pose_encode_persons', 'b200pose_triangulate', 'b200pose_gather_persons',
-           'b200pose_set_debug', 'b200pose_pack_record', 'b200pose_linear_n', 'b200pose_encode_persons_n', 'b200pose_pack_json', 'b200pose_packed_sizes', 'b200pose_packed_copy', 'b200pose_packed_free']
+           'b200pose_set_debug', 'b200pose_pack_record', 'b200pose_linear_n', 'b200pose_linear_fused2', 'b200pose_encode_persons_n', 'b200pose_pack_json', 'b200pose_packed_sizes', 'b200pose_packed_copy', 'b200pose_packed_free']
 
 
 class Cameras(C.Structure):
@@ -44,6 +44,7 @@ def lib():
         L.b200pose_node_features.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp]
         L.b200pose_linear.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, f32, vp, i32, vp, vp, i32, i32, vp]
         L.b200pose_linear_n.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, f32, f32, vp, i32, vp, vp, i32, i32, vp]
+        L.b200pose_linear_fused2.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, vp, i32, vp, i32, vp, i32, vp]
         L.b200pose_encode_persons_n.argtypes = [i32, vp, vp, vp, vp, vp, camp, vp, i32, vp, vp, i32, vp, vp]
         L.b200pose_split_planes.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
         L.b200pose_gat_aggregate.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32,

@@ -309,6 +309,9 @@ struct GemmParams2 {
     const float* bias; float slope, out_scale;
     int has_f32, has_planes;
     const int* m_dev;                        // when set: the number of valid rows lives on the device (M is then the capacity the maps were made for)
+    // fused second projection (b200pose_linear_fused2): out2[row, t] = sum_c act(out1)[row, c] * fuse_w[t, c] + fuse_b[t], t < fuse_n <= 4,
+    // evaluated in the epilogue registers of a single n-tile; nothing of out1 is stored
+    const float* fuse_w; const float* fuse_b; float* fuse_out; int fuse_n, fuse_ldw, fuse_ldo;
     int dbg;                                 // kernel bring-up switches (b200pose_set_debug): 1 = no stores, 2 = hi*hi only, 4 = no epilogue math
 };
 
@@ -555,6 +558,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
             tcgen05_fence_after();
             const uint32_t tmem_t = tmem_base + (uint32_t)a * acc_cols + ((uint32_t)(q * 32) << 16);
             const int npanels = t.bn / 64;
+            float facc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int j = 0; j < npanels; ++j) {
                 const int col0 = t.n0 + 64 * j;
                 uint32_t r0[32], r1[32];
@@ -643,6 +647,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_split_tc2_kernel(
                         v[32 + c] = (col0 + 32 + c < p.N) ? leaky(__uint_as_float(r1[c]) + bb1, p.slope) * p.out_scale : 0.f;
                     }
                 }
+                }
+                if (p.fuse_n > 0) {
+                    // second projection on the activated row in registers (this thread owns row m0 + rank*128 + q*32 + lane): the
+                    // weight rows are read as broadcast float4 loads, all lanes the same address
+#pragma unroll
+                    for (int tt = 0; tt < 4; ++tt) {
+                        if (tt >= p.fuse_n) break;
+                        const float4* w4 = reinterpret_cast<const float4*>(p.fuse_w + (size_t)tt * p.fuse_ldw + col0);
+                        float sacc = facc[tt];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float4 w = __ldg(w4 + c);
+                            sacc = fmaf(v[4 * c], w.x, sacc); sacc = fmaf(v[4 * c + 1], w.y, sacc);
+                            sacc = fmaf(v[4 * c + 2], w.z, sacc); sacc = fmaf(v[4 * c + 3], w.w, sacc);
+                        }
+                        facc[tt] = sacc;
+                    }
+                    if (j == npanels - 1) {
+                        const int row = t.m0 + (int)rank * kBM + q * 32 + lane;
+                        if (row < M_rows && !(p.dbg & 1)) {
+                            for (int tt = 0; tt < p.fuse_n; ++tt) p.fuse_out[(size_t)row * p.fuse_ldo + tt] = facc[tt] + __ldg(p.fuse_b + tt);
+                        }
+                    }
+                    continue;
                 }
                 if (stores_pending) {                             // staging buffers are about to be overwritten
                     if (lane == 0) bulk_wait_read0();
@@ -1287,18 +1315,28 @@ static int choose_bn(int n) {
 using namespace b200pose;
 
 
+struct FuseArgs { const float* w; const float* b; float* out; int n, ldw, ldo; };
+
 static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                        const uint16_t* w_hi, const uint16_t* w_lo, int32_t ldw,
                        const float* bias, int32_t m, const int32_t* m_dev, int32_t n, int32_t k, float slope, float out_scale,
                        float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
-                       int32_t impl, void* stream)
+                       int32_t impl, void* stream, const FuseArgs* fuse = nullptr)
 {
     B2_CHECK_ARG(a_hi && a_lo && w_hi && w_lo, "linear: null operand");
+    if (fuse) {
+        B2_CHECK_ARG(impl == 0 && !m_dev, "linear_fused2: impl must be 0");
+        B2_CHECK_ARG(fuse->w && fuse->b && fuse->out && fuse->n >= 1 && fuse->n <= 4, "linear_fused2: 1..4 fused output columns");
+        B2_CHECK_ARG(n <= 256, "linear_fused2: the first projection must fit one n-tile (n <= 256)");
+        B2_CHECK_ARG(fuse->ldw % 4 == 0 && fuse->ldw >= ((n + 63) / 64) * 64 && ((uintptr_t)fuse->w % 16 == 0), "linear_fused2: fused weight rows must be 16-byte aligned and padded to a multiple of 64 columns");
+        B2_CHECK_ARG(fuse->ldo >= fuse->n, "linear_fused2: ld_out2 < n2");
+        B2_CHECK_ARG(!out_f32 && !out_hi, "linear_fused2: the first projection is not stored");
+    }
     if (m_dev) B2_CHECK_ARG(impl == 0 || impl == 4 || impl == 5, "linear_n: only the persistent kernels read the row count from the device");
     B2_CHECK_ARG(m >= 0 && n >= 1 && k >= 1, "linear: bad shape m=%d n=%d k=%d", m, n, k);
     const int kpad = ceil_div(k, kBK) * kBK;
     B2_CHECK_ARG(lda % 64 == 0 && ldw % 64 == 0 && lda >= kpad && ldw >= kpad, "linear: lda/ldw must be multiples of 64 >= round_up(k,64)");
-    B2_CHECK_ARG(out_f32 || out_hi, "linear: no output requested");
+    B2_CHECK_ARG(out_f32 || out_hi || fuse, "linear: no output requested");
     B2_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr), "linear: planes go together");
     if (out_f32) B2_CHECK_ARG(ld_out >= n, "linear: ld_out < n");
     if (out_hi) B2_CHECK_ARG(ld_planes % 64 == 0 && ld_planes >= n, "linear: ld_planes must be a multiple of 64 >= n");
@@ -1355,7 +1393,7 @@ static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
         return B200POSE_E_UNSUPPORTED;
     }
 #endif
-    if (!m_dev && (impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
+    if (!m_dev && !fuse && (impl == 0 || impl == 7) && m <= 8 && kpad <= 4096 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight stream with A in registers: k split over the CTA's lanes, blocks of 32 / MMAX columns
         const int warps = ceil_div(kpad, 256);
         const int cols = out_hi ? ld_planes : n;
@@ -1370,7 +1408,7 @@ static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
         };
         return m <= 4 ? launch_stream(gemm_stream_kernel<4>, 8) : launch_stream(gemm_stream_kernel<8>, 4);
     }
-    if (!m_dev && (impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
+    if (!m_dev && !fuse && (impl == 0 || impl == 7) && m <= kSmallM && (size_t)m * kpad * sizeof(float) <= 200 * 1024 && lda % 8 == 0 && ldw % 8 == 0) {
         // weight-streaming small-M kernel: as many CTAs as fit at once (the A staging is per CTA), every warp takes columns
         const size_t smem = (size_t)m * kpad * sizeof(float);
         const int cols = out_hi ? ld_planes : n;
@@ -1398,6 +1436,8 @@ static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
     GemmParams2 q;
     q.M = m; q.N = n; q.num_kb = kpad / kBK; q.k_last = ceil_div(k - (kpad / kBK - 1) * kBK, kUmmaK); q.bias = bias; q.slope = slope; q.out_scale = out_scale;
     q.has_f32 = out_f32 ? 1 : 0; q.has_planes = out_hi ? 1 : 0; q.dbg = g_debug_flags; q.m_dev = m_dev;
+    q.fuse_n = 0; q.fuse_w = nullptr; q.fuse_b = nullptr; q.fuse_out = nullptr; q.fuse_ldw = 0; q.fuse_ldo = 0;
+    if (fuse) { q.fuse_n = fuse->n; q.fuse_w = fuse->w; q.fuse_b = fuse->b; q.fuse_out = fuse->out; q.fuse_ldw = fuse->ldw; q.fuse_ldo = fuse->ldo; }
     q.panels_total = ceil_div(n, 64);                         // 64-column panels; planes panels also zero columns [n, 64*panels)
     const size_t staging = 4 * (size_t)((q.has_f32 ? 8192 : 0) + (q.has_planes ? 8192 : 0));
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo, mw2_hi, mw2_lo, mo_f32, mo_hi, mo_lo;
@@ -1449,7 +1489,7 @@ static int linear_impl(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
     q.tiles_m = ceil_div(m, kBM * ncta);
     // a handful of m-tiles (single-frame calls: ~180 graph nodes): one 64-column panel per tile, so that the k-loops of
     // an output row run side by side on many SMs instead of back to back on one - latency, not throughput, matters here
-    if (impl == 0 && ncta == 1 && q.tiles_m * q.tiles_n * 8 < num_sms()) q.tiles_n = q.panels_total;
+    if (impl == 0 && ncta == 1 && !fuse && q.tiles_m * q.tiles_n * 8 < num_sms()) q.tiles_n = q.panels_total;
     q.stage_bn = 64 * ceil_div(q.panels_total, q.tiles_n);
     const size_t stage2 = 2 * (size_t)kBM * kBK * 2 + 2 * (size_t)(q.stage_bn / ncta) * kBK * 2;
     int stages = (int)((227 * 1024 - 2048 - staging) / stage2);
@@ -1500,4 +1540,15 @@ extern "C" __attribute__((visibility("default"))) int b200pose_linear_n(const ui
 {
     B2_CHECK_ARG(m_dev, "linear_n: null row-count pointer");
     return linear_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, m_capacity, m_dev, n, k, slope, out_scale, out_f32, ld_out, out_hi, out_lo, ld_planes, impl, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_linear_fused2(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                                      const uint16_t* w1_hi, const uint16_t* w1_lo, int32_t ldw1, const float* bias1,
+                                      int32_t m, int32_t n1, int32_t k, float slope1,
+                                      const float* w2_f32, int32_t ldw2, const float* bias2, int32_t n2,
+                                      float* out2_f32, int32_t ld_out2, void* stream)
+{
+    FuseArgs f;
+    f.w = w2_f32; f.b = bias2; f.out = out2_f32; f.n = n2; f.ldw = ldw2; f.ldo = ld_out2;
+    return linear_impl(a_hi, a_lo, lda, w1_hi, w1_lo, ldw1, bias1, m, nullptr, n1, k, slope1, 1.0f, nullptr, 0, nullptr, nullptr, 0, 0, stream, &f);
 }

@@ -235,6 +235,7 @@ class PosePipeline:
         self.L = _lib.lib()
         self.gemm_impl = gemm_impl
         self.agg_impl = 0          # 0 = frame-resident aggregation kernel when it fits, 1 = gather kernel
+        self.fuse_small_fc2 = True  # last GAT layer: fc2 (3 columns) inside fc1's epilogue (False: two launches, for A/B runs)
         self.threshold = float(threshold)
         self.launches = 0
         self._ws = {}
@@ -321,10 +322,17 @@ class PosePipeline:
             W2e = torch.cat([W2, Wl, Wr], 0).float().to(self.device)
             b2e = torch.cat([b2, bl, br], 0).float().to(self.device)
             s = self._stream()
-            layers.append(dict(
+            lay = dict(
                 din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4),
                 w1=Planes.from_f32(W1.float().to(self.device), s), b1=b1.float().to(self.device),
-                w2=Planes.from_f32(W2e, s), b2=b2e))
+                w2=Planes.from_f32(W2e, s), b2=b2e)
+            if lay['n2'] <= 4 and din <= 256:
+                # a few output columns (the last layer: ft2 | a1 | a2 = 3): fc2 is evaluated in fc1's epilogue
+                # (b200pose_linear_fused2) from fp32 weight rows padded to a multiple of 64 columns
+                w2f = torch.zeros((lay['n2'], round_up(din, 64)), dtype=torch.float32, device=self.device)
+                w2f[:, :din] = W2e
+                lay['w2_f32'] = w2f
+            layers.append(lay)
         return layers
 
     def prepare_mlp(self, st):
@@ -442,10 +450,17 @@ class PosePipeline:
         logits = torch.empty(max(N, 1), dtype=torch.float32, device=self.device) if not final_sigmoid else None
         for l, lay in enumerate(layers):
             last = l == len(layers) - 1
-            h = self.planes_ws('gat_h', rows, lay['din'])
-            self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], alpha, out_planes=h)
             z = self.f32_ws('gat_z', rows, lay['ldz'])
-            self.linear(h, rows, lay['w2'], lay['b2'], lay['n2'], lay['din'], 1.0, out_f32=z)
+            if 'w2_f32' in lay and self.gemm_impl == 0 and rows > 16 and self.fuse_small_fc2:
+                self.launches += 1
+                w2f = lay['w2_f32']
+                check(self.L.b200pose_linear_fused2(ptr(x.hi), ptr(x.lo), x.ld, ptr(lay['w1'].hi), ptr(lay['w1'].lo), lay['w1'].ld, ptr(lay['b1']),
+                                                    rows, lay['din'], lay['din'], alpha, ptr(w2f), w2f.stride(0), ptr(lay['b2']), lay['n2'],
+                                                    ptr(z), z.stride(0), self._stream()), 'linear_fused2')
+            else:
+                h = self.planes_ws('gat_h', rows, lay['din'])
+                self.linear(x, rows, lay['w1'], lay['b1'], lay['din'], lay['din'], alpha, out_planes=h)
+                self.linear(h, rows, lay['w2'], lay['b2'], lay['n2'], lay['din'], 1.0, out_f32=z)
             raw = torch.empty((max(N, 1), lay['hd']), dtype=torch.float32, device=self.device) if keep_layers else None
             act = None if last else self.planes_ws('gat_act%d' % (l & 1), N, lay['hd'])
             if last and not final_sigmoid and raw is None:

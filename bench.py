@@ -232,6 +232,7 @@ def main():
                          'every rank streams its share in chunks of --frames frames')
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
+    ap.add_argument('--no-fuse2', action='store_true', help='A/B: run the last GAT layer as two projections instead of the fused launch')
     ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
@@ -305,6 +306,7 @@ def main():
         pb = pb.tile(-(-args.frames // distinct)).slice(0, args.frames)
     hb = pm.HostBatch(pb)
     pipe = pm.PosePipeline(cfg, gat, mlp, device=dev, gemm_impl=args.gemm_impl)
+    pipe.fuse_small_fc2 = not args.no_fuse2
     db = hb.to_device(dev)
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

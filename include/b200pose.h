@@ -146,6 +146,17 @@ int b200pose_linear_n(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
                       float slope, float out_scale,
                       float* out_f32, int32_t ld_out, uint16_t* out_hi, uint16_t* out_lo, int32_t ld_planes,
                       int32_t impl, void* stream);
+/* Two projections in one launch when the second is only a few columns wide (the last GAT layer: fc1 150 -> 150, then
+ * fc2 + attention dots 150 -> 3, gat2.py:53-58 with num_heads = 1, out_dim = 1):
+ *   out2[m, n2] = LeakyReLU_slope1(A W1^T + b1) W2^T + b2,  n1 <= 256, n2 <= 4.
+ * The first projection runs on the tensor cores as in b200pose_linear; its activated rows never leave the epilogue
+ * registers - each is dotted with the n2 fp32 rows of W2 there (w2_f32 [n2, ldw2], rows padded with zeros to a multiple of
+ * 64 columns, 16-byte aligned). Saves writing and re-reading the intermediate planes (2 x 141 MB at 184 k rows). */
+int b200pose_linear_fused2(const uint16_t* a_hi, const uint16_t* a_lo, int32_t lda,
+                           const uint16_t* w1_hi, const uint16_t* w1_lo, int32_t ldw1, const float* bias1,
+                           int32_t m, int32_t n1, int32_t k, float slope1,
+                           const float* w2_f32, int32_t ldw2, const float* bias2, int32_t n2,
+                           float* out2_f32, int32_t ld_out2, void* stream);
 
 /* Kernel bring-up switches for the persistent GEMM (results become WRONG; used by scripts/gemm_probe.py to attribute time):
  * bit 0 = skip the output stores, bit 1 = issue only the hi*hi MMA, bit 2 = skip the epilogue arithmetic. Returns the old value. */

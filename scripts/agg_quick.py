@@ -16,6 +16,7 @@ gat, mlp = load_weights(config, cfg)
 pb = pack.pack_frames(frames, cfg, keep_json=False)
 pipe = pm.PosePipeline(cfg, gat, mlp, device='cuda:0')
 pipe.agg_impl = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+pipe.fuse_small_fc2 = os.environ.get('B200POSE_NO_FUSE2') != '1'
 db = pm.HostBatch(pb).to_device('cuda:0')
 for _ in range(3):
     pipe.infer(db)
@@ -23,8 +24,8 @@ torch.cuda.synchronize()
 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 for a, b in ev:
-    flush.fill_(1); a.record(); pipe.infer(db); b.record()
+    flush.fill_(1); a.record(); pipe.infer(db, sync=False); b.record()
 torch.cuda.synchronize()
 k = profile_classes(pipe, db, pm, torch)
-print(config, persons, 'heads/frame', pb.max_heads, 'impl %d: step %.4f ms | agg %.4f | gemm %.4f | mlp %.4f' % (pipe.agg_impl, np.mean([a.elapsed_time(b) for a, b in ev]),
+print(config, persons, 'heads/frame', pb.max_heads, 'fuse2', pipe.fuse_small_fc2, 'impl %d: step %.4f ms | agg %.4f | gemm %.4f | mlp %.4f' % (pipe.agg_impl, np.mean([a.elapsed_time(b) for a, b in ev]),
       k['edge_softmax_aggregate'], k['gat_projection_gemm'], k['mlp_gemm']))
