@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libb200pose.so')
 
 EXPORTS = ['b200pose_last_error', 'b200pose_version', 'b200pose_device_cc', 'b200pose_build_graph',
-           'b200pose_node_features', 'b200pose_linear', 'b200pose_split_planes', 'b200pose_gat_aggregate',
+           'b200pose_node_features', 'b200pose_linear', 'b200pose_split_planes', 'b200pose_gat_aggregate', 'b200pose_gat_aggregate_res',
            'b200pose_cluster', 'b200pose_cluster_pairs', 'b200pose_build_graph_pairs', 'b200pose_encode_persons', 'b200pose_triangulate', 'b200pose_gather_persons',
            'b200pose_set_debug', 'b200pose_pack_record', 'b200pose_linear_n', 'b200pose_linear_fused2', 'b200pose_encode_persons_n', 'b200pose_pack_json', 'b200pose_packed_sizes', 'b200pose_packed_copy', 'b200pose_packed_free']
 
@@ -49,6 +49,8 @@ def lib():
         L.b200pose_split_planes.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
         L.b200pose_gat_aggregate.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32,
                                              vp, vp, vp, i32, vp, i32, vp]
+        L.b200pose_gat_aggregate_res.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, vp, i32,
+                                                 vp, vp, vp, i32, vp, vp]
         L.b200pose_cluster.argtypes = [i32, vp, vp, vp, vp, vp, i32, f64, i32, i32, i32, vp, vp, vp]
         L.b200pose_cluster_pairs.argtypes = L.b200pose_cluster.argtypes
         L.b200pose_build_graph_pairs.argtypes = [i32, vp, vp, vp, camp, vp, i32, vp, vp, vp, vp, vp, vp]

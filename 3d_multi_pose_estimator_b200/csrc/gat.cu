@@ -32,6 +32,7 @@ struct AggParams {
     const float* z; int ldz; int heads, dim, layer0;
     float alpha, act_slope;
     float* raw_f32; __nv_bfloat16* act_hi; __nv_bfloat16* act_lo; int ld_planes;
+    const float* res; int ld_res;   // residual term added to the aggregate before the activation (gat2.py:70-75: res_fc(h)), gather / scalar kernels only
     int stage_rows;     // z rows of shared memory available per CTA for staging
     int chunk;          // destination nodes per CTA (work unit = frame x chunk)
     int n_chunks;       // chunks per frame (grid = n_frames * n_chunks)
@@ -237,6 +238,11 @@ __global__ void __launch_bounds__(kAggWarps * 32) gat_aggregate_kernel(AggParams
         for (int k = 0; k < KMAX; ++k) {
             const int cv = lane + 32 * k;
             if (cv >= n_vec) continue;
+            if (p.res) {                                        // ret = resval + ret (gat2.py:75)
+                const float* rr = p.res + (size_t)gv * p.ld_res + cv * VEC;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc[k][q] = rr[q] + acc[k][q];
+            }
             if (p.raw_f32) {
                 float* o = p.raw_f32 + (size_t)gv * HD + cv * VEC;
 #pragma unroll
@@ -1302,7 +1308,8 @@ __global__ void __launch_bounds__((W + 2) * 32, 1) gat_aggregate_frame_p_kernel(
 // last layer (heads*dim == 1): one thread per destination node, sigmoid fused (gat2.py:143-145)
 __global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
     int n_nodes_total, const int* __restrict__ row_ptr, const int* __restrict__ col,
-    const float* __restrict__ z, int ldz, float alpha, float* __restrict__ raw_f32, float* __restrict__ scores)
+    const float* __restrict__ z, int ldz, float alpha, float* __restrict__ raw_f32, float* __restrict__ scores,
+    const float* __restrict__ res, int ld_res)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes_total) return;
@@ -1317,6 +1324,7 @@ __global__ void __launch_bounds__(256) gat_aggregate_scalar_kernel(
         const float* ru = z + (size_t)col[e] * ldz;
         acc = fmaf(expf(leaky(ru[1] + a2v, alpha) - m) / den, ru[0], acc);
     }
+    if (res) acc = res[(size_t)v * ld_res] + acc;             // residual (gat2.py:75)
     if (raw_f32) raw_f32[v] = acc;
     if (scores) scores[v] = 1.0f / (1.0f + expf(-acc));
 }
@@ -1758,14 +1766,20 @@ __global__ void __launch_bounds__(kAggWarps * 32, 2) gat_aggregate_large_kernel(
 
 using namespace b200pose;
 
-extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
-                                      const int32_t* head_off, const int32_t* node_off,
-                                      const int32_t* row_ptr, const int32_t* col,
-                                      const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
-                                      int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
-                                      float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
-                                      float* scores, int32_t impl, void* stream)
+static int gat_aggregate_impl(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                              const int32_t* head_off, const int32_t* node_off,
+                              const int32_t* row_ptr, const int32_t* col,
+                              const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
+                              int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
+                              float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                              float* scores, int32_t impl, void* stream, const float* res, int32_t ld_res)
 {
+    if (res) {
+        B2_CHECK_ARG(!layer0, "gat_aggregate_res: the first layer has no residual (gat2.py:118)");
+        B2_CHECK_ARG(ld_res >= heads * dim, "gat_aggregate_res: ld_res < heads * dim");
+        B2_CHECK_ARG(impl == 0 || impl == 1, "gat_aggregate_res: the residual term is added by the gather kernel (impl 0 or 1)");
+        impl = 1;
+    }
     B2_CHECK_ARG(head_off && node_off && row_ptr && col && z, "gat_aggregate: null input");
     B2_CHECK_ARG(heads >= 1 && dim >= 1 && ldz >= heads * dim + 2 * heads, "gat_aggregate: ldz too small");
     B2_CHECK_ARG(heads <= 32, "gat_aggregate: more than 32 attention heads");
@@ -1776,7 +1790,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     if (HD == 1) {
         B2_CHECK_ARG(!layer0 && !act_hi, "gat_aggregate: scalar layer cannot be layer 0 / produce planes");
         gat_aggregate_scalar_kernel<<<ceil_div(n_nodes_total, 256), 256, 0, st>>>(n_nodes_total, row_ptr, col, z, ldz,
-                                                                                  alpha, raw_f32, scores);
+                                                                                  alpha, raw_f32, scores, res, ld_res);
         B2_CHECK_LAUNCH();
         return B200POSE_OK;
     }
@@ -1789,6 +1803,7 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     p.alpha = alpha; p.act_slope = act_slope; p.raw_f32 = raw_f32;
     p.act_hi = reinterpret_cast<__nv_bfloat16*>(act_hi); p.act_lo = reinterpret_cast<__nv_bfloat16*>(act_lo);
     p.ld_planes = ld_planes;
+    p.res = res; p.ld_res = ld_res;
     p.dbg = g_debug_flags;
     p.stage_cap = 0; p.edge_units = 0; p.head_units = 0;
     const int vec = (dim % 4 == 0) ? 4 : (dim % 2 == 0 ? 2 : 1);
@@ -1956,4 +1971,32 @@ extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int
     if (vec == 4) return n_vec <= 64 ? launch(gat_aggregate_kernel<4, 2>) : n_vec <= 128 ? launch(gat_aggregate_kernel<4, 4>) : launch(gat_aggregate_kernel<4, 8>);
     if (vec == 2) return n_vec <= 64 ? launch(gat_aggregate_kernel<2, 2>) : n_vec <= 128 ? launch(gat_aggregate_kernel<2, 4>) : launch(gat_aggregate_kernel<2, 8>);
     return n_vec <= 128 ? launch(gat_aggregate_kernel<1, 4>) : launch(gat_aggregate_kernel<1, 8>);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                                      const int32_t* head_off, const int32_t* node_off,
+                                      const int32_t* row_ptr, const int32_t* col,
+                                      const float* z, int32_t ldz, int32_t heads, int32_t dim, int32_t layer0,
+                                      int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
+                                      float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                                      float* scores, int32_t impl, void* stream)
+{
+    return gat_aggregate_impl(n_frames, n_nodes_total, n_heads_total, head_off, node_off, row_ptr, col, z, ldz, heads, dim, layer0,
+                              max_heads_per_frame, max_enodes_per_frame, alpha, act_slope, raw_f32, act_hi, act_lo, ld_planes, scores, impl,
+                              stream, nullptr, 0);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200pose_gat_aggregate_res(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                                          const int32_t* head_off, const int32_t* node_off,
+                                          const int32_t* row_ptr, const int32_t* col,
+                                          const float* z, int32_t ldz, int32_t heads, int32_t dim,
+                                          int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
+                                          const float* res, int32_t ld_res,
+                                          float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                                          float* scores, void* stream)
+{
+    B2_CHECK_ARG(res, "gat_aggregate_res: null residual");
+    return gat_aggregate_impl(n_frames, n_nodes_total, n_heads_total, head_off, node_off, row_ptr, col, z, ldz, heads, dim, 0,
+                              max_heads_per_frame, max_enodes_per_frame, alpha, act_slope, raw_f32, act_hi, act_lo, ld_planes, scores, 1,
+                              stream, res, ld_res);
 }

@@ -299,7 +299,7 @@ class PosePipeline:
             self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         return C.c_void_p(torch._C._cuda_getCurrentRawStream(self._dev_index))
 
-    def prepare_gat(self, st):
+    def prepare_gat(self, st, residual: bool = False):
         """Split every projection into planes; fold the attention vectors into fc2 as 2*heads extra output
         rows: a1[n,h] = sum_d ft2[n,h,d]*attn_l[h,d] = h2[n,:] . (sum_d attn_l[h,d]*W2[hD+d,:]) + bias term
         (gat2.py:55-58), so one GEMM yields [ft2 | a1 | a2]."""
@@ -332,6 +332,18 @@ class PosePipeline:
                 w2f = torch.zeros((lay['n2'], round_up(din, 64)), dtype=torch.float32, device=self.device)
                 w2f[:, :din] = W2e
                 lay['w2_f32'] = w2f
+            if residual and l > 0:
+                # gat2.py:43-48, 70-75: res_fc(h) when the layer changes the width, the input itself (broadcast over the
+                # attention heads) when in_dim == out_dim; the first layer is always built without a residual (:108)
+                if ('layers.%d.res_fc.weight' % l) in st:
+                    Wr_ = g('res_fc.weight')
+                    lay['res_w'] = Planes.from_f32(Wr_.float().to(self.device), s)
+                    lay['res_b'] = (g('res_fc.bias') if ('layers.%d.res_fc.bias' % l) in st
+                                    else torch.zeros(Wr_.shape[0], dtype=torch.float64)).float().to(self.device)
+                elif din == D:
+                    lay['res_identity'] = True
+                else:
+                    raise ValueError('prepare_gat: residual layer %d has in_dim %d != out_dim %d but no res_fc weights' % (l, din, D))
             layers.append(lay)
         return layers
 
@@ -424,9 +436,16 @@ class PosePipeline:
 
     def aggregate(self, db: DeviceBatch, g: GraphArrays, z: torch.Tensor, layer: dict, layer0: bool,
                   raw: Optional[torch.Tensor], act: Optional[Planes], scores: Optional[torch.Tensor],
-                  alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE):
+                  alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE, res: Optional[torch.Tensor] = None):
         self.launches += 1
         self.wait_graph(g)
+        if res is not None:
+            check(self.L.b200pose_gat_aggregate_res(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
+                                                    ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
+                                                    db.max_heads, db.max_enodes, alpha, act_slope, ptr(res), res.stride(0), ptr(raw),
+                                                    ptr(act.hi) if act else None, ptr(act.lo) if act else None, act.ld if act else 0,
+                                                    ptr(scores), self._stream()), 'gat_aggregate_res')
+            return
         check(self.L.b200pose_gat_aggregate(db.n_frames, db.n_nodes, db.n_heads, ptr(db.head_off), ptr(db.node_off),
                                             ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), layer['heads'], layer['dim'],
                                             1 if layer0 else 0, db.max_heads, db.max_enodes, alpha, act_slope, ptr(raw),
@@ -451,6 +470,12 @@ class PosePipeline:
         for l, lay in enumerate(layers):
             last = l == len(layers) - 1
             z = self.f32_ws('gat_z', rows, lay['ldz'])
+            res = None
+            if 'res_w' in lay:
+                res = self.f32_ws('gat_res', rows, round_up(lay['hd'], 4))
+                self.linear(x, rows, lay['res_w'], lay['res_b'], lay['hd'], lay['din'], 1.0, out_f32=res)
+            elif lay.get('res_identity'):
+                res = x.to_f32()[:rows, : lay['din']].repeat(1, lay['heads']).contiguous()
             if 'w2_f32' in lay and self.gemm_impl == 0 and rows > 16 and self.fuse_small_fc2:
                 self.launches += 1
                 w2f = lay['w2_f32']
@@ -466,7 +491,7 @@ class PosePipeline:
             if last and not final_sigmoid and raw is None:
                 raw = logits.view(-1, 1)
             self.aggregate(db, g, z, lay, layer0=(l == 0 and not dense_rows), raw=raw, act=act,
-                           scores=scores if (last and final_sigmoid) else None, alpha=alpha, act_slope=act_slope)
+                           scores=scores if (last and final_sigmoid) else None, alpha=alpha, act_slope=act_slope, res=res)
             if keep_layers:
                 raws.append(raw[:N])
             x, rows = act, N

@@ -2,7 +2,8 @@
 
 Same constructors, parameter names (state_dict keys `layers.{l}.{attn_l,attn_r,fc1.*,fc2.*[,res_fc.*]}`) and
 initialisation order; `forward` runs on the B200 kernels (split-bf16 tcgen05 projections + the fused
-edge-softmax/aggregation kernel) instead of DGL. Inference only: dropout must be 0, no residual.
+edge-softmax/aggregation kernel) instead of DGL. Inference only: dropout must be 0. Residual layers (gat2.py:70-75, not the
+shipped configuration) add res_fc(h) - or h itself when the widths agree - inside the gather aggregation kernel.
 """
 import torch
 import torch.nn as nn
@@ -68,8 +69,6 @@ class GAT2(nn.Module):
         for lyr in self.layers:
             if lyr.feat_drop_p or lyr.attn_drop_p:
                 raise NotImplementedError('B200 GAT2 is inference-only: feat_drop/attn_drop must be 0')
-            if lyr.residual:
-                raise NotImplementedError('B200 GAT2: residual connections are not implemented')
         if not isinstance(self.activation, nn.LeakyReLU):
             raise NotImplementedError('B200 GAT2: the inter-layer activation must be nn.LeakyReLU')
         if self.final_activation is not None and not isinstance(self.final_activation, nn.Sigmoid):
@@ -85,7 +84,8 @@ class GAT2(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in plist)
         if self._prepared is None or key != self._prepared_key:
             rt.sync_live()
-            self._prepared = ctx.prepare_gat({k: v for k, v in self.state_dict().items()})
+            self._prepared = ctx.prepare_gat({k: v for k, v in self.state_dict().items()},
+                                              residual=any(lyr.residual for lyr in self.layers))
             self._prepared_key = key
         return self._prepared
 
@@ -99,7 +99,7 @@ class GAT2(nn.Module):
         # the whole-frame submissions of the dataset drop-in use these weights from now on - when the model is the shipped
         # kind (the pipeline's activation constants) - and this call is answered from the submission of its own graph
         P = rt.pipeline
-        shipped = (abs(self.alpha - P.GAT_ALPHA) < 1e-12 and abs(self.activation.negative_slope - P.GAT_ACT_SLOPE) < 1e-12
+        shipped = (not any(lyr.residual for lyr in self.layers) and abs(self.alpha - P.GAT_ALPHA) < 1e-12 and abs(self.activation.negative_slope - P.GAT_ACT_SLOPE) < 1e-12
                    and self.final_activation is not None)
         if shipped:
             rt.note_model('gat', self, self._prepared_key, layers)

@@ -36,10 +36,13 @@ def gat_layer_dims(in_dim: int, num_hidden: Sequence[int] = GAT_HIDDEN, heads: S
     return dims
 
 
-def make_gat_state(in_dim: int, seed: int = 0, bias: bool = True) -> Dict[str, torch.Tensor]:
+def make_gat_state(in_dim: int, seed: int = 0, bias: bool = True, num_hidden: Sequence[int] = GAT_HIDDEN,
+                   heads: Sequence[int] = GAT_HEADS, residual: bool = False) -> Dict[str, torch.Tensor]:
+    """residual=True adds `layers.{l}.res_fc.*` for every layer after the first whose in_dim != out_dim, created after the
+    layer's attention vectors as gat2.py:43-46 does."""
     torch.manual_seed(seed)
     state = {}
-    for l, (din, h, dout) in enumerate(gat_layer_dims(in_dim)):
+    for l, (din, h, dout) in enumerate(gat_layer_dims(in_dim, num_hidden, heads)):
         fc1 = nn.Linear(din, din, bias=bias)
         fc2 = nn.Linear(din, h * dout, bias=bias)
         attn_l = torch.empty(h, dout, 1)
@@ -55,6 +58,12 @@ def make_gat_state(in_dim: int, seed: int = 0, bias: bool = True) -> Dict[str, t
         if bias:
             state['layers.%d.fc1.bias' % l] = fc1.bias.data
             state['layers.%d.fc2.bias' % l] = fc2.bias.data
+        if residual and l > 0 and din != dout:
+            res_fc = nn.Linear(din, h * dout, bias=bias)
+            nn.init.xavier_normal_(res_fc.weight.data, gain=1.414)
+            state['layers.%d.res_fc.weight' % l] = res_fc.weight.data
+            if bias:
+                state['layers.%d.res_fc.bias' % l] = res_fc.bias.data
     return state
 
 

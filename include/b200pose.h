@@ -190,6 +190,18 @@ int b200pose_gat_aggregate(int32_t n_frames, int32_t n_nodes_total, int32_t n_he
                            int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
                            float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
                            float* scores, int32_t impl, void* stream);
+/* The same layer with a residual connection (GraphAttention2 built with residual=True and in_dim != out_dim,
+ * gat2.py:43-48, 70-75): out[v] = res[v] + sum_u softmax * ft2[u], `res` [N, ld_res] fp32 = res_fc(h) computed by the caller
+ * with b200pose_linear. Not the shipped configuration (train_skeleton_matching.py:50: residual = False); served by the
+ * gather kernel. */
+int b200pose_gat_aggregate_res(int32_t n_frames, int32_t n_nodes_total, int32_t n_heads_total,
+                               const int32_t* head_off, const int32_t* node_off,
+                               const int32_t* row_ptr, const int32_t* col,
+                               const float* z, int32_t ldz, int32_t heads, int32_t dim,
+                               int32_t max_heads_per_frame, int32_t max_enodes_per_frame, float alpha, float act_slope,
+                               const float* res, int32_t ld_res,
+                               float* raw_f32, uint16_t* act_hi, uint16_t* act_lo, int32_t ld_planes,
+                               float* scores, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 2b. Person proposals: get_person_proposal_from_network_output

@@ -297,9 +297,10 @@ def leaky(x, slope):
     return np.where(x >= 0, x, x * f32(slope)).astype(f32)
 
 
-def gat_layer(x, src, dst, W1, b1, W2, b2, attn_l, attn_r, heads, alpha):
+def gat_layer(x, src, dst, W1, b1, W2, b2, attn_l, attn_r, heads, alpha, res=None):
     """GraphAttention2.forward (gat2.py:50-76) with DGL's edge_softmax(norm_by='dst') and
-    update_all(u_mul_e, sum) semantics (gat2.py:61-66, 78-88); dropout is the identity at inference."""
+    update_all(u_mul_e, sum) semantics (gat2.py:61-66, 78-88); dropout is the identity at inference.
+    res: None (residual=False), (W, b) = res_fc, or 'identity' (in_dim == out_dim), gat2.py:70-75."""
     n = x.shape[0]
     ft1 = x @ W1.T + b1                                               # :53
     h2 = leaky(ft1, alpha)                                            # :54
@@ -315,20 +316,30 @@ def gat_layer(x, src, dst, W1, b1, W2, b2, attn_l, attn_r, heads, alpha):
     a = (ex / den[dst]).astype(f32)                                   # :84
     out = np.zeros_like(ft2)
     np.add.at(out, dst, ft2[src] * a[:, :, None])                     # :66
+    if res is not None:
+        if isinstance(res, str):
+            resval = x.astype(f32)[:, None, :]                            # :74
+        else:
+            resval = (x @ res[0].T + res[1]).astype(f32).reshape(n, heads, -1)   # :72
+        out = (resval + out).astype(f32)                                  # :75
     return out
 
 
 def gat_forward(weights: dict, feats, src, dst, heads=(10, 10, 8, 5, 1), alpha=0.15, act_slope=0.01,
-                return_layers=False):
+                return_layers=False, residual=False):
     """GAT2.forward (gat2.py:137-149): LeakyReLU(0.01) between layers, sigmoid at the end
-    (train_skeleton_matching.py:54,148-149). weights: reference state_dict as numpy arrays."""
+    (train_skeleton_matching.py:54,148-149). weights: reference state_dict as numpy arrays.
+    residual=True: every layer after the first adds res_fc(h) when its weights exist, h itself otherwise (gat2.py:43-48)."""
     h = feats.astype(f32)
     layers = []
     L = len(heads)
     for l in range(L):
         p = lambda k: weights['layers.%d.%s' % (l, k)]
+        res = None
+        if residual and l > 0:
+            res = (p('res_fc.weight'), p('res_fc.bias')) if ('layers.%d.res_fc.weight' % l) in weights else 'identity'
         out = gat_layer(h, src, dst, p('fc1.weight'), p('fc1.bias'), p('fc2.weight'), p('fc2.bias'),
-                        p('attn_l'), p('attn_r'), heads[l], alpha)
+                        p('attn_l'), p('attn_r'), heads[l], alpha, res)
         layers.append(out)
         if l < L - 1:
             h = leaky(out.reshape(out.shape[0], -1), act_slope)       # :141-142

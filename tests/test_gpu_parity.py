@@ -159,6 +159,41 @@ def test_gat_scores_vs_reference(config, agg_impl):
     print('worst relative score error', config, worst)
 
 
+RESIDUAL_MODELS = {'resfc': ([40, 40, 40, 30], [10, 10, 8, 5], 3), 'ident': ([40, 40], [1, 4], 4)}   # make_golden_residual.py
+
+
+@pytest.mark.parametrize('dense', [False, True])
+@pytest.mark.parametrize('model', sorted(RESIDUAL_MODELS))
+def test_gat_residual_vs_reference(model, dense):
+    """GAT2 built with residual=True (gat2.py:43-48, 70-75; not the shipped configuration): res_fc projections on the tcgen05
+    GEMM, the sum inside the gather aggregation kernel (b200pose_gat_aggregate_res) - against the unmodified reference."""
+    import os
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    res = np.load(os.path.join(helpers.GOLDEN, 'golden_residual.npz'))
+    hidden, heads, seed = RESIDUAL_MODELS[model]
+    state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, seed, True, hidden, heads, residual=True)
+    pipe = get_pipe('panoptic')
+    layers = pipe.prepare_gat(state, residual=True)
+    assert any('res_w' in l or l.get('res_identity') for l in layers)
+    tags, pb, db = golden_batch('panoptic', ['p3', 'rag1'])
+    g = pipe.build_graph(db, with_coo=False)
+    x0 = pipeline_mod.Planes.from_f32(pipe.node_features_f32(db), pipe._stream()) if dense else None
+    scores, raws = pipe.gat_forward(db, g, x0=x0, dense_rows=dense, layers=layers, keep_layers=True)
+    scores = scores.cpu().numpy()
+    worst = 0.0
+    for b, tag in enumerate(tags):
+        n0, n1 = pb.node_off[b], pb.node_off[b + 1]
+        ref = res['%s/%s/scores' % (model, tag)]
+        rel = np.abs(scores[n0:n1] - ref) / np.abs(ref)
+        worst = max(worst, rel.max())
+        assert rel.max() <= SCORE_RTOL, (model, tag, rel.max())
+        for l in range(len(layers)):
+            want = res['%s/%s/layer%d' % (model, tag, l)]
+            a = raws[l][n0:n1].cpu().numpy().reshape(want.shape)
+            assert np.abs(a - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (model, tag, l)
+    print('worst relative score error, residual model', model, worst)
+
+
 @pytest.mark.parametrize('config', ['panoptic', 'arp3', 'arp6', 'pansub'])
 def test_aggregation_kernels_agree_bitwise(config):
     """The frame-resident kernels (shape-specialised product kernel and its generic form) and the gather kernel sum every

@@ -1,6 +1,7 @@
 """CPU: the oracle restatement (oracle/pose_oracle.py) against fixtures produced by the unmodified
 reference (tests/golden/make_golden.py). This is what pins the oracle."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -155,3 +156,27 @@ def test_encoder_triangulation_mlp(config):
                 assert np.abs(t - npz[tag + '/' + prefix + 'tri'][p]).max() < 1e-9, (tag, prefix, p)
             checked += len(persons)
     assert checked > 0
+
+
+RESIDUAL_MODELS = {'resfc': ([40, 40, 40, 30], [10, 10, 8, 5], 3), 'ident': ([40, 40], [1, 4], 4)}   # make_golden_residual.py
+
+
+@pytest.mark.parametrize('model', sorted(RESIDUAL_MODELS))
+def test_gat_residual_scores(model):
+    """GAT2 built with residual=True (gat2.py:43-48, 70-75): res_fc layers and the identity branch, against the unmodified
+    reference (tests/golden/make_golden_residual.py)."""
+    cfg, npz, meta, tabs = _tabs('panoptic')
+    res = np.load(os.path.join(helpers.GOLDEN, 'golden_residual.npz'))
+    hidden, heads, seed = RESIDUAL_MODELS[model]
+    state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, seed, True, hidden, heads, residual=True)
+    assert sorted(state) == list(res[model + '/keys'])
+    assert abs(float(sum(v.double().sum() for v in state.values())) - float(res[model + '/checksum'][0])) < 1e-6
+    w = helpers.np_state(state)
+    for tag in ('p3', 'rag1'):
+        scores, layers = O.gat_forward(w, npz[tag + '/feats'], npz[tag + '/src'], npz[tag + '/dst'], heads=tuple(heads) + (1,),
+                                       return_layers=True, residual=True)
+        ref = res['%s/%s/scores' % (model, tag)]
+        assert (np.abs(scores - ref) / np.abs(ref)).max() < 1e-4, (model, tag)
+        for l, a in enumerate(layers):
+            b = res['%s/%s/layer%d' % (model, tag, l)]
+            assert np.abs(a.reshape(b.shape) - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), (model, tag, l)
