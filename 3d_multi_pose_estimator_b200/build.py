@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, 'libb200pose.so')
 # loaded only by tests/test_gpu_parity.py::test_linear_kernels, never by the package
 LIB_SELFTEST = os.path.join(HERE, 'libb200pose_selftest.so')
 SELFTEST_SOURCES = ['common.cu', 'gemm.cu']
-SOURCES = ['common.cu', 'graph.cu', 'gat.cu', 'cluster.cu', 'lift.cu', 'gemm.cu', 'pack_json.cu']
+SOURCES = ['common.cu', 'graph.cu', 'gat.cu', 'cluster.cu', 'lift.cu', 'gemm.cu', 'pack_json.cu', 'train.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

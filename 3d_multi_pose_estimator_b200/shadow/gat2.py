@@ -2,13 +2,46 @@
 
 Same constructors, parameter names (state_dict keys `layers.{l}.{attn_l,attn_r,fc1.*,fc2.*[,res_fc.*]}`) and
 initialisation order; `forward` runs on the B200 kernels (split-bf16 tcgen05 projections + the fused
-edge-softmax/aggregation kernel) instead of DGL. Inference only: dropout must be 0. Residual layers (gat2.py:70-75, not the
+edge-softmax/aggregation kernel) instead of DGL; under autograd (grad enabled, trainable parameters) `loss.backward()` runs
+the hand-written backward of csrc/train.cu. Dropout must be 0. Residual layers (gat2.py:70-75, not the
 shipped configuration) add res_fc(h) - or h itself when the widths agree - inside the gather aggregation kernel.
 """
 import torch
 import torch.nn as nn
 
 import _b200pose_runtime as rt
+
+
+class _GatTrainFunction(torch.autograd.Function):
+    """GAT2.forward under autograd: the forward keeps its activations inside a GatGrad (3d_multi_pose_estimator_b200/train.py),
+    `loss.backward()` (train_skeleton_matching.py:181) lands here and the parameter gradients come from csrc/train.cu + the
+    tensor-core GEMM instead of torch's autograd graph of gat2.py:50-88."""
+
+    @staticmethod
+    def forward(ctx, inputs, holder, *params):
+        net, db, arrays, x0, sigmoid, names = holder
+        scores = net.forward(db, arrays, x0)
+        if not sigmoid:
+            raise NotImplementedError('B200 GAT2 training path: final_activation must be nn.Sigmoid (train_skeleton_matching.py:33)')
+        out = scores.clone()
+        ctx.holder = holder
+        ctx.save_for_backward(out)
+        return out.reshape(-1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.holder[0]
+        (scores,) = ctx.saved_tensors
+        n = scores.shape[0]
+        if net.cache is None or net.cache['N'] != n or net.cache_token is not ctx.holder:
+            raise RuntimeError('B200 GAT2: backward() after another forward of the same model (the drop-in keeps one set of activations)')
+        dl = net.buf.f('dlogit', n, 1)
+        d = dout.reshape(-1).contiguous().float()
+        rt.pipeline.check(net.L.b200pose_sigmoid_bwd(rt.pipeline.ptr(scores), rt.pipeline.ptr(d), n, rt.pipeline.ptr(dl), net.pipe._stream()),
+                          'sigmoid_bwd')
+        net.backward(dl)
+        grads = net.grads()
+        return (None, None) + tuple(grads[k].reshape(shape).clone() for k, shape in ctx.holder[5])
 
 
 class GraphAttention2(nn.Module):
@@ -89,12 +122,36 @@ class GAT2(nn.Module):
             self._prepared_key = key
         return self._prepared
 
+    def _forward_train(self, inputs, g, ctx):
+        """Grad mode with trainable parameters (the loop of train_skeleton_matching.py:163-184)."""
+        if any(lyr.residual for lyr in self.layers):
+            raise NotImplementedError('B200 GAT2: residual layers are inference-only')
+        named = list(self.named_parameters())
+        key = tuple((p.data_ptr(), p._version) for _, p in named)
+        net = self.__dict__.get('_grad_net')
+        rt.sync_live()
+        if net is None:
+            train_mod = rt.importlib.import_module('3d_multi_pose_estimator_b200.train')
+            net = train_mod.GatGrad(ctx, {k: v for k, v in self.state_dict().items()}, self.alpha, self.activation.negative_slope)
+            self.__dict__['_grad_net'] = net
+        elif key != self.__dict__.get('_grad_key'):
+            net.load_state({k: v for k, v in self.state_dict().items()})       # optimizer.step() changed them
+        self.__dict__['_grad_key'] = key
+        db, arrays = g._b200
+        ctx.wait_graph(arrays)
+        x0 = rt.pipeline.Planes.from_f32(inputs.to(ctx.device).float(), ctx._stream())
+        holder = (net, db, arrays, x0, self.final_activation is not None, [(k, tuple(p.shape)) for k, p in named])
+        net.cache_token = holder
+        return _GatTrainFunction.apply(inputs, holder, *[p for _, p in named])
+
     def forward(self, inputs, g):
         self.set_g(g)
         self._check_supported()
         ctx = rt.context()
         if not hasattr(g, '_b200'):
             raise TypeError('GAT2.forward needs a graph built by the B200 graph_generator drop-in')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(inputs, g, ctx)
         layers = self._weights(ctx)
         # the whole-frame submissions of the dataset drop-in use these weights from now on - when the model is the shipped
         # kind (the pipeline's activation constants) - and this call is answered from the submission of its own graph

@@ -233,7 +233,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
     ap.add_argument('--no-fuse2', action='store_true', help='A/B: run the last GAT layer as two projections instead of the fused launch')
-    ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch'],
+    ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch', 'train_step'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
     ap.add_argument('--latency-frames', type=int, default=200, help='single-frame calls timed for p50_frame_latency_ms')
@@ -251,6 +251,8 @@ def main():
         return triangulation_workload(args, rank, world, local_rank)
     if args.workload == 'train_batch':
         return train_batch_workload(args, rank, world, local_rank)
+    if args.workload == 'train_step':
+        return train_step_workload(args, rank, world, local_rank)
     pkg = importlib.import_module('3d_multi_pose_estimator_b200')
     cfg0 = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
     METRIC, workload = describe(args.config, cfg0, args.frames, args.persons)
@@ -757,6 +759,143 @@ def train_batch_workload(args, rank, world, local_rank):
             'kernels': kernels,
             'cpu_baseline': {'value': cpu, 'unit': 'graphs/s', 'cores': 1, 'kind': 'port',
                              'sample': '%d graphs in batches of 15 (the reference loader\'s batch size), one process' % n}}
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def train_step_workload(args, rank, world, local_rank):
+    """SURVEY.md 8f-3, the optimisation step: the loop body of skeleton_matching/train_skeleton_matching.py:163-184 - GAT2 forward
+    on a dgl.batch of process_training graphs, MSE loss on the edge-node scores, backward, Adam - as GatTrainer.step. One step =
+    one batch of --frames graphs (the reference's loader makes batches of 15, :42). Dataset synthesis and the graph build are
+    outside the timed region (the reference builds its datasets before the loop, :134-141, and its collate runs in the loader)."""
+    import random
+    import torch
+    pkg = importlib.import_module('3d_multi_pose_estimator_b200')
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    pm = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+    tg = importlib.import_module('3d_multi_pose_estimator_b200.training_graphs')
+    tr = importlib.import_module('3d_multi_pose_estimator_b200.train')
+    W = importlib.import_module('3d_multi_pose_estimator_b200.weights')
+    cfg = pkg.CameraConfig.from_npz(os.path.join(GOLDEN, 'cameras_%s.npz' % args.config))
+    G = args.frames
+    n_files, per_file = 4, 24
+    files = [[synth.make_frame(cfg, 7000 + 100 * f + t, 1, drop_joint_p=0.1, drop_view_p=0.1) for t in range(per_file)] for f in range(n_files)]
+    random.seed(rank)
+    inputs, indices = tg.load_inputs(files, 'train', cfg.used_pe_names, random)
+    built = []
+    for mp in tg.sample_sets(inputs, indices, [0.8, 0.6, 0.7, 0.5], 10 ** 9, random):
+        b = tg.training_graph_inputs(mp, cfg)
+        if b is not None:
+            built.append(b)
+        if len(built) >= min(G, 256):
+            break
+    members = [built[i % len(built)] for i in range(G)]
+    pb, pairs = tg.batch_packed([(m[0], m[1]) for m in members])
+    idx, off = [], 0
+    for m in members:
+        H, N = m[0].n_heads, int(m[0].node_off[-1])
+        idx.append(np.arange(off + H, off + N))
+        off += N
+    idx = np.concatenate(idx).astype(np.int32)
+    labels = np.concatenate([m[2].ravel() for m in members]).astype(np.float32)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    state = W.make_gat_state(cfg.n_features_sm, 0, True)
+    pipe = pm.PosePipeline(cfg, None, None, device=dev)
+    trainer = tr.GatTrainer(pipe, state)
+    hb = pm.HostBatch(pb)
+    db = hb.to_device(dev)
+    g = pipe.build_graph_pairs(db, torch.from_numpy(pairs).to(dev), with_coo=False)
+    d_idx, d_lab = torch.from_numpy(idx).to(dev), torch.from_numpy(labels).to(dev)
+    x0 = trainer.features(db)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    warmup = max(3, args.warmup)
+    losses = []
+    for _ in range(warmup):
+        losses.append(float(trainer.step(db, g, d_idx, d_lab, x0=x0).item()))
+    torch.cuda.synchronize()
+    l0 = trainer.net.launches + pipe.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_losses = []
+    for a, b in ev:
+        flush.fill_(1); a.record(); dev_losses.append(trainer.step(db, g, d_idx, d_lab, x0=x0).clone()); b.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = (trainer.net.launches + pipe.launches - l0) // args.steps
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    losses += [float(x.item()) for x in dev_losses]
+    # end to end: host batch (packed skeletons, edge-node list, indices, labels) -> device -> step -> loss on the host
+    h_pairs, h_idx, h_lab = torch.from_numpy(pairs).pin_memory(), torch.from_numpy(idx).pin_memory(), torch.from_numpy(labels).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2 = hb.to_device(dev)
+        g2 = pipe.build_graph_pairs(d2, h_pairs.to(dev, non_blocking=True), with_coo=False)
+        host_loss = float(trainer.step(d2, g2, h_idx.to(dev, non_blocking=True), h_lab.to(dev, non_blocking=True)).item())
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    # CPU port of the same step (oracle/train_oracle.py: numpy forward, hand-written backward, Adam) on batches of the same size
+    from oracle import pose_oracle as O
+    from oracle import train_oracle as TO
+    tabs = O.CameraTables(cfg)
+    random.seed(rank)
+    oin, oidx = O.load_training_inputs(files, 'train', cfg.used_pe_names, random)
+    ogs = []
+    for mp in O.training_samples(oin, oidx, [0.8, 0.6, 0.7, 0.5], 10 ** 9, random):
+        og = O.build_training_graph(mp, tabs)
+        if og is not None:
+            ogs.append(og)
+        if len(ogs) >= min(G, 64):
+            break
+    ow = {k: v.numpy().copy() for k, v in state.items()}
+    oadam = TO.Adam(ow)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < min(args.cpu_budget, 15.0) or n == 0:
+        mem = [ogs[(n * G + i) % len(ogs)] for i in range(G)]
+        bg = O.batch_graphs(mem)
+        oi, o = [], 0
+        for m in mem:
+            oi.append(np.asarray(m['indices']) + o)
+            o += m['n_nodes']
+        ol, _, ograds = TO.forward_backward(ow, bg['feats'], bg['src'], bg['dst'], np.concatenate(oi), np.concatenate([m['labels'].ravel() for m in mem]))
+        oadam.step(ow, ograds)
+        n += 1
+    cpu = n * G / (time.perf_counter() - t0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    # executed tensor-core work of a step: forward 2 N (din^2 + din n2), backward dW1 + dW2 + dh2 (+ dx above layer 0), x3 split MMAs
+    N = pb.n_nodes
+    flops = 0
+    for l, (din, H, D) in enumerate(W.gat_layer_dims(cfg.n_features_sm)):
+        hd, n2 = H * D, H * D + 2 * H
+        flops += 2 * N * (din * din + din * n2)                      # forward
+        flops += 2 * N * (hd * din + hd * din + din * din)           # dW2, dh2, dW1
+        if l > 0:
+            flops += 2 * N * din * din                               # dx
+    tc_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+    line = {'metric': 'graphs/sec (process_training graphs, one optimisation step per %d-graph batch: forward + MSE + backward + Adam)' % G,
+            'value': G / ms * 1e3, 'unit': 'graphs/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate; fp32 optimiser state', 'data': 'synthetic',
+            'config': {'workload': 'training step: %d process_training graphs (%d nodes, %d edges, %d labelled edge-nodes) merged block-diagonally; '
+                                   'GAT2 forward, MSE, backward, Adam (train_skeleton_matching.py:163-184)' % (G, pb.n_nodes, pb.n_edges, len(idx)),
+                       'camera_config': args.config, 'graphs_per_step': G, 'l2': 'L2 flushed (256 MiB write) between timed iterations'},
+            'e2e': {'value': G / e2e_ms * 1e3, 'unit': 'graphs/s',
+                    'h2d_bytes_per_step': int(hb.nbytes() + h_pairs.numel() * 4 + h_idx.numel() * 4 + h_lab.numel() * 4),
+                    'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms, 'includes': 'graph build from the edge-node list and feature synthesis'},
+            'gpu_launches': launches, 'clocks': sampler.summary(),
+            'roofline': {'kernel': 'training step (all launches)', 'bound': 'tensor', 'achieved': 3 * flops / ms / 1e9, 'peak': tc_peak, 'unit': 'TFLOP/s',
+                         'frac': 3 * flops / ms / 1e9 / tc_peak, 'traffic': None,
+                         'note': 'a 15-graph batch is launch-latency bound (%d dependent launches per step); the fraction is of the whole step' % launches,
+                         'peak_source': 'measured' if peaks else 'fallback'},
+            'loss_first_last': [losses[0], losses[-1]],
+            'cpu_baseline': {'value': cpu, 'unit': 'graphs/s', 'cores': 1, 'kind': 'port',
+                             'sample': '%d optimisation steps on batches of %d graphs (numpy restatement oracle/train_oracle.py), one process' % (n, G)}}
     if rank == 0:
         print(json.dumps(line))
 

@@ -277,6 +277,50 @@ int b200pose_pack_record(int32_t n_frames, int32_t n_cameras, int32_t n_out,
                          int32_t head_base, int32_t* record, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training side (after the forward): the backward pass and the optimiser step of the skeleton-matching
+ * loop, skeleton_matching/train_skeleton_matching.py:163-184. The reference has no hand-written backward - torch autograd
+ * differentiates gat2.py:50-88, 137-149 - so these entry points replace `loss.backward()` / `optimizer.step()` for the GAT.
+ * The projections' gradients (dW = G^T X, dX = G W) run on b200pose_linear with the transposed planes produced below.
+ * Everything is deterministic (no atomics).
+ * ------------------------------------------------------------------------------------------- */
+/* Backward of b200pose_gat_aggregate (gat2.py:59-66, 78-88: attention logits, edge softmax, weighted sum) for one layer.
+ *   z [N, ldz] = [ft2 | a1 | a2] of the forward, dout [N, ld_dout] = gradient of the layer output (before the inter-layer
+ *   activation), attn_l / attn_r [heads*dim] fp32 (gat2.py:35-36), stats [N * heads * 3] fp32 scratch.
+ *   dz [N, ld_dz] = [d ft2 (incl. the a1 / a2 paths through gat2.py:57-58) | d a1 | d a2].
+ * The graph must be symmetric (v in row(u) <=> u in row(v)), which every graph of graph_generator.py:627-656 is. */
+int b200pose_gat_aggregate_bwd(int32_t n_nodes, const int32_t* row_ptr, const int32_t* col,
+                               const float* z, int32_t ldz, int32_t heads, int32_t dim, float alpha,
+                               const float* dout, int32_t ld_dout, const float* attn_l, const float* attn_r,
+                               float* stats, float* dz, int32_t ld_dz, void* stream);
+/* x = g * (mask_hi ? LeakyReLU'_slope(mask) : 1) -> out_f32 (may alias g) and/or planes [rows, ld_p] and/or TRANSPOSED
+ * planes [cols, ld_t] (padding columns up to the next multiple of 64 zero: the K padding of b200pose_linear). mask_hi = hi plane of the activated tensor (same sign as its input;
+ * autograd: nn.LeakyReLU backward, gat2.py:54, 141-142). */
+int b200pose_grad_planes(const float* g, int32_t rows, int32_t cols, int32_t ld_g,
+                         const uint16_t* mask_hi, int32_t ld_mask, float slope,
+                         float* out_f32, int32_t ld_out,
+                         uint16_t* p_hi, uint16_t* p_lo, int32_t ld_p,
+                         uint16_t* t_hi, uint16_t* t_lo, int32_t ld_t, void* stream);
+/* planes [rows, ld] -> planes [cols, ld_t] of the transposed matrix (columns [rows, round_up(rows, 64)) zero) */
+int b200pose_transpose_planes(const uint16_t* hi, const uint16_t* lo, int32_t rows, int32_t cols, int32_t ld,
+                              uint16_t* t_hi, uint16_t* t_lo, int32_t ld_t, void* stream);
+/* out[j] = sum_r x[r, j] * (w ? w[r, j / group] : 1): bias gradients; d attn[h, d] = sum_u d a[u, h] ft2[u, h, d] */
+int b200pose_colsum(const float* x, int32_t rows, int32_t cols, int32_t ld, const float* w, int32_t ld_w, int32_t group,
+                    float* out, void* stream);
+/* w2e [heads*dim + 2*heads, ld_w2e] = [W2 ; sum_d attn_l[h,d] W2[h*dim+d, :] ; same with attn_r], b2e likewise (gat2.py:55-58
+ * as one projection; the inference path does this fold once on the host, a training step after every parameter update) */
+int b200pose_fold_attention(const float* w2, int32_t ld_w2, const float* b2, const float* attn_l, const float* attn_r,
+                            int32_t heads, int32_t dim, int32_t din, float* w2e, int32_t ld_w2e, float* b2e, void* stream);
+/* nn.MSELoss on scores[idx[i]] vs labels[i] (train_skeleton_matching.py:37, 174-178) and its gradient through the final
+ * sigmoid: dlogit [n_nodes] (zero outside idx; idx entries distinct). loss / dlogit may be null. */
+int b200pose_mse_sigmoid(const float* scores, int32_t n_nodes, const int32_t* idx, const float* labels, int32_t m,
+                         float* loss, float* dlogit, void* stream);
+/* dlogit = dscores * s * (1 - s): the final sigmoid when the loss is computed by the caller (autograd drop-in) */
+int b200pose_sigmoid_bwd(const float* scores, const float* dscores, int32_t n, float* dlogit, void* stream);
+/* torch.optim.Adam (train_skeleton_matching.py:150), single-tensor form, over one flat parameter buffer; step counts from 1 */
+int b200pose_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-side frame packer (no GPU work): the reference's frame JSON - a list of frames
  * {camera: [json.dumps([skeleton, ...]), timestamp, ...]} as read by test/metrics_from_model.py:117-191, or one such
  * frame - parsed in parallel into the packed skeleton batch above. Replaces json.loads + the per-joint Python loops of

@@ -9,6 +9,7 @@ cfg, frames = bench.load_workload('panoptic', 40, 4, 0)
 gat, mlp_state = bench.load_weights('panoptic', cfg)
 mods = dropin_env.activate(cfg)
 dev = torch.device('cuda')
+torch.set_grad_enabled(False)   # test/metrics_from_model.py:54
 model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(), torch.nn.Sigmoid(), 0., 0., 0.15, False, bias=True)
 model.load_state_dict(gat); model = model.to(dev)
 mlp = mods['mlp'].PoseEstimatorMLP(input_dimensions=cfg.n_cameras * 18 * 14, output_dimensions=54)

@@ -19,6 +19,7 @@ def measure(cfg, frames, gat, mlp_state, warm=8):
     import torch
     import dropin_env
     T = collections.OrderedDict()
+    torch.set_grad_enabled(False)                                # test/metrics_from_model.py:54
     with contextlib.redirect_stdout(io.StringIO()):             # the reference's modules print while they work
         mods = dropin_env.activate(cfg)
         dev = torch.device('cuda')

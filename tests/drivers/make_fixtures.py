@@ -68,6 +68,23 @@ def make(workdir, config='panoptic'):
     return dict(test_file=test_file, viewer_file=viewer_file, single_files=singles, frames=frames, tm_dir=workdir, tm_file=tm_file, models=models, n_frames=len(frames))
 
 
+def make_training_files(workdir, config='panoptic'):
+    """Single-person recordings for skeleton_matching/train_skeleton_matching.py (each file one individual, a few frames with
+    some views missing): two for --trainset, one each for --devset / --testset. Small on purpose: the script always runs its
+    100 epochs (:39), here of one batch each."""
+    import helpers
+    synth = importlib.import_module('3d_multi_pose_estimator_b200.synth')
+    cfg, _, _ = helpers.load_golden(config)
+    os.makedirs(workdir, exist_ok=True)
+    paths = []
+    for k in range(4):
+        one = [synth.make_frame(cfg, 600 + 40 * k + t, 1, drop_joint_p=0.1 * (k % 2), drop_view_p=0.25) for t in range(3)]
+        path = os.path.join(workdir, 'train_single_%d.json' % k)
+        json.dump(one, open(path, 'w'))
+        paths.append(path)
+    return dict(trainset=paths[:2], devset=paths[2:3], testset=paths[3:4])
+
+
 if __name__ == '__main__':
     out = make(sys.argv[1] if len(sys.argv) > 1 else '/tmp/b200pose_driver_fixtures')
     out.pop('frames')

@@ -15,6 +15,17 @@ from oracle import pose_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _grad_disabled_like_the_drivers():
+    """Every driver these tests restate starts with torch.set_grad_enabled(False) (test/metrics_from_model.py:54,
+    test/sm_metrics_without_gt.py:43, ...); with grad enabled the drop-in GAT2 - like the reference's - returns a tensor that
+    requires grad (the training path)."""
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)
+
+
 def run_frame(mods, cfg, model, mlp, frame):
     """One pass of the reference driver's loop body. Returns None when the frame yields no graph."""
     gg, smu, ds = mods['graph_generator'], mods['skeleton_matching_utils'], mods['pose_estimator_dataset_from_json']

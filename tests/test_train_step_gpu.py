@@ -1,0 +1,192 @@
+"""GPU: the optimisation step of the skeleton-matching training loop (SURVEY.md 8f-3 after the forward) on the B200 path.
+
+* the backward kernels (csrc/train.cu + the tensor-core GEMM on transposed planes) against the CPU restatement
+  oracle/train_oracle.py on a batch of golden frames;
+* the reference's own loop body (skeleton_matching/train_skeleton_matching.py:163-184: zero_grad, forward, MSELoss,
+  loss.backward(), torch.optim.Adam.step()) run on the drop-in modules, against the goldens the UNMODIFIED reference produced
+  under torch autograd (tests/golden/make_golden_train_step.py): losses, every gradient tensor, the parameters after 3 steps;
+* the native trainer (GatTrainer.step: loss + Adam kernels of csrc/train.cu) against the same goldens.
+"""
+import importlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import dropin_env
+import helpers
+from test_train_oracle_cpu import check_digest, check_parameters, sample
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = helpers.GOLDEN
+# against the reference's autograd on the small golden batches (~100 nodes): a LeakyReLU mask flipped by the forward's ~1e-5
+# difference (see test_backward_kernels_vs_oracle) weighs 1/N of a column sum, so single gradient elements may differ by ~1e-2 of
+# the tensor maximum; the bulk and the loss trajectory (which the updated parameters drive) agree far more tightly
+GRAD_RTOL, GRAD_L2TOL, LOSS_RTOL = 2e-2, 2e-2, 1e-4
+pipeline_mod = importlib.import_module('3d_multi_pose_estimator_b200.pipeline')
+pack_mod = importlib.import_module('3d_multi_pose_estimator_b200.pack')
+train_mod = importlib.import_module('3d_multi_pose_estimator_b200.train')
+
+
+def collate(batch, dgl, device):
+    """train_skeleton_matching.py:63-84"""
+    graphs = [batch[0][0]]
+    batched_labels = batch[0][1]
+    batched_indices = batch[0][2]
+    total_nodes = batch[0][0].number_of_nodes()
+    for graph, labels, indices, _ in batch[1:]:
+        graphs.append(graph)
+        batched_labels = torch.cat([batched_labels, labels], dim=0)
+        batched_indices = torch.cat([batched_indices, indices + total_nodes], dim=0)
+        total_nodes += graph.number_of_nodes()
+    return dgl.batch(graphs).to(torch.device(device)), batched_labels, batched_indices
+
+
+def test_backward_kernels_vs_oracle():
+    """All golden Panoptic frames as one batch (closed-form test-mode graphs, ~1.3 k nodes), random labels: loss, scores and
+    every gradient tensor of one forward + backward against oracle/train_oracle.py; two runs are bit-identical."""
+    from oracle import pose_oracle as O
+    from oracle import train_oracle as TO
+    cfg, npz, meta = helpers.load_golden('panoptic')
+    tags = helpers.graph_cases('panoptic')
+    frames = [{c: meta['frames'][t][c] for c in meta['frames'][t] if json.loads(meta['frames'][t][c][0])} for t in tags]
+    pb = pack_mod.pack_frames(frames, cfg)
+    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+    pipe = pipeline_mod.PosePipeline(cfg, None, None, device='cuda:0')
+    g = pipe.build_graph(db, with_coo=True)
+    state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, 11, True)
+    trainer = train_mod.GatTrainer(pipe, state)
+    node_off, head_off = pb.node_off, pb.head_off
+    idx = np.concatenate([np.arange(node_off[b] + (head_off[b + 1] - head_off[b]), node_off[b + 1]) for b in range(pb.n_frames)])
+    rng = np.random.default_rng(5)
+    labels = (rng.random(len(idx)) < 0.3).astype(np.float32)
+    d_idx = torch.from_numpy(idx.astype(np.int32)).cuda()
+    d_lab = torch.from_numpy(labels).cuda()
+    loss = float(trainer.step(db, g, d_idx, d_lab, update=False).item())
+    grads = {k: v.clone().cpu().numpy() for k, v in trainer.net.grads().items()}
+    scores = trainer.last_scores.cpu().numpy().copy()
+    feats = pipe.node_features_f32(db).cpu().numpy()
+    row_ptr, col = g.row_ptr.cpu().numpy(), g.col[: db.n_edges].cpu().numpy()       # CSR by destination, global node ids (the COO
+    src, dst = col, np.repeat(np.arange(db.n_nodes), np.diff(row_ptr))                # arrays hold frame-local ids)
+    w = helpers.np_state(state)
+    oloss, oscores, ograds = TO.forward_backward(w, feats, src, dst, idx, labels)
+    assert abs(loss - oloss) <= 1e-5 * oloss, (loss, oloss)
+    assert (np.abs(scores - oscores) / np.abs(oscores)).max() <= 1e-4
+    # (1) the backward kernels in isolation: the oracle's backward run on the forward state the DEVICE kept (same activation
+    # masks, same attention weights), from the device's own d loss / d logit: what remains is the arithmetic of the backward
+    N = db.n_nodes
+    cl = trainer.net.cache['layers']
+    caches, raws = TO.caches_from_device(w, [c['x'].to_f32()[:N].cpu().numpy() for c in cl], [c['h2'].to_f32()[:N].cpu().numpy() for c in cl],
+                                         [c['z'][:N].cpu().numpy() for c in cl], src, dst)
+    dl = trainer.net.buf.f('dlogit', N, 1)[:N, 0].cpu().numpy().reshape(-1, 1, 1)
+    dgrads = TO.backward(w, caches, raws, src.astype(np.int64), dst.astype(np.int64), dl)
+    worst_k = 0.0
+    for k, og in dgrads.items():
+        got = grads[k].reshape(og.shape)
+        scale, err = np.abs(og).max(), np.abs(got - og).max()
+        assert err <= 1e-4 * scale or err <= 1e-9, ('backward kernels', k, err, scale)
+        worst_k = max(worst_k, err / scale if err > 1e-9 else 0.0)
+    # (2) end to end against the fp32 restatement. The forward's ~1e-5 differences (split-bf16 GEMMs) flip the LeakyReLU mask
+    # of the few pre-activations that sit within that distance of zero; each flip changes one row's contribution by a factor
+    # 1/alpha, so single elements differ by up to ~1e-3 of the tensor maximum while the bulk agrees to ~1e-4
+    worst, worst_l2 = 0.0, 0.0
+    for k, og in ograds.items():
+        got = grads[k].reshape(og.shape)
+        scale, err = np.abs(og).max(), np.abs(got - og).max()
+        l2 = np.linalg.norm((got - og).ravel().astype(np.float64)) / max(np.linalg.norm(og.ravel().astype(np.float64)), 1e-30)
+        assert err <= 5e-3 * scale or err <= 1e-9, ('end to end', k, err, scale)
+        assert l2 <= 2e-3 or err <= 1e-9, ('end to end, L2', k, l2)
+        if err > 1e-9:
+            worst, worst_l2 = max(worst, err / scale), max(worst_l2, l2)
+    print('N = %d nodes, M = %d edge-nodes; backward kernels on the device forward state: worst %.3g of the tensor maximum; end to end vs '
+          'the fp32 restatement: worst %.3g, worst relative L2 %.3g' % (N, len(idx), worst_k, worst, worst_l2))
+    trainer.step(db, g, d_idx, d_lab, update=False)
+    again = {k: v.clone().cpu().numpy() for k, v in trainer.net.grads().items()}
+    assert all(np.array_equal(grads[k], again[k]) for k in grads), 'the backward pass is not reproducible run to run'
+
+
+def _dataset(mods, cfg, tmp_path):
+    gm = json.load(open(os.path.join(GOLDEN, 'golden_training_panoptic.json')))
+    paths = []
+    for i, frames in enumerate(gm['files']):
+        p = tmp_path / ('single_%d.json' % i)
+        p.write_text(json.dumps(frames))
+        paths.append(str(p))
+    random.seed(gm['seed'])
+    return mods['graph_generator'].MergedMultipleHumansDataset(paths, gm['probabilities'], limit=gm['limit'], mode='train', alt='3',
+                                                               raw_dir='.', verbose=False, debug=True)
+
+
+def test_reference_training_loop_on_dropin(tmp_path):
+    """The loop body of train_skeleton_matching.py:163-184, as written there, on the drop-in modules."""
+    cfg, _, _ = helpers.load_golden('panoptic')
+    gz = np.load(os.path.join(GOLDEN, 'golden_train_step.npz'))
+    mods = dropin_env.activate(cfg)
+    dgl = importlib.import_module('dgl')
+    device = torch.device('cuda')
+    ds = _dataset(mods, cfg, tmp_path)
+    with torch.enable_grad():
+        torch.manual_seed(int(gz['gat_seed'][0]))
+        model = mods['gat2'].GAT2(None, 5, cfg.n_features_sm, 1, [40, 40, 40, 30], [10, 10, 8, 5], torch.nn.LeakyReLU(), torch.nn.Sigmoid(),
+                                  0., 0., 0.15, False, bias=True)
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1.e-20)
+        model = model.to(device)
+        loss_function = torch.nn.MSELoss()
+        model.train()
+        worst = 0.0
+        for step in range(int(gz['steps'][0])):
+            pre = 'step%d/' % step
+            subgraph, labels, indices = collate([ds[int(i)] for i in gz[pre + 'members']], dgl, device)
+            assert np.array_equal(indices.numpy().ravel(), gz[pre + 'indices'])
+            optimizer.zero_grad()
+            feats = subgraph.ndata['h'].to(device)
+            model.g = subgraph
+            for layer in model.layers:
+                layer.g = subgraph
+            outputs = torch.squeeze(model(feats.float(), subgraph))
+            filtered_output = outputs[indices]
+            loss = loss_function(filtered_output.float().to(device), labels.float().to(device))
+            loss.backward()
+            ref_loss = float(gz[pre + 'loss'][0])
+            assert abs(loss.item() - ref_loss) <= LOSS_RTOL * ref_loss, (step, loss.item(), ref_loss)
+            sc = outputs.detach().cpu().numpy()
+            assert (np.abs(sc - gz[pre + 'scores']) / np.abs(gz[pre + 'scores'])).max() <= 1e-4
+            for k, p in model.named_parameters():
+                assert p.grad is not None and p.grad.shape == p.shape, k
+                worst = max(worst, check_digest('grad %s step %d' % (k, step), p.grad.cpu().numpy(), gz, pre + 'grad/' + k, GRAD_RTOL, GRAD_L2TOL, atol=1e-7))
+            optimizer.step()
+        far = check_parameters({k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}, gz, 1e-4, int(gz['steps'][0]))
+        print('worst gradient error relative to the tensor maximum:', worst, '; parameters after the steps: fraction further than 2.5e-5, worst:', far)
+        # evaluation mode of the same script (:86-109): no_grad forward on the inference path with the trained parameters
+        model.eval()
+        with torch.no_grad():
+            out_eval = torch.squeeze(model(feats.float(), subgraph))
+        assert out_eval.grad_fn is None and out_eval.shape == outputs.shape
+
+
+def test_native_trainer_against_reference_golden(tmp_path):
+    """GatTrainer.step (MSE + sigmoid gradient, backward, Adam - all on csrc/train.cu) over the golden steps."""
+    cfg, _, _ = helpers.load_golden('panoptic')
+    gz = np.load(os.path.join(GOLDEN, 'golden_train_step.npz'))
+    mods = dropin_env.activate(cfg)
+    dgl = importlib.import_module('dgl')
+    ds = _dataset(mods, cfg, tmp_path)
+    ctx = mods['rt'].context()
+    state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, int(gz['gat_seed'][0]), True)
+    trainer = train_mod.GatTrainer(ctx, state, lr=1e-4, weight_decay=1e-20)
+    for step in range(int(gz['steps'][0])):
+        pre = 'step%d/' % step
+        subgraph, labels, indices = collate([ds[int(i)] for i in gz[pre + 'members']], dgl, 'cuda')
+        db, arrays = subgraph._b200
+        loss = trainer.step(db, arrays, indices.reshape(-1).to(torch.int32).cuda(), labels.reshape(-1).float().cuda())
+        ref_loss = float(gz[pre + 'loss'][0])
+        assert abs(float(loss.item()) - ref_loss) <= LOSS_RTOL * ref_loss, (step, float(loss.item()), ref_loss)
+        for k, g in trainer.net.grads().items():
+            check_digest('grad %s step %d' % (k, step), g.cpu().numpy(), gz, pre + 'grad/' + k, GRAD_RTOL, GRAD_L2TOL, atol=1e-7)
+    far = check_parameters({k: v.cpu().numpy() for k, v in trainer.net.state_dict().items()}, gz, 1e-4, int(gz['steps'][0]))
+    print('parameters after the steps: fraction further than 2.5e-5 from the reference, worst:', far)
+    assert trainer.t == int(gz['steps'][0])

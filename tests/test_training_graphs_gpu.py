@@ -17,6 +17,17 @@ import helpers
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _grad_disabled_like_the_drivers():
+    """Every driver these tests restate starts with torch.set_grad_enabled(False) (test/metrics_from_model.py:54,
+    test/sm_metrics_without_gt.py:43, ...); with grad enabled the drop-in GAT2 - like the reference's - returns a tensor that
+    requires grad (the training path)."""
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
