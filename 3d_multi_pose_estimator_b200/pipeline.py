@@ -943,14 +943,21 @@ class PosePipeline:
             turn[0] += 1
             return sets[turn[0] % 3]
 
-        def enqueue(hb, db, ev):
-            """Compute of one batch + the read-back of its person counts; nothing here waits for the GPU."""
+        def enqueue_compute(hb, db, ev):
+            """Compute of one batch; nothing here waits for the GPU."""
             cur.wait_event(ev)
             res = self.infer(db, sync=False)
             if res.get('n_persons_dev') is not None and 'joints' in res:
                 res['joints'] = res['joints'].clone()            # 'mlp_out' is a shared workspace: the next batch overwrites it
             done = torch.cuda.Event()
             done.record(cur)
+            return hb, res, done
+
+        def enqueue_counts(hb, res, done):
+            """Read-back of the batch's per-frame person counts, behind its compute, on the read-back stream. Enqueued only
+            AFTER the previous batch's rows have been read back (finalize): the read-back stream runs in order, so rows
+            queued behind this wait would not move - and the host, which waits for them, would not enqueue the next batch -
+            until this batch's compute has finished."""
             bufs = result_set(hb)
             with torch.cuda.stream(ds):
                 ds.wait_event(done)
@@ -982,9 +989,10 @@ class PosePipeline:
         while nxt is not None:
             hb, db, ev = nxt
             nxt = prefetch()                                   # the next batch's copy is in flight during this compute
-            job = enqueue(hb, db, ev)
-            if pending is not None:
-                yield finalize(*pending)                       # batch i-1 is read back while batch i computes
-            pending = job
+            job = enqueue_compute(hb, db, ev)
+            out = finalize(*pending) if pending is not None else None    # batch i-1 is read back while batch i computes
+            pending = enqueue_counts(*job)
+            if out is not None:
+                yield out
         if pending is not None:
             yield finalize(*pending)
