@@ -298,6 +298,33 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ theta, co
     theta[i] = th - step_size * (mi / denom);
 }
 
+// Adam with the step count on the device (so a whole optimisation step can be replayed as a CUDA graph): one thread advances
+// the counter and writes step_size = lr / (1 - b1^t) and sqrt(1 - b2^t) for the element kernel that follows
+__global__ void adam_scalars_kernel(int* __restrict__ step, float lr, float b1, float b2, float* __restrict__ scal)
+{
+    const int t = *step + 1;
+    *step = t;
+    scal[0] = (float)((double)lr / (1.0 - pow((double)b1, (double)t)));
+    scal[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+}
+
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                                                      float* __restrict__ v, long long n, float b1, float b2, float eps, float wd,
+                                                      const float* __restrict__ scal)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float step_size = scal[0], bc2_sqrt = scal[1];
+    float g = grad[i];
+    const float th = theta[i];
+    if (wd != 0.f) g = fmaf(wd, th, g);
+    float mi = m[i], vi = v[i];
+    mi = mi + (g - mi) * (1.f - b1);
+    vi = vi * b2 + (1.f - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    theta[i] = th - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -411,6 +438,19 @@ B2_EXPORT int b200pose_adam_step(float* theta, const float* grad, float* m, floa
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     adam_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, (long long)n, beta1, beta2, eps, weight_decay,
                                                                           (float)((double)lr / bc1), (float)sqrt(bc2));
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+B2_EXPORT int b200pose_adam_step_dev(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                     float eps, float weight_decay, int32_t* step_dev, float* scalars_dev, void* stream)
+{
+    B2_CHECK_ARG(theta && grad && m && v && n >= 0 && step_dev && scalars_dev, "adam_step_dev: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    adam_scalars_kernel<<<1, 1, 0, st>>>(step_dev, lr, beta1, beta2, scalars_dev);
+    B2_CHECK_LAUNCH();
+    if (n == 0) return B200POSE_OK;
+    adam_dev_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(theta, grad, m, v, (long long)n, beta1, beta2, eps, weight_decay, scalars_dev);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

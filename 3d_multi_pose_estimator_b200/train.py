@@ -35,6 +35,7 @@ class _Buf:
         self.device = device
         self.f32 = {}
         self.planes = {}
+        self.gen = 0            # bumped on every (re)allocation: captured CUDA graphs hold the old addresses
 
     def f(self, tag, rows, cols):
         t = self.f32.get(tag)
@@ -42,6 +43,7 @@ class _Buf:
             cap = max(rows, int(t.shape[0] * 1.25) if t is not None and t.shape[1] == cols else rows, 1)
             t = torch.zeros((cap, cols), dtype=torch.float32, device=self.device)
             self.f32[tag] = t
+            self.gen += 1
         return t
 
     def p(self, tag, rows, cols) -> Planes:
@@ -54,6 +56,7 @@ class _Buf:
                     ws.ld if ws is not None else 0)
             ws = Planes(r, c, self.device)
             self.planes[tag] = ws
+            self.gen += 1
         view = Planes.__new__(Planes)
         view.rows, view.cols, view.ld, view.hi, view.lo = rows, cols, ws.ld, ws.hi, ws.lo
         return view
@@ -242,7 +245,11 @@ class GatGrad:
 
 
 class GatTrainer:
-    """One `step()` = the loop body of train_skeleton_matching.py:166-181 on a batch of training graphs."""
+    """One `step()` = the loop body of train_skeleton_matching.py:166-181 on a batch of training graphs.
+
+    `step()` enqueues the ~125 launches of a step one by one; `step_captured()` replays the same step as ONE CUDA graph per batch
+    shape (the reference's DataLoader does not shuffle, :143, so every epoch presents the same batches): the inputs are copied
+    into the capture's static buffers, the Adam step count lives on the device."""
 
     def __init__(self, pipe: PosePipeline, state: Dict[str, torch.Tensor], lr: float = 1e-4, betas: Sequence[float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-20, alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE):
@@ -252,20 +259,19 @@ class GatTrainer:
         dev = pipe.device
         self.m = torch.zeros(self.net.n_flat, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.net.n_flat, dtype=torch.float32, device=dev)
-        self.t = 0
+        self.t = 0                                                            # host mirror of the device-side step count
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.last_scores = None
+        self._graphs = {}
 
     def features(self, db) -> Planes:
         """ndata['h'] of the batch as GEMM operand planes (the reference feeds the dense N x F matrix, :171-176)"""
         return Planes.from_f32(self.pipe.node_features_f32(db), self.pipe._stream())
 
-    def step(self, db, g, indices: torch.Tensor, labels: torch.Tensor, x0: Optional[Planes] = None, update: bool = True):
-        """indices [M] int32 (edge-node ids of the batched graph), labels [M] fp32, both on the device. Returns the loss as a
-        device scalar (read it with .item() when it is needed: the step itself does not synchronise)."""
+    def _enqueue(self, db, g, indices, labels, x0, update):
         net, L, s = self.net, self.pipe.L, self.pipe._stream()
-        if x0 is None:
-            x0 = self.features(db)
         scores = net.forward(db, g, x0)
         self.last_scores = scores
         N, M = db.n_nodes, int(indices.shape[0])
@@ -274,9 +280,67 @@ class GatTrainer:
         net.backward(dlogit)
         net.launches += 1
         if update:
-            self.t += 1
-            check(L.b200pose_adam_step(ptr(net.theta), ptr(net.grad), ptr(self.m), ptr(self.v), net.n_flat, self.lr, self.betas[0],
-                                       self.betas[1], self.eps, self.weight_decay, self.t, s), 'adam_step')
+            check(L.b200pose_adam_step_dev(ptr(net.theta), ptr(net.grad), ptr(self.m), ptr(self.v), net.n_flat, self.lr, self.betas[0],
+                                           self.betas[1], self.eps, self.weight_decay, ptr(self.t_dev), ptr(self.adam_scalars), s), 'adam_step_dev')
             net.refresh_weights()
-            net.launches += 1
+            net.launches += 2
+
+    def step(self, db, g, indices: torch.Tensor, labels: torch.Tensor, x0: Optional[Planes] = None, update: bool = True):
+        """indices [M] int32 (edge-node ids of the batched graph), labels [M] fp32, both on the device. Returns the loss as a
+        device scalar (read it with .item() when it is needed: the step itself does not synchronise)."""
+        if x0 is None:
+            x0 = self.features(db)
+        self._enqueue(db, g, indices, labels, x0, update)
+        if update:
+            self.t += 1
+        return self.loss
+
+    def step_captured(self, db, g, indices: torch.Tensor, labels: torch.Tensor, x0: Optional[Planes] = None):
+        """step() as one CUDA-graph replay. The first call for a batch shape (frames, heads, nodes, edges, labelled edge-nodes,
+        in-degree bounds) runs one eager forward + backward to size the workspaces and captures the step on static copies of
+        the inputs; later calls copy their inputs there and replay. A workspace re-allocation (a larger batch) drops the graphs."""
+        from .pipeline import DeviceBatch
+        if x0 is None:
+            x0 = self.features(db)
+        M = int(indices.shape[0])
+        key = (db.n_frames, db.n_heads, db.n_nodes, db.n_edges, M, db.max_heads, db.max_enodes, bool(getattr(g, 'general', False)), x0.ld)
+        ent = self._graphs.get(key)
+        if ent is not None and ent['gen'] != self.net.buf.gen:
+            self._graphs.clear()
+            ent = None
+        if ent is None:
+            self.pipe.wait_graph(g)
+            self._enqueue(db, g, indices, labels, x0, update=False)                 # sizes every workspace; no parameter changes
+            clone = lambda t: t.clone()
+            sdb = DeviceBatch(db.n_frames, db.n_heads, db.n_nodes, db.max_heads, db.max_enodes, db.sk_xy, db.sk_vp, db.sk_mask, db.sk_cam,
+                              clone(db.head_off), clone(db.node_off), host_offsets=db.host_offsets)
+            sg = type('StaticGraph', (), {})()
+            sg.row_ptr, sg.col, sg.general, sg.pending = clone(g.row_ptr), clone(g.col), bool(getattr(g, 'general', False)), None
+            sx = Planes.__new__(Planes)
+            sx.rows, sx.cols, sx.ld, sx.hi, sx.lo = x0.rows, x0.cols, x0.ld, clone(x0.hi), clone(x0.lo)
+            ent = dict(db=sdb, g=sg, x0=sx, idx=clone(indices), lab=clone(labels), gen=self.net.buf.gen)
+            torch.cuda.synchronize(self.pipe.device)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(self.pipe.device)
+            side.wait_stream(torch.cuda.current_stream(self.pipe.device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    self._enqueue(sdb, sg, ent['idx'], ent['lab'], sx, update=True)
+            torch.cuda.current_stream(self.pipe.device).wait_stream(side)
+            if ent['gen'] != self.net.buf.gen:
+                raise RuntimeError('GatTrainer.step_captured: a workspace was allocated during the capture')
+            ent['graph'] = graph
+            self._graphs[key] = ent
+        else:
+            ent['db'].head_off.copy_(db.head_off, non_blocking=True)
+            ent['db'].node_off.copy_(db.node_off, non_blocking=True)
+            ent['g'].row_ptr.copy_(g.row_ptr, non_blocking=True)
+            ent['g'].col.copy_(g.col, non_blocking=True)
+            ent['x0'].hi.copy_(x0.hi, non_blocking=True)
+            ent['x0'].lo.copy_(x0.lo, non_blocking=True)
+            ent['idx'].copy_(indices, non_blocking=True)
+            ent['lab'].copy_(labels, non_blocking=True)
+        ent['graph'].replay()
+        self.t += 1
+        self.last_scores = self.net.cache['scores'][: db.n_nodes, 0]
         return self.loss

@@ -319,6 +319,10 @@ int b200pose_sigmoid_bwd(const float* scores, const float* dscores, int32_t n, f
 /* torch.optim.Adam (train_skeleton_matching.py:150), single-tensor form, over one flat parameter buffer; step counts from 1 */
 int b200pose_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int32_t step, void* stream);
+/* The same with the step count kept on the device: *step_dev is advanced by one and the bias corrections are computed there
+ * (scalars_dev: 2 floats of scratch), so a whole optimisation step - forward, loss, backward, this - is replayable as a CUDA graph */
+int b200pose_adam_step_dev(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int32_t* step_dev, float* scalars_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side frame packer (no GPU work): the reference's frame JSON - a list of frames

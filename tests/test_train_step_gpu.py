@@ -190,3 +190,29 @@ def test_native_trainer_against_reference_golden(tmp_path):
     far = check_parameters({k: v.cpu().numpy() for k, v in trainer.net.state_dict().items()}, gz, 1e-4, int(gz['steps'][0]))
     print('parameters after the steps: fraction further than 2.5e-5 from the reference, worst:', far)
     assert trainer.t == int(gz['steps'][0])
+
+
+def test_captured_step_is_the_eager_step(tmp_path):
+    """GatTrainer.step_captured (one CUDA-graph replay per batch shape, Adam step count on the device) against GatTrainer.step
+    (launch by launch) over two alternating batches: same losses and bit-identical parameters after every step."""
+    cfg, _, _ = helpers.load_golden('panoptic')
+    gz = np.load(os.path.join(GOLDEN, 'golden_train_step.npz'))
+    mods = dropin_env.activate(cfg)
+    dgl = importlib.import_module('dgl')
+    ds = _dataset(mods, cfg, tmp_path)
+    ctx = mods['rt'].context()
+    state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, 3, True)
+    eager, captured = train_mod.GatTrainer(ctx, state), train_mod.GatTrainer(ctx, state)
+    batches = []
+    for step in range(2):
+        subgraph, labels, indices = collate([ds[int(i)] for i in gz['step%d/members' % step]], dgl, 'cuda')
+        db, arrays = subgraph._b200
+        batches.append((db, arrays, indices.reshape(-1).to(torch.int32).cuda(), labels.reshape(-1).float().cuda()))
+    for it in range(6):
+        db, arrays, idx, lab = batches[it % 2]
+        le = float(eager.step(db, arrays, idx, lab).item())
+        lc = float(captured.step_captured(db, arrays, idx, lab).item())
+        assert le == lc, (it, le, lc)
+        assert torch.equal(eager.net.theta, captured.net.theta), 'parameters differ after step %d' % it
+    assert eager.t == captured.t == 6 and int(captured.t_dev.item()) == 6
+    assert len(captured._graphs) == 2
