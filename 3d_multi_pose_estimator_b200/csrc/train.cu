@@ -248,6 +248,92 @@ __global__ void __launch_bounds__(256) fold_attention_kernel(const float* __rest
     if (c < din) W2e[(size_t)r * ld_w2e + c] = (float)v; else b2e[r] = (float)v;
 }
 
+// Every operand plane of one layer from its fp32 parameters, in one launch (after each optimiser step): W1 -> planes and
+// transposed planes; [W2 ; attention folds] -> planes (+ the folded bias); W2 -> transposed planes. Thread (r, c) of two index
+// spaces; paddings are written as zeros so the planes can be consumed as K padding.
+__global__ void __launch_bounds__(256) prepare_layer_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int ld_w,
+                                                           const float* __restrict__ b2, const float* __restrict__ attn_l,
+                                                           const float* __restrict__ attn_r, int H, int D, int din,
+                                                           __nv_bfloat16* __restrict__ w1_hi, __nv_bfloat16* __restrict__ w1_lo, int ld_w1,
+                                                           __nv_bfloat16* __restrict__ w1t_hi, __nv_bfloat16* __restrict__ w1t_lo, int ld_w1t,
+                                                           __nv_bfloat16* __restrict__ w2_hi, __nv_bfloat16* __restrict__ w2_lo, int ld_w2,
+                                                           __nv_bfloat16* __restrict__ w2t_hi, __nv_bfloat16* __restrict__ w2t_lo, int ld_w2t,
+                                                           float* __restrict__ b2e, int rows_a, int rows_b)
+{
+    const int HD = H * D, n2 = HD + 2 * H;
+    const int cols = ld_w1 > ld_w2 ? ld_w1 : ld_w2;          // both are round_up(din, 64)
+    const long long total_a = (long long)rows_a * cols, total = total_a + (long long)rows_b * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        __nv_bfloat16 hi, lo;
+        if (i < total_a) {                                     // ---- W1: rows_a = max(din, its transposed planes' K padding)
+            const int r = (int)(i / cols), c = (int)(i % cols);
+            const float x = (r < din && c < din) ? W1[(size_t)r * ld_w + c] : 0.f;
+            split_bf16(x, hi, lo);
+            if (r < din && c < ld_w1) { w1_hi[(size_t)r * ld_w1 + c] = hi; w1_lo[(size_t)r * ld_w1 + c] = lo; }
+            if (c < din && r < ld_w1t) { w1t_hi[(size_t)c * ld_w1t + r] = hi; w1t_lo[(size_t)c * ld_w1t + r] = lo; }
+        } else {                                               // ---- W2 and its folds: rows_b = max(n2, K padding of W2^T)
+            const long long k = i - total_a;
+            const int r = (int)(k / cols), c = (int)(k % cols);
+            float x = 0.f;                                     // row r of [W2 ; folds]
+            if (c < din) {
+                if (r < HD) x = W2[(size_t)r * ld_w + c];
+                else if (r < n2) {
+                    const int h = (r - HD) % H;
+                    const float* a = (r - HD) < H ? attn_l : attn_r;
+                    double v = 0.0;
+                    for (int d = 0; d < D; ++d) v += (double)a[h * D + d] * (double)W2[(size_t)(h * D + d) * ld_w + c];
+                    x = (float)v;
+                }
+            }
+            if (r < n2 && c < ld_w2) { split_bf16(x, hi, lo); w2_hi[(size_t)r * ld_w2 + c] = hi; w2_lo[(size_t)r * ld_w2 + c] = lo; }
+            if (c < din && r < ld_w2t) {                       // W2^T [din, ld_w2t]: only the W2 rows, zeros in the K padding
+                split_bf16(r < HD ? x : 0.f, hi, lo);
+                w2t_hi[(size_t)c * ld_w2t + r] = hi; w2t_lo[(size_t)c * ld_w2t + r] = lo;
+            }
+            if (c == 0 && r < n2) {
+                if (r < HD) b2e[r] = b2[r];
+                else {
+                    const int h = (r - HD) % H;
+                    const float* a = (r - HD) < H ? attn_l : attn_r;
+                    double v = 0.0;
+                    for (int d = 0; d < D; ++d) v += (double)a[h * D + d] * (double)b2[h * D + d];
+                    b2e[r] = (float)v;
+                }
+            }
+        }
+    }
+}
+
+// The three column sums behind the aggregation backward in one pass over z and dz: d attn_l[h,d] = sum_u d a1[u,h] ft2[u,h,d],
+// d attn_r likewise with d a2, d b2[j] = sum_u d ft2[u,j]. Same summation order as colsum_kernel.
+__global__ void __launch_bounds__(256) attn_bias_grad_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ dz, int ld_dz,
+                                                            int R, int H, int D, float* __restrict__ g_attn_l, float* __restrict__ g_attn_r,
+                                                            float* __restrict__ g_b2)
+{
+    __shared__ float part[3][8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int HD = H * D, j = blockIdx.x * 32 + tx;
+    float sl = 0.f, sr = 0.f, sb = 0.f;
+    if (j < HD) {
+        const int h = j / D;
+        for (int r = ty; r < R; r += 8) {
+            const float f = z[(size_t)r * ldz + j];
+            const float* d = dz + (size_t)r * ld_dz;
+            sl = fmaf(f, d[HD + h], sl);
+            sr = fmaf(f, d[HD + H + h], sr);
+            sb += d[j];
+        }
+    }
+    part[0][ty][tx] = sl; part[1][ty][tx] = sr; part[2][ty][tx] = sb;
+    __syncthreads();
+    if (ty < 3 && j < HD) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[ty][i][tx];
+        (ty == 0 ? g_attn_l : ty == 1 ? g_attn_r : g_b2)[j] = t;
+    }
+}
+
 // nn.MSELoss over the edge-node scores (train_skeleton_matching.py:37, 174-178) and its gradient through the final sigmoid
 // (gat2.py:145): dlogit[idx[i]] = 2/M (s - y) s (1 - s). dlogit must be zeroed by the caller; idx entries are distinct
 // (edge-node ids). One CTA; the loss is summed in fp64 in a fixed order.
@@ -451,6 +537,42 @@ B2_EXPORT int b200pose_adam_step_dev(float* theta, const float* grad, float* m, 
     B2_CHECK_LAUNCH();
     if (n == 0) return B200POSE_OK;
     adam_dev_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(theta, grad, m, v, (long long)n, beta1, beta2, eps, weight_decay, scalars_dev);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+B2_EXPORT int b200pose_gat_prepare_layer(const float* w1, const float* w2, int32_t ld_w, const float* b2, const float* attn_l,
+                                         const float* attn_r, int32_t heads, int32_t dim, int32_t din,
+                                         uint16_t* w1_hi, uint16_t* w1_lo, int32_t ld_w1, uint16_t* w1t_hi, uint16_t* w1t_lo, int32_t ld_w1t,
+                                         uint16_t* w2_hi, uint16_t* w2_lo, int32_t ld_w2, uint16_t* w2t_hi, uint16_t* w2t_lo, int32_t ld_w2t,
+                                         float* b2e, void* stream)
+{
+    B2_CHECK_ARG(w1 && w2 && b2 && attn_l && attn_r && w1_hi && w1_lo && w1t_hi && w1t_lo && w2_hi && w2_lo && w2t_hi && w2t_lo && b2e,
+                 "gat_prepare_layer: null argument");
+    const int hd = heads * dim, n2 = hd + 2 * heads, kp = ((din + 63) / 64) * 64, hp = ((hd + 63) / 64) * 64;
+    B2_CHECK_ARG(heads >= 1 && dim >= 1 && din >= 1 && ld_w >= din, "gat_prepare_layer: bad shape");
+    B2_CHECK_ARG(ld_w1 == kp && ld_w2 == kp && ld_w1t >= kp && ld_w2t >= hp, "gat_prepare_layer: plane leading dimensions must be round_up(din, 64) "
+                 "(W1, [W2; folds]), >= round_up(din, 64) (W1^T) and >= round_up(heads*dim, 64) (W2^T)");
+    const int rows_a = kp;                                    // din rows of W1 + the K padding of W1^T
+    const int rows_b = n2 > hp ? n2 : hp;
+    const long long total = (long long)(rows_a + rows_b) * kp;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    prepare_layer_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w1, w2, ld_w, b2, attn_l, attn_r, heads, dim, din,
+        reinterpret_cast<__nv_bfloat16*>(w1_hi), reinterpret_cast<__nv_bfloat16*>(w1_lo), ld_w1,
+        reinterpret_cast<__nv_bfloat16*>(w1t_hi), reinterpret_cast<__nv_bfloat16*>(w1t_lo), ld_w1t,
+        reinterpret_cast<__nv_bfloat16*>(w2_hi), reinterpret_cast<__nv_bfloat16*>(w2_lo), ld_w2,
+        reinterpret_cast<__nv_bfloat16*>(w2t_hi), reinterpret_cast<__nv_bfloat16*>(w2t_lo), ld_w2t, b2e, rows_a, rows_b);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+B2_EXPORT int b200pose_gat_attn_bias_grad(const float* z, int32_t ldz, const float* dz, int32_t ld_dz, int32_t rows, int32_t heads, int32_t dim,
+                                          float* g_attn_l, float* g_attn_r, float* g_b2, void* stream)
+{
+    B2_CHECK_ARG(z && dz && g_attn_l && g_attn_r && g_b2 && rows >= 0 && heads >= 1 && dim >= 1, "gat_attn_bias_grad: bad argument");
+    B2_CHECK_ARG(ldz >= heads * dim && ld_dz >= heads * dim + 2 * heads, "gat_attn_bias_grad: leading dimension too small");
+    attn_bias_grad_kernel<<<ceil_div(heads * dim, 32), 256, 0, (cudaStream_t)stream>>>(z, ldz, dz, ld_dz, rows, heads, dim, g_attn_l, g_attn_r, g_b2);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

@@ -6,7 +6,7 @@ DGL, exactly the graph `process_test` builds (:813-876): heads in frame-dict cam
 cross-camera skeleton pair wired with 5 directed edges, alternative-'3' node features bit-exact in fp32. Any other
 mode ('train', 'dev', 'test_generated', ...) over a list of single-person files runs `process_training` (:672-810):
 the same sample tuples for the same `random` seed, the same edge-node order and labels, graphs built on the GPU from
-the explicit edge-node list (forward only - the B200 GAT2 has no backward). The graph object it hands out offers the
+the explicit edge-node list (the drop-in GAT2 differentiates through them: 3d_multi_pose_estimator_b200/train.py). The graph object it hands out offers the
 slice of the DGL API the reference's callers use (`.to`, `.ndata['h']`, `.edata`, `.edges()`, `.nodes()`,
 `.number_of_nodes()`), carries the CSR the B200 GAT2 / clustering drop-ins consume, and is what the `dgl.batch` of
 the sibling `dgl` drop-in module merges.

@@ -109,7 +109,6 @@ class GatGrad:
                 din, hd, n2 = lay['din'], lay['hd'], lay['n2']
                 lay['w1'] = Planes(din, din, self.device)
                 lay['w1t'] = Planes(din, din, self.device)
-                lay['w2e_f32'] = torch.zeros((n2, _ld4(din)), dtype=torch.float32, device=self.device)
                 lay['b2e'] = torch.zeros(n2, dtype=torch.float32, device=self.device)
                 lay['w2'] = Planes(n2, din, self.device)
                 lay['w2t'] = Planes(din, hd, self.device)
@@ -150,21 +149,15 @@ class GatGrad:
         L, s = self.L, self.pipe._stream()
         for l, lay in enumerate(self.layers):
             pre = 'layers.%d.' % l
-            din, hd, H, D = lay['din'], lay['hd'], lay['heads'], lay['dim']
             W1 = self.view(self.theta, pre + 'fc1.weight', padded=True)
             W2 = self.view(self.theta, pre + 'fc2.weight', padded=True)
-            ld = W1.stride(0)
-            check(L.b200pose_split_planes(ptr(W1), din, din, ld, ptr(lay['w1'].hi), ptr(lay['w1'].lo), lay['w1'].ld, s), 'split_planes')
-            check(L.b200pose_grad_planes(ptr(W1), din, din, ld, None, 0, 1.0, None, 0, None, None, 0,
-                                         ptr(lay['w1t'].hi), ptr(lay['w1t'].lo), lay['w1t'].ld, s), 'grad_planes')
-            w2e = lay['w2e_f32']
-            check(L.b200pose_fold_attention(ptr(W2), ld, ptr(self.view(self.theta, pre + 'fc2.bias')), ptr(self.view(self.theta, pre + 'attn_l')),
-                                            ptr(self.view(self.theta, pre + 'attn_r')), H, D, din, ptr(w2e), w2e.stride(0), ptr(lay['b2e']), s),
-                  'fold_attention')
-            check(L.b200pose_split_planes(ptr(w2e), lay['n2'], din, w2e.stride(0), ptr(lay['w2'].hi), ptr(lay['w2'].lo), lay['w2'].ld, s), 'split_planes')
-            check(L.b200pose_grad_planes(ptr(W2), hd, din, ld, None, 0, 1.0, None, 0, None, None, 0,
-                                         ptr(lay['w2t'].hi), ptr(lay['w2t'].lo), lay['w2t'].ld, s), 'grad_planes')
-            self.launches += 5
+            check(L.b200pose_gat_prepare_layer(ptr(W1), ptr(W2), W1.stride(0), ptr(self.view(self.theta, pre + 'fc2.bias')),
+                                               ptr(self.view(self.theta, pre + 'attn_l')), ptr(self.view(self.theta, pre + 'attn_r')),
+                                               lay['heads'], lay['dim'], lay['din'],
+                                               ptr(lay['w1'].hi), ptr(lay['w1'].lo), lay['w1'].ld, ptr(lay['w1t'].hi), ptr(lay['w1t'].lo), lay['w1t'].ld,
+                                               ptr(lay['w2'].hi), ptr(lay['w2'].lo), lay['w2'].ld, ptr(lay['w2t'].hi), ptr(lay['w2t'].lo), lay['w2t'].ld,
+                                               ptr(lay['b2e']), s), 'gat_prepare_layer')
+            self.launches += 1
 
     # ------------------------------------------------------------------ forward
     def forward(self, db, g, x0: Planes) -> torch.Tensor:
@@ -213,9 +206,8 @@ class GatGrad:
             check(L.b200pose_gat_aggregate_bwd(N, ptr(g.row_ptr), ptr(g.col), ptr(z), z.stride(0), H, D, self.alpha, ptr(d), ld_d,
                                                ptr(self.view(self.theta, pre + 'attn_l')), ptr(self.view(self.theta, pre + 'attn_r')),
                                                ptr(stats), ptr(dz), dz.stride(0), s), 'gat_aggregate_bwd')
-            check(L.b200pose_colsum(ptr(z), N, hd, z.stride(0), ptr(dz[:, hd:]), dz.stride(0), D, ptr(self.view(self.grad, pre + 'attn_l')), s), 'colsum')
-            check(L.b200pose_colsum(ptr(z), N, hd, z.stride(0), ptr(dz[:, hd + H:]), dz.stride(0), D, ptr(self.view(self.grad, pre + 'attn_r')), s), 'colsum')
-            check(L.b200pose_colsum(ptr(dz), N, hd, dz.stride(0), None, 0, 1, ptr(self.view(self.grad, pre + 'fc2.bias')), s), 'colsum')
+            check(L.b200pose_gat_attn_bias_grad(ptr(z), z.stride(0), ptr(dz), dz.stride(0), N, H, D, ptr(self.view(self.grad, pre + 'attn_l')),
+                                                ptr(self.view(self.grad, pre + 'attn_r')), ptr(self.view(self.grad, pre + 'fc2.bias')), s), 'gat_attn_bias_grad')
             G2 = self.buf.p('G2_%d' % l, N, hd)
             G2T = self.buf.p('G2T_%d' % l, hd, N)
             check(L.b200pose_grad_planes(ptr(dz), N, hd, dz.stride(0), None, 0, 1.0, None, 0, ptr(G2.hi), ptr(G2.lo), G2.ld,
@@ -233,7 +225,7 @@ class GatGrad:
             xT = self.buf.p('xT_%d' % l, din, N)
             check(L.b200pose_transpose_planes(ptr(x.hi), ptr(x.lo), N, din, x.ld, ptr(xT.hi), ptr(xT.lo), xT.ld, s), 'transpose_planes')
             self._linear(G1T, din, xT, din, N, self.view(self.grad, pre + 'fc1.weight', padded=True))          # dW1 = G1^T x
-            self.launches += 9
+            self.launches += 8          # kernels of the calls above other than the GEMMs (counted by _linear)
             if l > 0:
                 dx = self.buf.f('dx_%d' % _ld4(din), N, _ld4(din))
                 self._linear(G1, N, lay['w1t'], din, din, dx)                                                   # dx = G1 W1

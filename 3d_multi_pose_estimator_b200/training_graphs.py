@@ -1,4 +1,4 @@
-"""Training-side graphs on the B200 path (forward only): the sample synthesis of
+"""Training-side graphs on the B200 path (the optimisation step itself is train.py): the sample synthesis of
 `MergedMultipleHumansDataset.process_training` (reference skeleton_matching/graph_generator.py:516-560, 672-810, with the
 view augmentation of utils/data_augmentation.py:14-89) and the block-diagonal batching the training / validation drivers
 do with `dgl.batch` (train_skeleton_matching.py:67-84, sm_metrics_without_gt.py:46-64).

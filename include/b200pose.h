@@ -310,6 +310,16 @@ int b200pose_colsum(const float* x, int32_t rows, int32_t cols, int32_t ld, cons
  * as one projection; the inference path does this fold once on the host, a training step after every parameter update) */
 int b200pose_fold_attention(const float* w2, int32_t ld_w2, const float* b2, const float* attn_l, const float* attn_r,
                             int32_t heads, int32_t dim, int32_t din, float* w2e, int32_t ld_w2e, float* b2e, void* stream);
+/* The two calls above for a whole layer in one launch each: every operand plane of a layer from its fp32 parameters (W1 and
+ * W1^T planes, [W2 ; folds] planes + folded bias, W2^T planes; ld_w1 = ld_w2 = round_up(din, 64)), and the three column sums
+ * behind b200pose_gat_aggregate_bwd (d attn_l, d attn_r, d fc2.bias) in one pass over z and dz. */
+int b200pose_gat_prepare_layer(const float* w1, const float* w2, int32_t ld_w, const float* b2, const float* attn_l,
+                               const float* attn_r, int32_t heads, int32_t dim, int32_t din,
+                               uint16_t* w1_hi, uint16_t* w1_lo, int32_t ld_w1, uint16_t* w1t_hi, uint16_t* w1t_lo, int32_t ld_w1t,
+                               uint16_t* w2_hi, uint16_t* w2_lo, int32_t ld_w2, uint16_t* w2t_hi, uint16_t* w2t_lo, int32_t ld_w2t,
+                               float* b2e, void* stream);
+int b200pose_gat_attn_bias_grad(const float* z, int32_t ldz, const float* dz, int32_t ld_dz, int32_t rows, int32_t heads, int32_t dim,
+                                float* g_attn_l, float* g_attn_r, float* g_b2, void* stream);
 /* nn.MSELoss on scores[idx[i]] vs labels[i] (train_skeleton_matching.py:37, 174-178) and its gradient through the final
  * sigmoid: dlogit [n_nodes] (zero outside idx; idx entries distinct). loss / dlogit may be null. */
 int b200pose_mse_sigmoid(const float* scores, int32_t n_nodes, const int32_t* idx, const float* labels, int32_t m,

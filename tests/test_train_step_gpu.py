@@ -46,24 +46,38 @@ def collate(batch, dgl, device):
     return dgl.batch(graphs).to(torch.device(device)), batched_labels, batched_indices
 
 
-def test_backward_kernels_vs_oracle():
-    """All golden Panoptic frames as one batch (closed-form test-mode graphs, ~1.3 k nodes), random labels: loss, scores and
-    every gradient tensor of one forward + backward against oracle/train_oracle.py; two runs are bit-identical."""
+@pytest.mark.parametrize('case', ['test_frames', 'many_person_training_graph'])
+def test_backward_kernels_vs_oracle(case):
+    """Loss, scores and every gradient tensor of one forward + backward against oracle/train_oracle.py; two runs are
+    bit-identical. 'test_frames': all golden Panoptic frames as one batch (closed-form test-mode graphs, ~1.3 k nodes), random
+    labels. 'many_person_training_graph': one process_training graph of a 12-sample tuple (about 60 heads, ordered pairs: ~2900
+    edge-nodes, head in-degree ~100 - the large-frame aggregation kernel in the forward, long CSR rows in the backward) with the
+    reference's own labels."""
     from oracle import pose_oracle as O
     from oracle import train_oracle as TO
     cfg, npz, meta = helpers.load_golden('panoptic')
-    tags = helpers.graph_cases('panoptic')
-    frames = [{c: meta['frames'][t][c] for c in meta['frames'][t] if json.loads(meta['frames'][t][c][0])} for t in tags]
-    pb = pack_mod.pack_frames(frames, cfg)
-    db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
     pipe = pipeline_mod.PosePipeline(cfg, None, None, device='cuda:0')
-    g = pipe.build_graph(db, with_coo=True)
+    if case == 'test_frames':
+        tags = helpers.graph_cases('panoptic')
+        frames = [{c: meta['frames'][t][c] for c in meta['frames'][t] if json.loads(meta['frames'][t][c][0])} for t in tags]
+        pb = pack_mod.pack_frames(frames, cfg)
+        db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+        g = pipe.build_graph(db, with_coo=True)
+        node_off, head_off = pb.node_off, pb.head_off
+        idx = np.concatenate([np.arange(node_off[b] + (head_off[b + 1] - head_off[b]), node_off[b + 1]) for b in range(pb.n_frames)])
+        rng = np.random.default_rng(5)
+        labels = (rng.random(len(idx)) < 0.3).astype(np.float32)
+    else:
+        tg = importlib.import_module('3d_multi_pose_estimator_b200.training_graphs')
+        samples = [helpers.synth.make_frame(cfg, 31000 + i, 1 + (i % 3 == 0), drop_joint_p=0.2) for i in range(12)]
+        pb, pairs, lab = tg.training_graph_inputs(samples, cfg)
+        assert pb.n_heads > 48 and len(pairs) > 2000
+        db = pipeline_mod.HostBatch(pb).to_device('cuda:0')
+        g = pipe.build_graph_pairs(db, pairs, with_coo=True)
+        idx = np.arange(pb.n_heads, pb.n_heads + len(pairs))
+        labels = lab.ravel().astype(np.float32)
     state = helpers.weights_mod.make_gat_state(cfg.n_features_sm, 11, True)
     trainer = train_mod.GatTrainer(pipe, state)
-    node_off, head_off = pb.node_off, pb.head_off
-    idx = np.concatenate([np.arange(node_off[b] + (head_off[b + 1] - head_off[b]), node_off[b + 1]) for b in range(pb.n_frames)])
-    rng = np.random.default_rng(5)
-    labels = (rng.random(len(idx)) < 0.3).astype(np.float32)
     d_idx = torch.from_numpy(idx.astype(np.int32)).cuda()
     d_lab = torch.from_numpy(labels).cuda()
     loss = float(trainer.step(db, g, d_idx, d_lab, update=False).item())
