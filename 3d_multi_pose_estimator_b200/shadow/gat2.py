@@ -126,6 +126,9 @@ class GAT2(nn.Module):
         """Grad mode with trainable parameters (the loop of train_skeleton_matching.py:163-184)."""
         if any(lyr.residual for lyr in self.layers):
             raise NotImplementedError('B200 GAT2: residual layers are inference-only')
+        if inputs.requires_grad:
+            raise NotImplementedError('B200 GAT2: gradients with respect to the input features are not computed (the reference trains the '
+                                      'parameters only, train_skeleton_matching.py:150)')
         named = list(self.named_parameters())
         key = tuple((p.data_ptr(), p._version) for _, p in named)
         net = self.__dict__.get('_grad_net')

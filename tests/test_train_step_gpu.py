@@ -230,3 +230,68 @@ def test_captured_step_is_the_eager_step(tmp_path):
         assert torch.equal(eager.net.theta, captured.net.theta), 'parameters differ after step %d' % it
     assert eager.t == captured.t == 6 and int(captured.t_dev.item()) == 6
     assert len(captured._graphs) == 2
+
+
+@pytest.mark.parametrize('heads,dim', [(1, 1), (3, 7), (2, 33), (4, 64), (2, 100)])
+def test_aggregate_backward_shapes(heads, dim):
+    """b200pose_gat_aggregate_bwd alone, through the C ABI, on head counts / widths other than the shipped layers' (all three
+    column-group variants of the source-side kernel: dim <= 32, <= 64, <= 128) against the restatement's layer_backward on a
+    random symmetric graph with self-loops, rows of 1 to ~60 in-edges."""
+    from oracle import train_oracle as TO
+    _lib = importlib.import_module('3d_multi_pose_estimator_b200._lib')
+    L, ptr, check = _lib.lib(), _lib.ptr, _lib.check
+    rng = np.random.default_rng(100 * heads + dim)
+    n = 300
+    adj = np.zeros((n, n), dtype=bool)
+    hubs = rng.choice(n, 5, replace=False)
+    for u in range(n):
+        for v in rng.choice(n, 2, replace=False):
+            adj[u, v] = adj[v, u] = True
+        adj[u, u] = True
+    for h in hubs:
+        for v in rng.choice(n, 60, replace=False):
+            adj[h, v] = adj[v, h] = True
+    dst, src = np.nonzero(adj)                          # row-major: grouped by destination, sources ascending
+    row_ptr = np.concatenate([[0], np.cumsum(adj.sum(1))]).astype(np.int32)
+    hd = heads * dim
+    ldz = ((hd + 2 * heads + 3) // 4) * 4
+    ft2 = rng.standard_normal((n, heads, dim)).astype(np.float32)
+    al, ar = (0.3 * rng.standard_normal((2, heads, dim))).astype(np.float32)
+    a1 = np.einsum('nhd,hd->nh', ft2, al).astype(np.float32)
+    a2 = np.einsum('nhd,hd->nh', ft2, ar).astype(np.float32)
+    z = np.zeros((n, ldz), dtype=np.float32)
+    z[:, :hd], z[:, hd:hd + heads], z[:, hd + heads:hd + 2 * heads] = ft2.reshape(n, hd), a1, a2
+    dout = rng.standard_normal((n, heads, dim)).astype(np.float32)
+    # restatement: softmax state from z, then the aggregation part of layer_backward (W-independent outputs)
+    alpha = 0.15
+    s_ = (a1[src] + a2[dst]).astype(np.float32)
+    e = TO.leaky(s_, alpha)
+    mx = np.full((n, heads), -np.inf, dtype=np.float32)
+    np.maximum.at(mx, dst, e)
+    ex = np.exp(e - mx[dst]).astype(np.float32)
+    den = np.zeros((n, heads), dtype=np.float32)
+    np.add.at(den, dst, ex)
+    a = ex / den[dst]
+    dft2 = np.zeros_like(ft2)
+    np.add.at(dft2, src, a[:, :, None] * dout[dst])
+    da = np.einsum('ehd,ehd->eh', dout[dst], ft2[src])
+    c = np.zeros((n, heads), dtype=np.float32)
+    np.add.at(c, dst, a * da)
+    ds = a * (da - c[dst]) * TO.dleaky(s_, alpha)
+    da1, da2 = np.zeros((n, heads), dtype=np.float32), np.zeros((n, heads), dtype=np.float32)
+    np.add.at(da1, src, ds)
+    np.add.at(da2, dst, ds)
+    want = np.concatenate([(dft2 + da1[:, :, None] * al[None] + da2[:, :, None] * ar[None]).reshape(n, hd), da1, da2], axis=1)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    d_rp, d_col, d_z, d_dout = dev(row_ptr), dev(src.astype(np.int32)), dev(z), dev(dout.reshape(n, hd))
+    d_al, d_ar = dev(al.reshape(-1)), dev(ar.reshape(-1))
+    stats = torch.zeros(n * heads * 3, dtype=torch.float32, device='cuda')
+    dz = torch.zeros((n, ldz), dtype=torch.float32, device='cuda')
+    check(L.b200pose_gat_aggregate_bwd(n, ptr(d_rp), ptr(d_col), ptr(d_z), ldz, heads, dim, alpha, ptr(d_dout), hd, ptr(d_al), ptr(d_ar),
+                                       ptr(stats), ptr(dz), ldz, None), 'gat_aggregate_bwd')
+    torch.cuda.synchronize()
+    got = dz.cpu().numpy()[:, :hd + 2 * heads]
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err <= 2e-5, (heads, dim, err)
+    assert L.b200pose_gat_aggregate_bwd(n, ptr(d_rp), ptr(d_col), ptr(d_z), ldz, heads, 129, alpha, ptr(d_dout), hd, ptr(d_al), ptr(d_ar),
+                                        ptr(stats), ptr(dz), ldz, None) != 0          # dim > 128: rejected, not mis-computed
