@@ -269,6 +269,31 @@ class PosePipeline:
             self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         return self._dev_index
 
+    # ------------------------------------------------------------------ compute lanes
+    def twin(self) -> "PosePipeline":
+        """A second pipeline on the same device that SHARES this one's camera tables and weight planes (read-only) and has its
+        own workspaces, side stream and caches: two independent batches can then be in flight on two CUDA streams. A step
+        has ~0.26 ms of latency-bound phases (graph build + features, clustering, person list, encoder: 8-26 % warps
+        active) that fit beside another batch's tensor-core GEMMs on the same SMs."""
+        t = PosePipeline.__new__(PosePipeline)
+        t.__dict__.update(self.__dict__)
+        t._ws = {}
+        t.launches = 0
+        for k in ('_side_stream', '_copy_stream', '_d2h_stream', '_stream_results', '_graphs', '_graph_person_hint', '_person_stage', '_lanes'):
+            t.__dict__.pop(k, None)
+        return t
+
+    def lanes(self, n: int):
+        """[self, twin, ...] and one compute stream per extra lane (lane 0 runs on the caller's current stream); cached.
+        A lane whose weights were replaced on `self` since it was made is rebuilt."""
+        have = self.__dict__.get('_lanes')
+        gen = getattr(self, '_weights_gen', 0)
+        if have is None or have[0] != gen or len(have[1]) < n:
+            pipes = [self] + [self.twin() for _ in range(n - 1)]
+            streams = [None] + [torch.cuda.Stream(self.device) for _ in range(n - 1)]
+            have = self.__dict__['_lanes'] = (gen, pipes, streams)
+        return have[1][:n], have[2][:n]
+
     # ------------------------------------------------------------------ workspace
     def planes_ws(self, tag: str, rows: int, cols: int) -> Planes:
         """Activation planes from a per-pipeline workspace. They are zero-initialised once; kernels write
@@ -896,75 +921,89 @@ class PosePipeline:
             frames = [frames]
         return self.infer_host_graph(HostBatch(pack_frames_fast(frames, self.cfg, keep_json=False), pinned=False))
 
-    def infer_host_stream(self, batches):
+    def infer_host_stream(self, batches, lanes: int = 3):
         """Generator over host batches: yields the host results of each batch, in order (the serving loop of a camera rig or
-        of a recorded sequence: pack frames -> infer -> consume). Three things overlap in steady state: the host->device
-        copy of batch i+1 (copy stream), the compute of batch i - enqueued as one sync-free step, so the GPU never waits for
-        the host inside it - and the result read-back of batch i-1 (its own stream: first the per-frame person counts, then,
-        once the host knows the total, exactly the persons' rows). Results of batch i are yielded after batch i+1 has been
-        enqueued; the last batch is flushed at the end."""
+        of a recorded sequence: pack frames -> infer -> consume). In steady state the host->device copy of batch i+1 (copy
+        stream), the compute of batch i - enqueued as one sync-free step, so the GPU never waits for the host inside it - and
+        the result read-back of batch i-1 (its own stream: first the per-frame person counts, then, once the host knows the
+        total, exactly the persons' rows) overlap. With lanes > 1 consecutive batches also alternate between that many compute
+        streams (`twin()`: shared weights, own workspaces), so the latency-bound phases of one batch (graph build, clustering,
+        person list, encoder: few warps) run beside the projections of another; `lanes` batches stay enqueued behind the one
+        whose results the host is reading (measured on 1024-frame Panoptic batches: 2.43 ms per batch with one lane, 2.09 with
+        two, 2.05 with three, 2.03 with four). Results are yielded in order; the last batches are flushed at the end."""
         cur = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         if getattr(self, '_d2h_stream', None) is None:
             self._d2h_stream = torch.cuda.Stream(self.device)
-        cs, ds = self._copy_stream, self._d2h_stream
+        if getattr(self, '_cnt_stream', None) is None:
+            self._cnt_stream = torch.cuda.Stream(self.device)
+        cs, ds, dc = self._copy_stream, self._d2h_stream, self._cnt_stream
+        pipes, lane_streams = self.lanes(max(1, int(lanes)))
+        depth = len(pipes)                                     # batches enqueued ahead of the one whose results the host waits for
+        lane_streams = [cur if s is None else s for s in lane_streams]
+        for s in lane_streams[1:]:
+            s.wait_stream(cur)
         it = iter(batches)
         n_out = self.mlp[-1]['n'] if self.mlp is not None else 0
+        count = [0]
 
         def prefetch():
             try:
                 hb = next(it)
             except StopIteration:
                 return None
+            lane = count[0] % len(pipes)
+            count[0] += 1
             with torch.cuda.stream(cs):
                 db = hb.to_device(self.device)
                 for t in (db.sk_xy, db.sk_vp, db.sk_mask, db.sk_cam, db.head_off, db.node_off):
-                    t.record_stream(cur)
+                    t.record_stream(lane_streams[lane])
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            return hb, db, ev
+            return hb, db, ev, lane
 
-        # pinned result buffers: three rotating sets per batch size (a batch's results are handed out while the next batch
-        # computes and the one after is being enqueued), owned by the pipeline - the same HostBatch may be streamed repeatedly.
-        # A yielded result stays valid until two more batches have been yielded.
+        # pinned result buffers: depth + 3 rotating sets per batch size (depth + 1 batches are in flight, and a yielded result
+        # stays valid until two more batches have been yielded), owned by the pipeline - the same HostBatch may be streamed
+        # repeatedly.
         pool = self.__dict__.setdefault('_stream_results', {})
         turn = [0]
 
         def result_set(hb):
             B, cap = hb.pb.n_frames, person_capacity(hb.pb.n_heads, self.cfg.min_number_of_views)
-            key = (B, cap, n_out)
+            key = (B, cap, n_out, depth + 3)
             sets = pool.get(key)
             if sets is None:
                 mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
                 sets = pool[key] = [dict(n_persons=mk((B,), torch.int32), person_off=mk((B + 1,), torch.int32),
                                          person_sk=mk((cap, self.cfg.n_cameras), torch.int32), joints=mk((cap, max(n_out, 1)), torch.float32),
-                                         valid=mk((cap,), torch.uint8)) for _ in range(3)]
+                                         valid=mk((cap,), torch.uint8)) for _ in range(depth + 3)]
             turn[0] += 1
-            return sets[turn[0] % 3]
+            return sets[turn[0] % (depth + 3)]
 
-        def enqueue_compute(hb, db, ev):
-            """Compute of one batch; nothing here waits for the GPU."""
-            cur.wait_event(ev)
-            res = self.infer(db, sync=False)
-            if res.get('n_persons_dev') is not None and 'joints' in res:
-                res['joints'] = res['joints'].clone()            # 'mlp_out' is a shared workspace: the next batch overwrites it
-            done = torch.cuda.Event()
-            done.record(cur)
+        def enqueue_compute(hb, db, ev, lane):
+            """Compute of one batch on its lane's stream; nothing here waits for the GPU."""
+            st = lane_streams[lane]
+            with torch.cuda.stream(st):
+                st.wait_event(ev)
+                res = pipes[lane].infer(db, sync=False)
+                if res.get('n_persons_dev') is not None and 'joints' in res:
+                    res['joints'] = res['joints'].clone()        # 'mlp_out' is a shared workspace: the lane's next batch overwrites it
+                done = torch.cuda.Event()
+                done.record(st)
             return hb, res, done
 
         def enqueue_counts(hb, res, done):
-            """Read-back of the batch's per-frame person counts, behind its compute, on the read-back stream. Enqueued only
-            AFTER the previous batch's rows have been read back (finalize): the read-back stream runs in order, so rows
-            queued behind this wait would not move - and the host, which waits for them, would not enqueue the next batch -
-            until this batch's compute has finished."""
+            """Read-back of the batch's per-frame person counts, behind its compute, on the counts stream - NOT the stream the
+            rows are read back on: that one runs in order, and rows of an earlier batch queued behind this wait would not move
+            (nor would the host, which waits for them, enqueue anything) until this batch's compute has finished."""
             bufs = result_set(hb)
-            with torch.cuda.stream(ds):
-                ds.wait_event(done)
+            with torch.cuda.stream(dc):
+                dc.wait_event(done)
                 bufs['n_persons'].copy_(res['n_persons'], non_blocking=True)
                 bufs['person_off'].copy_(res['person_off'], non_blocking=True)
                 counts = torch.cuda.Event()
-                counts.record(ds)
+                counts.record(dc)
             return hb, res, bufs, counts
 
         def finalize(hb, res, bufs, counts):
@@ -985,14 +1024,14 @@ class PosePipeline:
             return out
 
         nxt = prefetch()
-        pending = None
+        pending = collections.deque()
         while nxt is not None:
-            hb, db, ev = nxt
+            hb, db, ev, lane = nxt
             nxt = prefetch()                                   # the next batch's copy is in flight during this compute
-            job = enqueue_compute(hb, db, ev)
-            out = finalize(*pending) if pending is not None else None    # batch i-1 is read back while batch i computes
-            pending = enqueue_counts(*job)
-            if out is not None:
-                yield out
-        if pending is not None:
-            yield finalize(*pending)
+            pending.append(enqueue_counts(*enqueue_compute(hb, db, ev, lane)))
+            if len(pending) > depth:                           # `depth` batches stay enqueued behind the one read back here
+                yield finalize(*pending.popleft())
+        for s in lane_streams[1:]:
+            cur.wait_stream(s)
+        while pending:
+            yield finalize(*pending.popleft())

@@ -233,6 +233,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
     ap.add_argument('--no-fuse2', action='store_true', help='A/B: run the last GAT layer as two projections instead of the fused launch')
+    ap.add_argument('--lanes', type=int, default=3, help='compute lanes (CUDA streams with their own workspaces) the job alternates its steps between; 1 = one stream')
     ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch', 'train_step'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
@@ -262,6 +263,10 @@ def main():
     if args.total_frames > 0:
         config_desc['job'] = '%d frames in total: %d steps of %d frames on each of %d GPUs (512 distinct frames per GPU, cycled)' % (
             args.steps * world * args.frames, args.steps, args.frames, world)
+    if args.lanes > 1:
+        config_desc['l2'] = ('job of K steps on %d compute lanes (consecutive steps alternate between CUDA streams with their own workspaces, '
+                             'shared weights); no flush between steps: a step\'s working set (1.3 GB of activations at 1024 frames) is ten times '
+                             'the 126 MB L2. one_lane = the same steps on one stream with a 256 MiB L2 flush between them' % args.lanes)
     kind = reference_kind() if args.cpu_kind == 'auto' else args.cpu_kind
     kind_note = {'reference': 'the unmodified reference (baseline/_ref) under the dgl / pytransform3d import shims, its own driver call sequence '
                               '(test/metrics_from_model.py:178-300), one single-threaded process per host core',
@@ -319,12 +324,19 @@ def main():
     # asynchronously; nothing on the compute stream waits for it until the end of the job ("final gather")
     gather = sharding.ResultGather(world, args.frames, P_cap, cfg.n_cameras, n_out, dev, depth=4) if world > 1 else None
 
-    def step_device():
+    n_lanes = max(1, args.lanes)
+    lanes, lane_streams = pipe.lanes(n_lanes)
+    main_stream = torch.cuda.current_stream(dev)
+    lane_streams = [main_stream if st is None else st for st in lane_streams]
+
+    def step_device(lane=0):
         # the whole step enqueued without a host round trip: stage 3 is launched for the person capacity and reads the
-        # count from the device (PosePipeline.stage_b_nosync)
-        res = pipe.infer(db, sync=False)
-        if gather is not None:
-            gather.submit(res, args.frames, head_base=rank * pb.n_heads, stream=pipe._stream())
+        # count from the device (PosePipeline.stage_b_nosync). Lane k = the k-th pipeline of pipe.lanes() (shared weights,
+        # own workspaces) on its own stream.
+        with torch.cuda.stream(lane_streams[lane]):
+            res = lanes[lane].infer(db, sync=False)
+            if gather is not None:
+                gather.submit(res, args.frames, head_base=rank * pb.n_heads, stream=lanes[lane]._stream())
         return res
 
     def barrier():
@@ -334,18 +346,20 @@ def main():
 
     # warm-up (also settles the caching allocator)
     for _ in range(warmup):
-        res = step_device()
+        for lane in range(n_lanes):
+            res = step_device(lane)
         pipe.infer_host(hb, n_chunks=args.chunks)
     if gather is not None:
         gather.finish()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- device-resident timing: one event pair per step, L2 flushed in between; the wait for the outstanding gathers
-    # (the end of the job) is timed as well and counted into the job time
+    # ---- device-resident timing, one lane: one event pair per step, L2 flushed in between; the wait for the outstanding
+    # gathers (the end of the job) is timed as well and counted into the job time
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-    pipe.launches = 0
+    for p_ in lanes:
+        p_.launches = 0
     barrier()
     for a, b in ev:
         flush.fill_(1)
@@ -358,7 +372,29 @@ def main():
     barrier()
     launches = pipe.launches // max(1, args.steps) + (1 if gather is not None else 0)
     tail_ms = float(tail[0].elapsed_time(tail[1]))
-    ms = (float(np.sum([a.elapsed_time(b) for a, b in ev])) + tail_ms) / args.steps
+    ms_one_lane = (float(np.sum([a.elapsed_time(b) for a, b in ev])) + tail_ms) / args.steps
+    ms = ms_one_lane
+    # ---- the same K steps as a job on n_lanes compute streams: consecutive steps alternate between the lanes, so the
+    # latency-bound tail of one step (clustering, person list, encoder) runs beside the projections of the next. One event pair
+    # around the whole job (+ the wait for the gathers). No flush: a step's working set (1.3 GB of activations at the
+    # headline size) is ten times the L2, and a flush on one lane would only take bandwidth from the step on the other.
+    if n_lanes > 1:
+        job = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        barrier()
+        job[0].record(main_stream)
+        for st in lane_streams[1:]:
+            st.wait_event(job[0])
+        for i in range(args.steps):
+            res = step_device(i % n_lanes)
+        for st in lane_streams[1:]:
+            main_stream.wait_stream(st)
+        job[1].record(main_stream)
+        tail[0].record()
+        gathered = gather.finish() if gather is not None else None
+        tail[1].record()
+        barrier()
+        tail_ms = float(tail[0].elapsed_time(tail[1]))
+        ms = (float(job[0].elapsed_time(job[1])) + tail_ms) / args.steps
     gather_ok = None
     if gathered is not None and rank == 0:                       # the gathered records really hold every rank's results
         last = sharding.unpack_records(gathered[-1], [args.frames] * world, args.frames, P_cap, cfg.n_cameras, n_out)
@@ -370,13 +406,13 @@ def main():
     # pinned host memory and reads its results back inside the timed region (the copy of step i+1 overlaps the compute of
     # step i: PosePipeline.infer_host_stream). Per-step activations (1.3 GB) are 10x the L2, so no flush is needed here.
     barrier()
-    for _ in pipe.infer_host_stream([hb] * 2):
+    for _ in pipe.infer_host_stream([hb] * 4, lanes=n_lanes):
         pass
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     n_done = 0
-    for out in pipe.infer_host_stream([hb] * args.steps):
+    for out in pipe.infer_host_stream([hb] * args.steps, lanes=n_lanes):
         n_done += 1
     torch.cuda.synchronize()
     e2e_total = time.perf_counter() - t0
@@ -447,10 +483,10 @@ def main():
     d2h = sum(v.numel() * v.element_size() for v in out.values() if hasattr(v, 'numel'))
     # ---- per-kernel-class timing for the roofline (separate pass, CUDA events around each class)
     kern = profile_classes(pipe, db, pm, torch) if rank == 0 else None
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, ms_one_lane], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_max = float(t[0]), float(t[1])
+    ms_max, e2e_max, one_lane_max = float(t[0]), float(t[1]), float(t[2])
     total_frames = args.frames * world
     if rank == 0:
         peaks = {}
@@ -507,9 +543,14 @@ def main():
                 'warmup': warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate; fp64 geometry', 'data': 'synthetic',
                 'config': config_desc,
+                'lanes': n_lanes,
+                'one_lane': {'value': total_frames / one_lane_max * 1e3, 'unit': UNIT, 'ms_per_step': one_lane_max,
+                             'how': 'the same K steps one after the other on one stream, one CUDA-event pair per step, L2 flushed (256 MiB '
+                                    'write) between them: the figure the per-kernel table below adds up to'},
                 'e2e': {'value': total_frames / e2e_max * 1e3, 'unit': UNIT, 'h2d_bytes_per_step': hb.nbytes(),
                         'd2h_bytes_per_step': int(d2h), 'ms_per_step': e2e_max, 'single_call_ms': single_ms,
-                        'mode': 'streamed: copy of step i+1 overlaps compute of step i'},
+                        'mode': 'streamed (PosePipeline.infer_host_stream): copy of step i+1 and read-back of step i-1 overlap the compute '
+                                'of step i; consecutive steps alternate between %d compute lanes' % n_lanes},
                 'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roofline, 'kernels': kernels,
                 'cpu_baseline': cpu_line, 'parity_sample': parity,
                 'final_gather': None if gather is None else {'mode': 'one packing kernel + one asynchronous all-gather per step, waited for once at '
