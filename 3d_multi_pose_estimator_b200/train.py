@@ -13,6 +13,7 @@ transposed planes). `GatTrainer` adds the loss and Adam kernels: one `step()` = 
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 from typing import Dict, Optional, Sequence
 
@@ -256,7 +257,8 @@ class GatTrainer:
         self.adam_scalars = torch.zeros(2, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.last_scores = None
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()        # captured steps, least recently used first
+        self.max_cached = 64
 
     def features(self, db) -> Planes:
         """ndata['h'] of the batch as GEMM operand planes (the reference feeds the dense N x F matrix, :171-176)"""
@@ -323,7 +325,10 @@ class GatTrainer:
                 raise RuntimeError('GatTrainer.step_captured: a workspace was allocated during the capture')
             ent['graph'] = graph
             self._graphs[key] = ent
+            while len(self._graphs) > self.max_cached:
+                self._graphs.popitem(last=False)
         else:
+            self._graphs.move_to_end(key)
             ent['db'].head_off.copy_(db.head_off, non_blocking=True)
             ent['db'].node_off.copy_(db.node_off, non_blocking=True)
             ent['g'].row_ptr.copy_(g.row_ptr, non_blocking=True)
