@@ -921,7 +921,7 @@ class PosePipeline:
             frames = [frames]
         return self.infer_host_graph(HostBatch(pack_frames_fast(frames, self.cfg, keep_json=False), pinned=False))
 
-    def infer_host_stream(self, batches, lanes: int = 3):
+    def infer_host_stream(self, batches, lanes: Optional[int] = None):
         """Generator over host batches: yields the host results of each batch, in order (the serving loop of a camera rig or
         of a recorded sequence: pack frames -> infer -> consume). In steady state the host->device copy of batch i+1 (copy
         stream), the compute of batch i - enqueued as one sync-free step, so the GPU never waits for the host inside it - and
@@ -930,7 +930,12 @@ class PosePipeline:
         streams (`twin()`: shared weights, own workspaces), so the latency-bound phases of one batch (graph build, clustering,
         person list, encoder: few warps) run beside the projections of another; `lanes` batches stay enqueued behind the one
         whose results the host is reading (measured on 1024-frame Panoptic batches: 2.43 ms per batch with one lane, 2.09 with
-        two, 2.05 with three, 2.03 with four). Results are yielded in order; the last batches are flushed at the end."""
+        two, 2.05 with three, 2.03 with four). lanes=None: three when the process has 32 hardware stream queues
+        (CUDA_DEVICE_MAX_CONNECTIONS, set by this package at import when it can), else two - see the package's
+        `_widen_stream_queues`. Results are yielded in order; the last batches are flushed at the end."""
+        if lanes is None:
+            from . import DEFAULT_LANES
+            lanes = DEFAULT_LANES
         cur = torch.cuda.current_stream(self.device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)

@@ -19,6 +19,10 @@ import sys
 import threading
 import time
 
+# more hardware stream queues than CUDA's default 8 (read when the CUDA context is created): the job runs on ~10 streams and
+# streams that share a queue serialise each other (3d_multi_pose_estimator_b200/__init__.py:_widen_stream_queues)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -233,7 +237,7 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0, help='seconds of CPU work for the cpu_baseline sample')
     ap.add_argument('--gemm-impl', type=int, default=0)
     ap.add_argument('--no-fuse2', action='store_true', help='A/B: run the last GAT layer as two projections instead of the fused launch')
-    ap.add_argument('--lanes', type=int, default=3, help='compute lanes (CUDA streams with their own workspaces) the job alternates its steps between; 1 = one stream')
+    ap.add_argument('--lanes', type=int, default=0, help='compute lanes (CUDA streams with their own workspaces) the job alternates its steps between; 1 = one stream; 0 = the package default (3 with 32 hardware stream queues, else 2)')
     ap.add_argument('--workload', default='pipeline', choices=['pipeline', 'triangulation', 'train_batch', 'train_step'],
                     help="'triangulation' = BASELINE.json configs[3]: batched pairwise DLT only (not the headline line)")
     ap.add_argument('--chunks', type=int, default=1, help='sub-batches of the end-to-end call (copy/compute overlap)')
@@ -263,10 +267,10 @@ def main():
     if args.total_frames > 0:
         config_desc['job'] = '%d frames in total: %d steps of %d frames on each of %d GPUs (512 distinct frames per GPU, cycled)' % (
             args.steps * world * args.frames, args.steps, args.frames, world)
-    if args.lanes > 1:
+    if args.lanes != 1:
         config_desc['l2'] = ('job of K steps on %d compute lanes (consecutive steps alternate between CUDA streams with their own workspaces, '
                              'shared weights); no flush between steps: a step\'s working set (1.3 GB of activations at 1024 frames) is ten times '
-                             'the 126 MB L2. one_lane = the same steps on one stream with a 256 MiB L2 flush between them' % args.lanes)
+                             'the 126 MB L2. one_lane = the same steps on one stream with a 256 MiB L2 flush between them' % (args.lanes if args.lanes > 0 else pkg.DEFAULT_LANES))
     kind = reference_kind() if args.cpu_kind == 'auto' else args.cpu_kind
     kind_note = {'reference': 'the unmodified reference (baseline/_ref) under the dgl / pytransform3d import shims, its own driver call sequence '
                               '(test/metrics_from_model.py:178-300), one single-threaded process per host core',
@@ -324,7 +328,7 @@ def main():
     # asynchronously; nothing on the compute stream waits for it until the end of the job ("final gather")
     gather = sharding.ResultGather(world, args.frames, P_cap, cfg.n_cameras, n_out, dev, depth=4) if world > 1 else None
 
-    n_lanes = max(1, args.lanes)
+    n_lanes = args.lanes if args.lanes > 0 else importlib.import_module('3d_multi_pose_estimator_b200').DEFAULT_LANES
     lanes, lane_streams = pipe.lanes(n_lanes)
     main_stream = torch.cuda.current_stream(dev)
     lane_streams = [main_stream if st is None else st for st in lane_streams]
@@ -543,7 +547,7 @@ def main():
                 'warmup': warmup, 'ms_per_step': ms_max, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 split (fp32-accurate), fp32 accumulate; fp64 geometry', 'data': 'synthetic',
                 'config': config_desc,
-                'lanes': n_lanes,
+                'lanes': n_lanes, 'cuda_device_max_connections': os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'),
                 'one_lane': {'value': total_frames / one_lane_max * 1e3, 'unit': UNIT, 'ms_per_step': one_lane_max,
                              'how': 'the same K steps one after the other on one stream, one CUDA-event pair per step, L2 flushed (256 MiB '
                                     'write) between them: the figure the per-kernel table below adds up to'},
