@@ -80,3 +80,20 @@ def test_packer_matches_oracle_graph_sizes(config):
     assert t.n_frames == 3 * pb.n_frames and t.n_nodes == 3 * pb.n_nodes
     s = t.slice(pb.n_frames, 2 * pb.n_frames)
     assert np.array_equal(s.head_off, pb.head_off) and np.array_equal(s.sk_xy, pb.sk_xy)
+
+
+def test_package_import_widens_the_stream_queues():
+    """Importing the package before any CUDA context exists sets CUDA_DEVICE_MAX_CONNECTIONS=32 (the streamed path runs on more
+    streams than the default 8 hardware queues) and then defaults to three compute lanes; a value the user chose is kept, and
+    with fewer than 16 queues the default falls back to two lanes."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import importlib, os; p = importlib.import_module('3d_multi_pose_estimator_b200'); "
+            "print(os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'), p.lanes_ok, p.DEFAULT_LANES)")
+    for preset, want in ((None, '32 True 3'), ('8', '8 False 2'), ('64', '64 True 3')):
+        env = {k: v for k, v in os.environ.items() if k != 'CUDA_DEVICE_MAX_CONNECTIONS'}
+        if preset is not None:
+            env['CUDA_DEVICE_MAX_CONNECTIONS'] = preset
+        out = subprocess.run([sys.executable, '-c', code], cwd=repo, env=env, stdout=subprocess.PIPE, check=True).stdout.decode().strip()
+        assert out.splitlines()[-1] == want, (preset, out)
