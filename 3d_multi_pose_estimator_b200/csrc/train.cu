@@ -197,18 +197,18 @@ __global__ void __launch_bounds__(256) transpose_planes_kernel(const __nv_bfloat
 }
 
 // out[j] = sum_r x[r, j] * (w ? w[r * ld_w + j / group] : 1): bias gradients (w = null) and the attention-vector gradients
-// d attn[h, d] = sum_u d a[u, h] ft2[u, h, d] (group = dim). One CTA per 32 columns, 8 warps striding the rows, partial sums
+// d attn[h, d] = sum_u d a[u, h] ft2[u, h, d] (group = dim). One CTA per 32 columns, 32 warps striding the rows, partial sums
 // merged in warp order.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int R, int C, int ld,
-                                                    const float* __restrict__ w, int ld_w, int group, float* __restrict__ out)
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ x, int R, int C, int ld,
+                                                     const float* __restrict__ w, int ld_w, int group, float* __restrict__ out)
 {
-    __shared__ float part[8][32];
+    __shared__ float part[32][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
     float s = 0.f;
     if (j < C) {
         const int gcol = w ? j / group : 0;
-        for (int r = ty; r < R; r += 8) {
+        for (int r = ty; r < R; r += 32) {
             const float v = x[(size_t)r * ld + j];
             s = w ? fmaf(v, w[(size_t)r * ld_w + gcol], s) : s + v;
         }
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
     if (ty == 0 && j < C) {
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += part[i][tx];
+        for (int i = 0; i < 32; ++i) t += part[i][tx];
         out[j] = t;
     }
 }
@@ -249,8 +249,20 @@ __global__ void __launch_bounds__(256) fold_attention_kernel(const float* __rest
 }
 
 // Every operand plane of one layer from its fp32 parameters, in one launch (after each optimiser step): W1 -> planes and
-// transposed planes; [W2 ; attention folds] -> planes (+ the folded bias); W2 -> transposed planes. Thread (r, c) of two index
-// spaces; paddings are written as zeros so the planes can be consumed as K padding.
+// transposed planes; [W2 ; attention folds] -> planes (+ the folded bias); W2 -> transposed planes. One CTA per 32x32 tile of
+// two stacked index spaces (rows_a rows of W1, then rows_b rows of [W2 ; folds]); the transposed planes go through a
+// shared-memory tile so that both layouts are written with coalesced stores. Paddings are written as zeros so the planes can
+// be consumed as K padding.
+__device__ __forceinline__ float fold_row_value(const float* __restrict__ W2, int ld_w, const float* __restrict__ attn_l,
+                                                const float* __restrict__ attn_r, int H, int D, int HD, int r, int c)
+{
+    const int h = (r - HD) % H;
+    const float* a = (r - HD) < H ? attn_l : attn_r;
+    double v = 0.0;
+    for (int d = 0; d < D; ++d) v += (double)a[h * D + d] * (double)W2[(size_t)(h * D + d) * ld_w + c];
+    return (float)v;
+}
+
 __global__ void __launch_bounds__(256) prepare_layer_kernel(const float* __restrict__ W1, const float* __restrict__ W2, int ld_w,
                                                            const float* __restrict__ b2, const float* __restrict__ attn_l,
                                                            const float* __restrict__ attn_r, int H, int D, int din,
@@ -258,38 +270,28 @@ __global__ void __launch_bounds__(256) prepare_layer_kernel(const float* __restr
                                                            __nv_bfloat16* __restrict__ w1t_hi, __nv_bfloat16* __restrict__ w1t_lo, int ld_w1t,
                                                            __nv_bfloat16* __restrict__ w2_hi, __nv_bfloat16* __restrict__ w2_lo, int ld_w2,
                                                            __nv_bfloat16* __restrict__ w2t_hi, __nv_bfloat16* __restrict__ w2t_lo, int ld_w2t,
-                                                           float* __restrict__ b2e, int rows_a, int rows_b)
+                                                           float* __restrict__ b2e, int tiles_a)
 {
+    __shared__ float tile[32][33];
     const int HD = H * D, n2 = HD + 2 * H;
-    const int cols = ld_w1 > ld_w2 ? ld_w1 : ld_w2;          // both are round_up(din, 64)
-    const long long total_a = (long long)rows_a * cols, total = total_a + (long long)rows_b * cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        __nv_bfloat16 hi, lo;
-        if (i < total_a) {                                     // ---- W1: rows_a = max(din, its transposed planes' K padding)
-            const int r = (int)(i / cols), c = (int)(i % cols);
-            const float x = (r < din && c < din) ? W1[(size_t)r * ld_w + c] : 0.f;
-            split_bf16(x, hi, lo);
-            if (r < din && c < ld_w1) { w1_hi[(size_t)r * ld_w1 + c] = hi; w1_lo[(size_t)r * ld_w1 + c] = lo; }
-            if (c < din && r < ld_w1t) { w1t_hi[(size_t)c * ld_w1t + r] = hi; w1t_lo[(size_t)c * ld_w1t + r] = lo; }
-        } else {                                               // ---- W2 and its folds: rows_b = max(n2, K padding of W2^T)
-            const long long k = i - total_a;
-            const int r = (int)(k / cols), c = (int)(k % cols);
-            float x = 0.f;                                     // row r of [W2 ; folds]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const bool part_a = (int)blockIdx.y < tiles_a;
+    const int r0 = (part_a ? (int)blockIdx.y : (int)blockIdx.y - tiles_a) * 32;
+    __nv_bfloat16 hi, lo;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        float x = 0.f;
+        if (part_a) {                                          // ---- W1 [din, din]
+            if (r < din && c < din) x = W1[(size_t)r * ld_w + c];
+            if (r < din && c < ld_w1) { split_bf16(x, hi, lo); w1_hi[(size_t)r * ld_w1 + c] = hi; w1_lo[(size_t)r * ld_w1 + c] = lo; }
+        } else {                                               // ---- [W2 ; folds] [n2, din]
+            float xe = 0.f;                                    // row r of [W2 ; folds]; x = the same restricted to the W2 rows (for W2^T)
             if (c < din) {
-                if (r < HD) x = W2[(size_t)r * ld_w + c];
-                else if (r < n2) {
-                    const int h = (r - HD) % H;
-                    const float* a = (r - HD) < H ? attn_l : attn_r;
-                    double v = 0.0;
-                    for (int d = 0; d < D; ++d) v += (double)a[h * D + d] * (double)W2[(size_t)(h * D + d) * ld_w + c];
-                    x = (float)v;
-                }
+                if (r < HD) xe = x = W2[(size_t)r * ld_w + c];
+                else if (r < n2) xe = fold_row_value(W2, ld_w, attn_l, attn_r, H, D, HD, r, c);
             }
-            if (r < n2 && c < ld_w2) { split_bf16(x, hi, lo); w2_hi[(size_t)r * ld_w2 + c] = hi; w2_lo[(size_t)r * ld_w2 + c] = lo; }
-            if (c < din && r < ld_w2t) {                       // W2^T [din, ld_w2t]: only the W2 rows, zeros in the K padding
-                split_bf16(r < HD ? x : 0.f, hi, lo);
-                w2t_hi[(size_t)c * ld_w2t + r] = hi; w2t_lo[(size_t)c * ld_w2t + r] = lo;
-            }
+            if (r < n2 && c < ld_w2) { split_bf16(xe, hi, lo); w2_hi[(size_t)r * ld_w2 + c] = hi; w2_lo[(size_t)r * ld_w2 + c] = lo; }
             if (c == 0 && r < n2) {
                 if (r < HD) b2e[r] = b2[r];
                 else {
@@ -301,22 +303,34 @@ __global__ void __launch_bounds__(256) prepare_layer_kernel(const float* __restr
                 }
             }
         }
+        tile[i][tx] = x;
+    }
+    __syncthreads();
+    __nv_bfloat16* t_hi = part_a ? w1t_hi : w2t_hi;
+    __nv_bfloat16* t_lo = part_a ? w1t_lo : w2t_lo;
+    const int ld_t = part_a ? ld_w1t : ld_w2t;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;                     // transposed: row c of the output, column r
+        if (c < din && r < ld_t) {
+            split_bf16(tile[tx][i], hi, lo);
+            t_hi[(size_t)c * ld_t + r] = hi; t_lo[(size_t)c * ld_t + r] = lo;
+        }
     }
 }
 
 // The three column sums behind the aggregation backward in one pass over z and dz: d attn_l[h,d] = sum_u d a1[u,h] ft2[u,h,d],
 // d attn_r likewise with d a2, d b2[j] = sum_u d ft2[u,j]. Same summation order as colsum_kernel.
-__global__ void __launch_bounds__(256) attn_bias_grad_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ dz, int ld_dz,
+__global__ void __launch_bounds__(1024) attn_bias_grad_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ dz, int ld_dz,
                                                             int R, int H, int D, float* __restrict__ g_attn_l, float* __restrict__ g_attn_r,
                                                             float* __restrict__ g_b2)
 {
-    __shared__ float part[3][8][32];
+    __shared__ float part[3][32][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int HD = H * D, j = blockIdx.x * 32 + tx;
     float sl = 0.f, sr = 0.f, sb = 0.f;
     if (j < HD) {
         const int h = j / D;
-        for (int r = ty; r < R; r += 8) {
+        for (int r = ty; r < R; r += 32) {
             const float f = z[(size_t)r * ldz + j];
             const float* d = dz + (size_t)r * ld_dz;
             sl = fmaf(f, d[HD + h], sl);
@@ -329,7 +343,7 @@ __global__ void __launch_bounds__(256) attn_bias_grad_kernel(const float* __rest
     if (ty < 3 && j < HD) {
         float t = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += part[ty][i][tx];
+        for (int i = 0; i < 32; ++i) t += part[ty][i][tx];
         (ty == 0 ? g_attn_l : ty == 1 ? g_attn_r : g_b2)[j] = t;
     }
 }
@@ -480,7 +494,7 @@ B2_EXPORT int b200pose_colsum(const float* x, int32_t rows, int32_t cols, int32_
 {
     B2_CHECK_ARG(x && out && rows >= 0 && cols >= 1 && ld >= cols, "colsum: bad argument");
     if (w) B2_CHECK_ARG(group >= 1 && ld_w >= ceil_div(cols, group), "colsum: bad weight layout");
-    colsum_kernel<<<ceil_div(cols, 32), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, w, ld_w, group, out);
+    colsum_kernel<<<ceil_div(cols, 32), 1024, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, w, ld_w, group, out);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }
@@ -553,16 +567,15 @@ B2_EXPORT int b200pose_gat_prepare_layer(const float* w1, const float* w2, int32
     B2_CHECK_ARG(heads >= 1 && dim >= 1 && din >= 1 && ld_w >= din, "gat_prepare_layer: bad shape");
     B2_CHECK_ARG(ld_w1 == kp && ld_w2 == kp && ld_w1t >= kp && ld_w2t >= hp, "gat_prepare_layer: plane leading dimensions must be round_up(din, 64) "
                  "(W1, [W2; folds]), >= round_up(din, 64) (W1^T) and >= round_up(heads*dim, 64) (W2^T)");
-    const int rows_a = kp;                                    // din rows of W1 + the K padding of W1^T
-    const int rows_b = n2 > hp ? n2 : hp;
-    const long long total = (long long)(rows_a + rows_b) * kp;
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    prepare_layer_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w1, w2, ld_w, b2, attn_l, attn_r, heads, dim, din,
+    const int rows_a = ld_w1t > kp ? ld_w1t : kp;             // din rows of W1 + the K padding of W1^T
+    const int rows_b = (n2 > ld_w2t ? n2 : ld_w2t);           // rows of [W2 ; folds], and the K padding of W2^T
+    const int tiles_a = ceil_div(rows_a, 32), tiles_b = ceil_div(rows_b, 32);
+    (void)hp;
+    prepare_layer_kernel<<<dim3(kp / 32, tiles_a + tiles_b), 256, 0, (cudaStream_t)stream>>>(w1, w2, ld_w, b2, attn_l, attn_r, heads, dim, din,
         reinterpret_cast<__nv_bfloat16*>(w1_hi), reinterpret_cast<__nv_bfloat16*>(w1_lo), ld_w1,
         reinterpret_cast<__nv_bfloat16*>(w1t_hi), reinterpret_cast<__nv_bfloat16*>(w1t_lo), ld_w1t,
         reinterpret_cast<__nv_bfloat16*>(w2_hi), reinterpret_cast<__nv_bfloat16*>(w2_lo), ld_w2,
-        reinterpret_cast<__nv_bfloat16*>(w2t_hi), reinterpret_cast<__nv_bfloat16*>(w2t_lo), ld_w2t, b2e, rows_a, rows_b);
+        reinterpret_cast<__nv_bfloat16*>(w2t_hi), reinterpret_cast<__nv_bfloat16*>(w2t_lo), ld_w2t, b2e, tiles_a);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }
@@ -572,7 +585,7 @@ B2_EXPORT int b200pose_gat_attn_bias_grad(const float* z, int32_t ldz, const flo
 {
     B2_CHECK_ARG(z && dz && g_attn_l && g_attn_r && g_b2 && rows >= 0 && heads >= 1 && dim >= 1, "gat_attn_bias_grad: bad argument");
     B2_CHECK_ARG(ldz >= heads * dim && ld_dz >= heads * dim + 2 * heads, "gat_attn_bias_grad: leading dimension too small");
-    attn_bias_grad_kernel<<<ceil_div(heads * dim, 32), 256, 0, (cudaStream_t)stream>>>(z, ldz, dz, ld_dz, rows, heads, dim, g_attn_l, g_attn_r, g_b2);
+    attn_bias_grad_kernel<<<ceil_div(heads * dim, 32), 1024, 0, (cudaStream_t)stream>>>(z, ldz, dz, ld_dz, rows, heads, dim, g_attn_l, g_attn_r, g_b2);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

@@ -180,8 +180,7 @@ class GatGrad:
                            alpha=self.alpha, act_slope=self.act_slope)
             cache.append(dict(x=x, h2=h2, z=z))
             x = act
-        self.cache = dict(layers=cache, N=N, g=g, scores=scores)
-        self.launches += 3 * len(self.layers)
+        self.cache = dict(layers=cache, N=N, g=g, scores=scores)        # (the forward's launches are counted by the pipeline)
         return scores[:N, 0]
 
     # ------------------------------------------------------------------ backward
