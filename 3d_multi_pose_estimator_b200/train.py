@@ -63,6 +63,41 @@ class _Buf:
         return view
 
 
+def param_layout(shapes: Dict[str, tuple]):
+    """Flat fp32 layout of the GAT's parameters from the shapes of a reference state dict (gat2.py:25-48 key names).
+    Returns (layers, slots, n_floats): per layer its sizes (din, heads, dim, hd, n2 = hd + 2 heads, ldz), and per key
+    (offset, rows, cols, ld) with ld = cols rounded up to 4 floats - every row, and so every slot, starts 16-byte aligned, which
+    is what lets the dW GEMMs store straight into the gradient buffer (TMA store pitch) and Adam run over one flat range (padding
+    elements have zero gradients and stay zero)."""
+    n_layers = len([k for k in shapes if k.endswith('fc1.weight')])
+    layers, slots, off = [], {}, 0
+
+    def slot(key, rows, cols):
+        nonlocal off
+        ld = _ld4(cols)
+        slots[key] = (off, rows, cols, ld)
+        off += rows * ld
+
+    for l in range(n_layers):
+        pre = 'layers.%d.' % l
+        if (pre + 'fc1.bias') not in shapes:
+            raise NotImplementedError('GatGrad: the training configuration has biases (train_skeleton_matching.py:148: bias=True)')
+        if (pre + 'res_fc.weight') in shapes:
+            raise NotImplementedError('GatGrad: residual layers are not differentiated (train_skeleton_matching.py:49: residual = False)')
+        H, D = shapes[pre + 'attn_l'][:2]
+        din = shapes[pre + 'fc1.weight'][1]
+        if shapes[pre + 'fc1.weight'] != (din, din) or shapes[pre + 'fc2.weight'] != (H * D, din):
+            raise ValueError('GatGrad: layer %d has shapes fc1 %s, fc2 %s for %d heads x %d' % (l, shapes[pre + 'fc1.weight'], shapes[pre + 'fc2.weight'], H, D))
+        layers.append(dict(din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4)))
+        slot(pre + 'attn_l', 1, H * D)
+        slot(pre + 'attn_r', 1, H * D)
+        slot(pre + 'fc1.weight', din, din)
+        slot(pre + 'fc1.bias', 1, din)
+        slot(pre + 'fc2.weight', H * D, din)
+        slot(pre + 'fc2.bias', 1, H * D)
+    return layers, slots, off
+
+
 class GatGrad:
     """Forward with saved activations + backward of the skeleton-matching GAT (no residual, no dropout: the shipped training
     configuration, train_skeleton_matching.py:46-49)."""
@@ -73,34 +108,7 @@ class GatGrad:
         self.L = pipe.L
         self.device = pipe.device
         self.alpha, self.act_slope = float(alpha), float(act_slope)
-        n_layers = len([k for k in state if k.endswith('fc1.weight')])
-        self.layers = []
-        off = 0
-        self.slots = {}                                   # key -> (offset, rows, cols, ld)
-
-        def slot(key, rows, cols):
-            nonlocal off
-            ld = _ld4(cols)
-            self.slots[key] = (off, rows, cols, ld)
-            off += rows * ld
-
-        for l in range(n_layers):
-            W1, W2 = state['layers.%d.fc1.weight' % l], state['layers.%d.fc2.weight' % l]
-            if ('layers.%d.fc1.bias' % l) not in state:
-                raise NotImplementedError('GatGrad: the training configuration has biases (train_skeleton_matching.py:148: bias=True)')
-            if ('layers.%d.res_fc.weight' % l) in state:
-                raise NotImplementedError('GatGrad: residual layers are not differentiated (train_skeleton_matching.py:49: residual = False)')
-            H, D = state['layers.%d.attn_l' % l].shape[:2]
-            din = W1.shape[1]
-            assert W1.shape[0] == din and W2.shape == (H * D, din)
-            self.layers.append(dict(din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4)))
-            pre = 'layers.%d.' % l
-            slot(pre + 'attn_l', 1, H * D)
-            slot(pre + 'attn_r', 1, H * D)
-            slot(pre + 'fc1.weight', din, din)
-            slot(pre + 'fc1.bias', 1, din)
-            slot(pre + 'fc2.weight', H * D, din)
-            slot(pre + 'fc2.bias', 1, H * D)
+        self.layers, self.slots, off = param_layout({k: tuple(v.shape) for k, v in state.items()})
         self.n_flat = off
         with torch.cuda.device(self.device):
             self.theta = torch.zeros(off, dtype=torch.float32, device=self.device)
