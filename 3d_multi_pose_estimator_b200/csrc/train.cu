@@ -348,6 +348,20 @@ __global__ void __launch_bounds__(1024) attn_bias_grad_kernel(const float* __res
     }
 }
 
+// Residual connections in the backward (gat2.py:70-75: ret = resval + ret): dx[r, c] += sum_h src[r, h * cols + c]. heads = 1 adds
+// the gradient that came back through res_fc; heads = H folds the identity branch, where the layer input was broadcast over the
+// attention heads (resval = h.unsqueeze(1)), i.e. sums the output gradient over them.
+__global__ void __launch_bounds__(256) residual_bwd_add_kernel(float* __restrict__ dx, int ld_dx, const float* __restrict__ src, int ld_src,
+                                                              int rows, int cols, int heads)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float s = 0.f;
+    for (int h = 0; h < heads; ++h) s += src[(size_t)r * ld_src + h * cols + c];
+    dx[(size_t)r * ld_dx + c] += s;
+}
+
 // nn.MSELoss over the edge-node scores (train_skeleton_matching.py:37, 174-178) and its gradient through the final sigmoid
 // (gat2.py:145): dlogit[idx[i]] = 2/M (s - y) s (1 - s). dlogit must be zeroed by the caller; idx entries are distinct
 // (edge-node ids). One CTA; the loss is summed in fp64 in a fixed order.
@@ -586,6 +600,17 @@ B2_EXPORT int b200pose_gat_attn_bias_grad(const float* z, int32_t ldz, const flo
     B2_CHECK_ARG(z && dz && g_attn_l && g_attn_r && g_b2 && rows >= 0 && heads >= 1 && dim >= 1, "gat_attn_bias_grad: bad argument");
     B2_CHECK_ARG(ldz >= heads * dim && ld_dz >= heads * dim + 2 * heads, "gat_attn_bias_grad: leading dimension too small");
     attn_bias_grad_kernel<<<ceil_div(heads * dim, 32), 1024, 0, (cudaStream_t)stream>>>(z, ldz, dz, ld_dz, rows, heads, dim, g_attn_l, g_attn_r, g_b2);
+    B2_CHECK_LAUNCH();
+    return B200POSE_OK;
+}
+
+B2_EXPORT int b200pose_residual_bwd_add(float* dx, int32_t ld_dx, const float* src, int32_t ld_src, int32_t rows, int32_t cols, int32_t heads,
+                                        void* stream)
+{
+    B2_CHECK_ARG(dx && src && rows >= 0 && cols >= 1 && heads >= 1 && ld_dx >= cols && ld_src >= heads * cols, "residual_bwd_add: bad argument");
+    if (rows == 0) return B200POSE_OK;
+    const long long total = (long long)rows * cols;
+    residual_bwd_add_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dx, ld_dx, src, ld_src, rows, cols, heads);
     B2_CHECK_LAUNCH();
     return B200POSE_OK;
 }

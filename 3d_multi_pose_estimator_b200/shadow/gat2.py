@@ -124,8 +124,6 @@ class GAT2(nn.Module):
 
     def _forward_train(self, inputs, g, ctx):
         """Grad mode with trainable parameters (the loop of train_skeleton_matching.py:163-184)."""
-        if any(lyr.residual for lyr in self.layers):
-            raise NotImplementedError('B200 GAT2: residual layers are inference-only')
         if inputs.requires_grad:
             raise NotImplementedError('B200 GAT2: gradients with respect to the input features are not computed (the reference trains the '
                                       'parameters only, train_skeleton_matching.py:150)')
@@ -135,7 +133,8 @@ class GAT2(nn.Module):
         rt.sync_live()
         if net is None:
             train_mod = rt.importlib.import_module('3d_multi_pose_estimator_b200.train')
-            net = train_mod.GatGrad(ctx, {k: v for k, v in self.state_dict().items()}, self.alpha, self.activation.negative_slope)
+            net = train_mod.GatGrad(ctx, {k: v for k, v in self.state_dict().items()}, self.alpha, self.activation.negative_slope,
+                                    residual=any(lyr.residual for lyr in self.layers))
             self.__dict__['_grad_net'] = net
         elif key != self.__dict__.get('_grad_key'):
             net.load_state({k: v for k, v in self.state_dict().items()})       # optimizer.step() changed them

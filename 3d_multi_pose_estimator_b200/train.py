@@ -63,12 +63,13 @@ class _Buf:
         return view
 
 
-def param_layout(shapes: Dict[str, tuple]):
+def param_layout(shapes: Dict[str, tuple], residual: bool = False):
     """Flat fp32 layout of the GAT's parameters from the shapes of a reference state dict (gat2.py:25-48 key names).
     Returns (layers, slots, n_floats): per layer its sizes (din, heads, dim, hd, n2 = hd + 2 heads, ldz), and per key
     (offset, rows, cols, ld) with ld = cols rounded up to 4 floats - every row, and so every slot, starts 16-byte aligned, which
     is what lets the dW GEMMs store straight into the gradient buffer (TMA store pitch) and Adam run over one flat range (padding
-    elements have zero gradients and stay zero)."""
+    elements have zero gradients and stay zero). residual: GAT2 built with residual=True - every layer after the first either
+    has `res_fc.*` entries (in_dim != out_dim) or, without them, adds its input broadcast over the heads (gat2.py:43-48)."""
     n_layers = len([k for k in shapes if k.endswith('fc1.weight')])
     layers, slots, off = [], {}, 0
 
@@ -82,33 +83,47 @@ def param_layout(shapes: Dict[str, tuple]):
         pre = 'layers.%d.' % l
         if (pre + 'fc1.bias') not in shapes:
             raise NotImplementedError('GatGrad: the training configuration has biases (train_skeleton_matching.py:148: bias=True)')
-        if (pre + 'res_fc.weight') in shapes:
-            raise NotImplementedError('GatGrad: residual layers are not differentiated (train_skeleton_matching.py:49: residual = False)')
+        has_res_fc = (pre + 'res_fc.weight') in shapes
+        if has_res_fc and not (residual and l > 0):
+            raise ValueError('GatGrad: layer %d has res_fc weights but the model is not declared residual (or it is the first layer)' % l)
         H, D = shapes[pre + 'attn_l'][:2]
         din = shapes[pre + 'fc1.weight'][1]
         if shapes[pre + 'fc1.weight'] != (din, din) or shapes[pre + 'fc2.weight'] != (H * D, din):
             raise ValueError('GatGrad: layer %d has shapes fc1 %s, fc2 %s for %d heads x %d' % (l, shapes[pre + 'fc1.weight'], shapes[pre + 'fc2.weight'], H, D))
-        layers.append(dict(din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4)))
+        res = None
+        if residual and l > 0:
+            if has_res_fc:
+                if shapes[pre + 'res_fc.weight'] != (H * D, din) or (pre + 'res_fc.bias') not in shapes:
+                    raise ValueError('GatGrad: layer %d res_fc has shape %s for %d heads x %d (bias required)' % (l, shapes[pre + 'res_fc.weight'], H, D))
+                res = 'fc'
+            elif din == D:
+                res = 'identity'
+            else:
+                raise ValueError('GatGrad: residual layer %d has in_dim %d != out_dim %d but no res_fc weights' % (l, din, D))
+        layers.append(dict(din=din, heads=H, dim=D, hd=H * D, n2=H * D + 2 * H, ldz=round_up(H * D + 2 * H, 4), res=res))
         slot(pre + 'attn_l', 1, H * D)
         slot(pre + 'attn_r', 1, H * D)
         slot(pre + 'fc1.weight', din, din)
         slot(pre + 'fc1.bias', 1, din)
         slot(pre + 'fc2.weight', H * D, din)
         slot(pre + 'fc2.bias', 1, H * D)
+        if res == 'fc':
+            slot(pre + 'res_fc.weight', H * D, din)
+            slot(pre + 'res_fc.bias', 1, H * D)
     return layers, slots, off
 
 
 class GatGrad:
-    """Forward with saved activations + backward of the skeleton-matching GAT (no residual, no dropout: the shipped training
-    configuration, train_skeleton_matching.py:46-49)."""
+    """Forward with saved activations + backward of the skeleton-matching GAT (no dropout: train_skeleton_matching.py:46-48).
+    residual=True: the model was built with residual connections (gat2.py:43-48, 70-75; the shipped configuration has none)."""
 
     def __init__(self, pipe: PosePipeline, state: Dict[str, torch.Tensor], alpha: float = GAT_ALPHA,
-                 act_slope: float = GAT_ACT_SLOPE):
+                 act_slope: float = GAT_ACT_SLOPE, residual: bool = False):
         self.pipe = pipe
         self.L = pipe.L
         self.device = pipe.device
         self.alpha, self.act_slope = float(alpha), float(act_slope)
-        self.layers, self.slots, off = param_layout({k: tuple(v.shape) for k, v in state.items()})
+        self.layers, self.slots, off = param_layout({k: tuple(v.shape) for k, v in state.items()}, residual)
         self.n_flat = off
         with torch.cuda.device(self.device):
             self.theta = torch.zeros(off, dtype=torch.float32, device=self.device)
@@ -121,6 +136,9 @@ class GatGrad:
                 lay['b2e'] = torch.zeros(n2, dtype=torch.float32, device=self.device)
                 lay['w2'] = Planes(n2, din, self.device)
                 lay['w2t'] = Planes(din, hd, self.device)
+                if lay['res'] == 'fc':
+                    lay['res_w'] = Planes(hd, din, self.device)
+                    lay['res_wt'] = Planes(din, hd, self.device)
         self.cache = None
         self.launches = 0
         self.load_state(state)
@@ -167,6 +185,12 @@ class GatGrad:
                                                ptr(lay['w2'].hi), ptr(lay['w2'].lo), lay['w2'].ld, ptr(lay['w2t'].hi), ptr(lay['w2t'].lo), lay['w2t'].ld,
                                                ptr(lay['b2e']), s), 'gat_prepare_layer')
             self.launches += 1
+            if lay['res'] == 'fc':
+                Wr = self.view(self.theta, pre + 'res_fc.weight', padded=True)
+                check(L.b200pose_grad_planes(ptr(Wr), lay['hd'], lay['din'], Wr.stride(0), None, 0, 1.0, None, 0,
+                                             ptr(lay['res_w'].hi), ptr(lay['res_w'].lo), lay['res_w'].ld,
+                                             ptr(lay['res_wt'].hi), ptr(lay['res_wt'].lo), lay['res_wt'].ld, s), 'grad_planes')
+                self.launches += 1
 
     # ------------------------------------------------------------------ forward
     def forward(self, db, g, x0: Planes) -> torch.Tensor:
@@ -184,8 +208,14 @@ class GatGrad:
             pipe.linear(x, N, lay['w1'], self.view(self.theta, pre + 'fc1.bias'), lay['din'], lay['din'], self.alpha, out_planes=h2)
             pipe.linear(h2, N, lay['w2'], lay['b2e'], lay['n2'], lay['din'], 1.0, out_f32=z)
             act = None if last else self.buf.p('act_%d' % l, N, lay['hd'])
+            res = None
+            if lay['res'] == 'fc':                                   # gat2.py:72: res_fc(h)
+                res = self.buf.f('res_%d' % l, N, _ld4(lay['hd']))
+                pipe.linear(x, N, lay['res_w'], self.view(self.theta, pre + 'res_fc.bias'), lay['hd'], lay['din'], 1.0, out_f32=res)
+            elif lay['res'] == 'identity':                           # gat2.py:74: the input itself, broadcast over the heads
+                res = x.to_f32()[:N, : lay['din']].repeat(1, lay['heads']).contiguous()
             pipe.aggregate(db, g, z, lay, layer0=False, raw=None, act=act, scores=scores if last else None,
-                           alpha=self.alpha, act_slope=self.act_slope)
+                           alpha=self.alpha, act_slope=self.act_slope, res=res)
             cache.append(dict(x=x, h2=h2, z=z))
             x = act
         self.cache = dict(layers=cache, N=N, g=g, scores=scores)        # (the forward's launches are counted by the pipeline)
@@ -233,10 +263,27 @@ class GatGrad:
             xT = self.buf.p('xT_%d' % l, din, N)
             check(L.b200pose_transpose_planes(ptr(x.hi), ptr(x.lo), N, din, x.ld, ptr(xT.hi), ptr(xT.lo), xT.ld, s), 'transpose_planes')
             self._linear(G1T, din, xT, din, N, self.view(self.grad, pre + 'fc1.weight', padded=True))          # dW1 = G1^T x
+            dxr = None
+            if lay['res'] == 'fc':                                   # the same output gradient d also flows through res_fc(x)
+                check(L.b200pose_colsum(ptr(d), N, hd, ld_d, None, 0, 1, ptr(self.view(self.grad, pre + 'res_fc.bias')), s), 'colsum')
+                Gr = self.buf.p('Gr_%d' % l, N, hd)
+                GrT = self.buf.p('GrT_%d' % l, hd, N)
+                check(L.b200pose_grad_planes(ptr(d), N, hd, ld_d, None, 0, 1.0, None, 0, ptr(Gr.hi), ptr(Gr.lo), Gr.ld,
+                                             ptr(GrT.hi), ptr(GrT.lo), GrT.ld, s), 'grad_planes')
+                self._linear(GrT, hd, xT, din, N, self.view(self.grad, pre + 'res_fc.weight', padded=True))    # dWres = d^T x
+                dxr = self.buf.f('dxr_%d' % _ld4(din), N, _ld4(din))
+                self._linear(Gr, N, lay['res_wt'], din, hd, dxr)                                              # d Wres
+                self.launches += 2
             self.launches += 8          # kernels of the calls above other than the GEMMs (counted by _linear)
             if l > 0:
-                dx = self.buf.f('dx_%d' % _ld4(din), N, _ld4(din))
+                dx = self.buf.f('dx_l%d' % l, N, _ld4(din))              # per layer: layer l+1's dx is this layer's d, read until the end
                 self._linear(G1, N, lay['w1t'], din, din, dx)                                                   # dx = G1 W1
+                if lay['res'] == 'fc':
+                    check(L.b200pose_residual_bwd_add(ptr(dx), dx.stride(0), ptr(dxr), dxr.stride(0), N, din, 1, s), 'residual_bwd_add')
+                    self.launches += 1
+                elif lay['res'] == 'identity':
+                    check(L.b200pose_residual_bwd_add(ptr(dx), dx.stride(0), ptr(d), ld_d, N, din, H, s), 'residual_bwd_add')
+                    self.launches += 1
                 # through the inter-layer LeakyReLU (GAT2.forward :141-142): x is the activated output of layer l-1
                 check(L.b200pose_grad_planes(ptr(dx), N, din, dx.stride(0), ptr(x.hi), x.ld, self.act_slope, ptr(dx), dx.stride(0),
                                              None, None, 0, None, None, 0, s), 'grad_planes')
@@ -252,9 +299,10 @@ class GatTrainer:
     into the capture's static buffers, the Adam step count lives on the device."""
 
     def __init__(self, pipe: PosePipeline, state: Dict[str, torch.Tensor], lr: float = 1e-4, betas: Sequence[float] = (0.9, 0.999),
-                 eps: float = 1e-8, weight_decay: float = 1e-20, alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE):
+                 eps: float = 1e-8, weight_decay: float = 1e-20, alpha: float = GAT_ALPHA, act_slope: float = GAT_ACT_SLOPE,
+                 residual: bool = False):
         self.pipe = pipe
-        self.net = GatGrad(pipe, state, alpha, act_slope)
+        self.net = GatGrad(pipe, state, alpha, act_slope, residual)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         dev = pipe.device
         self.m = torch.zeros(self.net.n_flat, dtype=torch.float32, device=dev)

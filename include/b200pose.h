@@ -320,6 +320,11 @@ int b200pose_gat_prepare_layer(const float* w1, const float* w2, int32_t ld_w, c
                                float* b2e, void* stream);
 int b200pose_gat_attn_bias_grad(const float* z, int32_t ldz, const float* dz, int32_t ld_dz, int32_t rows, int32_t heads, int32_t dim,
                                 float* g_attn_l, float* g_attn_r, float* g_b2, void* stream);
+/* Backward of a residual connection (gat2.py:70-75): dx[r, c] += sum_{h < heads} src[r, h * cols + c]. heads = 1: src = the gradient
+ * that came back through res_fc (computed with b200pose_linear); heads = H: the identity branch (resval = h.unsqueeze(1),
+ * broadcast over the attention heads), src = the layer's output gradient. */
+int b200pose_residual_bwd_add(float* dx, int32_t ld_dx, const float* src, int32_t ld_src, int32_t rows, int32_t cols, int32_t heads,
+                              void* stream);
 /* nn.MSELoss on scores[idx[i]] vs labels[i] (train_skeleton_matching.py:37, 174-178) and its gradient through the final
  * sigmoid: dlogit [n_nodes] (zero outside idx; idx entries distinct). loss / dlogit may be null. */
 int b200pose_mse_sigmoid(const float* scores, int32_t n_nodes, const int32_t* idx, const float* labels, int32_t m,

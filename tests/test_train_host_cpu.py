@@ -35,8 +35,15 @@ def test_param_layout_refusals():
     with pytest.raises(NotImplementedError):
         train_mod.param_layout(no_bias)
     residual = {k: tuple(v.shape) for k, v in helpers.weights_mod.make_gat_state(902, 0, True, residual=True).items()}
-    with pytest.raises(NotImplementedError):
-        train_mod.param_layout(residual)
+    with pytest.raises(ValueError):
+        train_mod.param_layout(residual)                                   # res_fc weights in a model not declared residual
+    layers, slots, n = train_mod.param_layout(residual, residual=True)
+    assert [l['res'] for l in layers] == [None, 'fc', 'fc', 'fc', 'fc'] and sorted(slots) == sorted(residual)
+    ident = {k: tuple(v.shape) for k, v in helpers.weights_mod.make_gat_state(902, 0, True, [40, 40], [1, 4], residual=True).items()}
+    layers, slots, n = train_mod.param_layout(ident, residual=True)
+    assert [l['res'] for l in layers] == [None, 'identity', 'fc'] and sorted(slots) == sorted(ident)
+    with pytest.raises(ValueError):                                        # in_dim != out_dim and no res_fc weights
+        train_mod.param_layout({k: v for k, v in residual.items() if 'res_fc' not in k}, residual=True)
     bad = {k: tuple(v.shape) for k, v in helpers.weights_mod.make_gat_state(902, 0, True).items()}
     bad['layers.1.fc2.weight'] = (399, 400)
     with pytest.raises(ValueError):

@@ -59,14 +59,14 @@ def check_digest(name, got, gz, key, rtol, l2tol=None, atol=1e-9):
     return 0.0 if err <= atol else err / scale
 
 
-def check_parameters(state, gz, lr, steps, tight=2.5e-5, frac=0.05):
+def check_parameters(state, gz, lr, steps, tight=2.5e-5, frac=0.05, prefix='final/'):
     """Parameters after `steps` Adam steps. Adam's first updates are lr * g / (|g| + eps): an element whose gradient is below
     the noise floor of the arithmetic moves by up to lr per step in EITHER direction, so two correct implementations that differ
     in the last bits of the forward agree tightly on most elements and by at most 2 * lr * steps on the rest. Returns the fraction
     of sampled elements further than `tight` from the reference."""
     n_far, n_all, worst = 0, 0, 0.0
     for k, v in state.items():
-        d = np.abs(sample(np.asarray(v)) - gz['final/' + k + '/sample'])
+        d = np.abs(sample(np.asarray(v)) - gz[prefix + k + '/sample'])
         worst = max(worst, float(d.max()))
         n_far += int((d > tight).sum())
         n_all += d.size
@@ -94,3 +94,34 @@ def test_training_step_restatement_against_reference_autograd():
         err = np.abs(sample(v) - gz['final/' + k + '/sample']).max()
         assert err <= 2.5e-5, ('parameter after %d steps' % len(batches), k, err)       # lr = 1e-4: a quarter of one step
     print('worst gradient error relative to the tensor maximum:', worst)
+
+
+RESIDUAL_MODELS = {'resfc': ([40, 40, 40, 30], [10, 10, 8, 5], 17), 'ident': ([40, 40], [1, 4], 18)}     # make_golden_train_step_residual.py
+
+
+def residual_batch():
+    cfg, gz, batches = golden_batches()
+    rz = np.load(os.path.join(GOLDEN, 'golden_train_step_residual.npz'))
+    bg, idx, labels = batches[0]
+    assert np.array_equal(idx, rz['indices']) and np.array_equal(labels, rz['labels'])
+    return cfg, rz, bg, idx, labels
+
+
+def test_residual_training_step_restatement_against_reference_autograd():
+    """The same for GAT2(residual=True): res_fc layers and the identity branch (gat2.py:43-48, 70-75)."""
+    cfg, rz, bg, idx, labels = residual_batch()
+    for name, (hidden, heads, seed) in RESIDUAL_MODELS.items():
+        w = helpers.np_state(helpers.weights_mod.make_gat_state(cfg.n_features_sm, seed, True, hidden, heads, residual=True))
+        adam = TO.Adam(w)
+        for step in range(int(rz['steps'][0])):
+            pre = '%s/step%d/' % (name, step)
+            loss, scores, grads = TO.forward_backward(w, bg['feats'], bg['src'], bg['dst'], idx, labels, heads=tuple(heads) + (1,), residual=True)
+            ref_loss = float(rz[pre + 'loss'][0])
+            assert abs(loss - ref_loss) <= 1e-5 * ref_loss, (name, step, loss, ref_loss)
+            assert sorted(grads) == sorted(w)
+            for k, g in grads.items():
+                check_digest('grad %s %s step %d' % (name, k, step), g, rz, pre + 'grad/' + k, 2e-4, atol=1e-8)
+            adam.step(w, grads)
+        # (the last layer's attn_r has a gradient that cancels to ~1e-10: Adam's g / |g| moves it by lr per step in a direction the
+        # last bit decides - check_parameters bounds that by 2 lr steps and asks for tight agreement on all but a sliver)
+        check_parameters(w, rz, 1e-4, int(rz['steps'][0]), frac=0.001, prefix=name + '/final/')
